@@ -1,0 +1,271 @@
+"""ctypes binding of libb2e.so (the C ABI declared in include/b2e.h).
+
+There is deliberately no fallback: if the library is missing, or a compute call is made without an
+sm_100 device, a ``NativeError`` is raised.  Tensors cross the boundary as ``data_ptr()`` integers
+plus sizes; the current torch CUDA stream is passed explicitly.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / 'libb2e.so'
+
+ARCH_BERT, ARCH_ESM2, ARCH_MISTRAL = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+POOL_MEAN_REF, POOL_MEAN_PER_ROW, POOL_LAST_TOKEN = 0, 1, 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID = 0, 1, 2
+
+_DTYPE_CODES = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
+
+# every symbol include/b2e.h declares (checked by the CPU test-suite)
+EXPORTS = (
+    'b2e_version',
+    'b2e_last_error',
+    'b2e_num_weights',
+    'b2e_encoder_create',
+    'b2e_encoder_destroy',
+    'b2e_workspace_bytes',
+    'b2e_encode',
+    'b2e_encode_pooled',
+    'b2e_embed_host',
+    'b2e_pool_mean',
+    'b2e_pool_last_token',
+    'b2e_l2_normalize',
+    'b2e_adjacent_cosine_dist',
+    'b2e_gemm_bf16',
+    'b2e_attention_d64',
+    'b2e_layernorm',
+)
+
+
+class NativeError(RuntimeError):
+    """Raised when libb2e.so is missing or a native call fails."""
+
+
+class ModelDesc(C.Structure):
+    """Mirror of ``B2EModelDesc``."""
+
+    _fields_ = [
+        ('arch', C.c_int32),
+        ('num_layers', C.c_int32),
+        ('hidden', C.c_int32),
+        ('heads', C.c_int32),
+        ('kv_heads', C.c_int32),
+        ('head_dim', C.c_int32),
+        ('intermediate', C.c_int32),
+        ('vocab', C.c_int32),
+        ('max_pos', C.c_int32),
+        ('type_vocab', C.c_int32),
+        ('eps', C.c_float),
+        ('rope_theta', C.c_float),
+        ('sliding_window', C.c_int32),
+        ('reserved', C.c_int32),
+    ]
+
+
+_lib: C.CDLL | None = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.b2e_version.restype = i32
+    lib.b2e_version.argtypes = []
+    lib.b2e_last_error.restype = C.c_char_p
+    lib.b2e_last_error.argtypes = []
+    lib.b2e_num_weights.restype = i32
+    lib.b2e_num_weights.argtypes = [C.POINTER(ModelDesc)]
+    lib.b2e_encoder_create.restype = i32
+    lib.b2e_encoder_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp), i32, i32, C.POINTER(vp)]
+    lib.b2e_encoder_destroy.restype = None
+    lib.b2e_encoder_destroy.argtypes = [vp]
+    lib.b2e_workspace_bytes.restype = i64
+    lib.b2e_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.b2e_encode.restype = i32
+    lib.b2e_encode.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp]
+    lib.b2e_encode_pooled.restype = i32
+    lib.b2e_encode_pooled.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.b2e_embed_host.restype = i32
+    lib.b2e_embed_host.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.b2e_pool_mean.restype = i32
+    lib.b2e_pool_mean.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.b2e_pool_last_token.restype = i32
+    lib.b2e_pool_last_token.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.b2e_l2_normalize.restype = i32
+    lib.b2e_l2_normalize.argtypes = [vp, i64, i32, vp]
+    lib.b2e_adjacent_cosine_dist.restype = i32
+    lib.b2e_adjacent_cosine_dist.argtypes = [vp, i32, i64, i32, vp, vp, vp]
+    lib.b2e_gemm_bf16.restype = i32
+    lib.b2e_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b2e_attention_d64.restype = i32
+    lib.b2e_attention_d64.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.b2e_layernorm.restype = i32
+    lib.b2e_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
+
+
+def load() -> C.CDLL:
+    """Load libb2e.so (once).  Raises ``NativeError`` when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeError(
+            f'{LIB_PATH} not found: build it with `python -m distllm_b200.build` '
+            '(or __graft_entry__.build()). There is no CPU fallback.',
+        )
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as exc:  # pragma: no cover - depends on the box
+        raise NativeError(f'cannot load {LIB_PATH}: {exc}') from exc
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Turn a non-zero return code into a NativeError carrying b2e_last_error()."""
+    if rc != 0:
+        msg = load().b2e_last_error()
+        raise NativeError(f'libb2e error {rc}: {msg.decode() if msg else "?"}')
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODES[dtype]
+    except KeyError:
+        raise NativeError(f'unsupported dtype {dtype}') from None
+
+
+def stream_ptr(device: torch.device | None = None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _cuda_contig(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NativeError(f'{what} must be a CUDA tensor (libb2e has no CPU fallback)')
+    if not t.is_contiguous():
+        raise NativeError(f'{what} must be contiguous')
+    return t
+
+
+# --------------------------------------------------------------------------- thin op wrappers
+def gemm_bf16(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    bias: torch.Tensor,
+    resid: torch.Tensor | None = None,
+    epilogue: int = EPI_BIAS,
+) -> torch.Tensor:
+    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; bf16 in/out."""
+    lib = load()
+    _cuda_contig(a, 'a'), _cuda_contig(w, 'w'), _cuda_contig(bias, 'bias')
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.b2e_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid),
+                                out.data_ptr(), m, n, k, epilogue, stream_ptr(a.device)))
+    return out
+
+
+def attention_d64(
+    qkv: torch.Tensor,
+    attention_mask: torch.Tensor,
+    batch: int,
+    seq: int,
+    heads: int,
+    debug_scores: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """qkv [B*S, 3*heads*64] bf16 -> context [B*S, heads*64] bf16."""
+    lib = load()
+    _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
+    ctx = torch.zeros((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.b2e_attention_d64(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch,
+                                    seq, heads, _ptr(debug_scores), stream_ptr(qkv.device)))
+    return ctx
+
+
+def layernorm(
+    x: torch.Tensor,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    eps: float,
+    out_dtype: torch.dtype = torch.bfloat16,
+) -> torch.Tensor:
+    lib = load()
+    _cuda_contig(x, 'x')
+    rows, h = x.shape
+    out = torch.empty((rows, h), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.b2e_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
+                                h, eps, dtype_code(out_dtype), stream_ptr(x.device)))
+    return out
+
+
+def pool_mean(
+    hidden: torch.Tensor,
+    attention_mask: torch.Tensor,
+    pool_kind: int = POOL_MEAN_REF,
+    mutate_mask: bool = True,
+) -> torch.Tensor:
+    """Masked mean over the sequence axis; fp32 [B,H].  Rewrites the mask like the reference."""
+    lib = load()
+    _cuda_contig(hidden, 'hidden'), _cuda_contig(attention_mask, 'attention_mask')
+    if attention_mask.dtype != torch.int64:
+        raise NativeError('attention_mask must be int64')
+    b, s, h = hidden.shape
+    out = torch.empty((b, h), dtype=torch.float32, device=hidden.device)
+    with torch.cuda.device(hidden.device):
+        check(lib.b2e_pool_mean(hidden.data_ptr(), dtype_code(hidden.dtype), attention_mask.data_ptr(),
+                                b, s, h, pool_kind, int(mutate_mask), out.data_ptr(),
+                                stream_ptr(hidden.device)))
+    return out
+
+
+def pool_last_token(hidden: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    lib = load()
+    _cuda_contig(hidden, 'hidden'), _cuda_contig(attention_mask, 'attention_mask')
+    if attention_mask.dtype != torch.int64:
+        raise NativeError('attention_mask must be int64')
+    b, s, h = hidden.shape
+    out = torch.empty((b, h), dtype=torch.float32, device=hidden.device)
+    with torch.cuda.device(hidden.device):
+        check(lib.b2e_pool_last_token(hidden.data_ptr(), dtype_code(hidden.dtype),
+                                      attention_mask.data_ptr(), b, s, h, out.data_ptr(),
+                                      stream_ptr(hidden.device)))
+    return out
+
+
+def l2_normalize_(x: torch.Tensor) -> torch.Tensor:
+    lib = load()
+    _cuda_contig(x, 'x')
+    if x.dtype != torch.float32:
+        raise NativeError('l2_normalize_ expects fp32')
+    n, h = x.shape
+    with torch.cuda.device(x.device):
+        check(lib.b2e_l2_normalize(x.data_ptr(), n, h, stream_ptr(x.device)))
+    return x
+
+
+def adjacent_cosine_dist(emb: torch.Tensor, doc_id: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [N-1]: 1 - cos(emb[i], emb[i+1]); NaN where doc_id changes."""
+    lib = load()
+    _cuda_contig(emb, 'emb')
+    n, h = emb.shape
+    out = torch.empty((max(n - 1, 0),), dtype=torch.float32, device=emb.device)
+    if doc_id is not None:
+        _cuda_contig(doc_id, 'doc_id')
+        if doc_id.dtype != torch.int32:
+            raise NativeError('doc_id must be int32')
+    with torch.cuda.device(emb.device):
+        check(lib.b2e_adjacent_cosine_dist(emb.data_ptr(), dtype_code(emb.dtype), n, h,
+                                           _ptr(doc_id), out.data_ptr(), stream_ptr(emb.device)))
+    return out

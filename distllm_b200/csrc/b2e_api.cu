@@ -1,0 +1,733 @@
+// libb2e.so -- C ABI (include/b2e.h) over the sm_100a kernels.  Host runtime only: handle,
+// lazily grown workspace, TMA descriptors and launches.  No CPU fallback: without an sm_100 device
+// every compute entry point fails with B2E_ERR_NO_DEVICE.
+#include "../../include/b2e.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+using namespace b2e;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(B2E_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = 64 columns (128 B, swizzle-128B) x box_rows.
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled(rows=%llu, cols=%llu, box_rows=%u) -> %d",
+                (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r);
+  return B2E_OK;
+}
+
+struct DeviceInfo {
+  int sms = 0;
+  int cc_major = 0;
+  bool ok = false;
+};
+
+int device_info(int device, DeviceInfo* info) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(B2E_ERR_NO_DEVICE, "no CUDA device visible; libb2e has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(B2E_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp p;
+  CUDA_TRY(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(B2E_ERR_NO_DEVICE, "device %d is sm_%d%d; libb2e is built for sm_100a only", device,
+                p.major, p.minor);
+  info->sms = p.multiProcessorCount;
+  info->cc_major = p.major;
+  info->ok = true;
+  return B2E_OK;
+}
+
+int current_device_info(DeviceInfo* info) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B2E_ERR_NO_DEVICE, "no CUDA device visible; libb2e has no CPU fallback");
+  }
+  static DeviceInfo cache[64];
+  if (dev < 64 && cache[dev].ok) {
+    *info = cache[dev];
+    return B2E_OK;
+  }
+  int rc = device_info(dev, info);
+  if (rc == B2E_OK && dev < 64) cache[dev] = *info;
+  return rc;
+}
+
+// ---------------------------------------------------------------- launches
+template <int BN, int STAGES, int EPI>
+int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
+                    const bf16* resid, int M, int N, int K, int sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, out, bias, resid, M, N, K);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+template <int BN, int STAGES>
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
+                   const bf16* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
+  switch (epi) {
+    case B2E_EPI_BIAS:
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS>(ta, tb, out, bias, resid, M, N, K, sms, st);
+    case B2E_EPI_BIAS_GELU:
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_GELU>(ta, tb, out, bias, resid, M, N, K, sms, st);
+    case B2E_EPI_BIAS_RESID:
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_RESID>(ta, tb, out, bias, resid, M, N, K, sms,
+                                                         st);
+  }
+  return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+inline int gemm_bn_for(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+int check_gemm_shape(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(B2E_ERR_INVALID, "gemm: empty shape %dx%dx%d", M, N, K);
+  if (N % 128 != 0) return fail(B2E_ERR_INVALID, "gemm: N=%d must be a multiple of 128", N);
+  if (K % 64 != 0) return fail(B2E_ERR_INVALID, "gemm: K=%d must be a multiple of 64", K);
+  return B2E_OK;
+}
+
+// A map: [M,K] box 128 rows; W map: [N,K] box BN rows.
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const float* bias,
+                const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
+  if (gemm_bn_for(N) == 256)
+    return launch_gemm_bn<256, 4>(ta, tb, static_cast<bf16*>(out), bias,
+                                  static_cast<const bf16*>(resid), M, N, K, epi, sms, st);
+  return launch_gemm_bn<128, 6>(ta, tb, static_cast<bf16*>(out), bias,
+                                static_cast<const bf16*>(resid), M, N, K, epi, sms, st);
+}
+
+int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
+                     int heads, float* dbg, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(attention_d64_tcgen05_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, heads, B);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  attention_d64_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(
+      tqkv, mask, static_cast<bf16*>(ctx), S, heads * ATT_D, scale_log2e, dbg);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+#define DISPATCH_NV(H, CALL)                                        \
+  switch ((H) / 256) {                                              \
+    case 1: { constexpr int NV = 1; CALL; break; }                  \
+    case 2: { constexpr int NV = 2; CALL; break; }                  \
+    case 3: { constexpr int NV = 3; CALL; break; }                  \
+    case 4: { constexpr int NV = 4; CALL; break; }                  \
+    case 5: { constexpr int NV = 5; CALL; break; }                  \
+    case 8: { constexpr int NV = 8; CALL; break; }                  \
+    case 16: { constexpr int NV = 16; CALL; break; }                \
+    default: return fail(B2E_ERR_INVALID, "hidden size %d not supported (need 256*{1,2,3,4,5,8,16})", (H)); \
+  }
+
+inline int row_blocks(int rows) { return (rows + ROW_WARPS - 1) / ROW_WARPS; }
+
+int check_h(int H) {
+  if (H % 256 != 0) return fail(B2E_ERR_INVALID, "hidden size %d must be a multiple of 256", H);
+  return B2E_OK;
+}
+
+// Pool-weight scratch shared by the fused and the standalone poolers.
+struct PoolScratch {
+  int* seq_len = nullptr;  // [B]
+  int* kill = nullptr;     // [S]
+  int* idx = nullptr;      // [B]
+  float* w = nullptr;      // [B,S]
+  float* count = nullptr;  // [B]
+  float* part = nullptr;   // [B,nsplit,H]
+  size_t cap_b = 0, cap_s = 0, cap_bs = 0, cap_part = 0;
+  int device = -1;
+
+  int ensure(int B, int S, size_t part_elems) {
+    if ((size_t)B > cap_b) {
+      if (seq_len) cudaFree(seq_len);
+      if (idx) cudaFree(idx);
+      if (count) cudaFree(count);
+      CUDA_TRY(cudaMalloc(&seq_len, sizeof(int) * B));
+      CUDA_TRY(cudaMalloc(&idx, sizeof(int) * B));
+      CUDA_TRY(cudaMalloc(&count, sizeof(float) * B));
+      cap_b = B;
+    }
+    if ((size_t)S > cap_s) {
+      if (kill) cudaFree(kill);
+      CUDA_TRY(cudaMalloc(&kill, sizeof(int) * S));
+      cap_s = S;
+    }
+    if ((size_t)B * S > cap_bs) {
+      if (w) cudaFree(w);
+      CUDA_TRY(cudaMalloc(&w, sizeof(float) * (size_t)B * S));
+      cap_bs = (size_t)B * S;
+    }
+    if (part_elems > cap_part) {
+      if (part) cudaFree(part);
+      CUDA_TRY(cudaMalloc(&part, sizeof(float) * part_elems));
+      cap_part = part_elems;
+    }
+    return B2E_OK;
+  }
+  void release() {
+    cudaFree(seq_len); cudaFree(kill); cudaFree(idx); cudaFree(w); cudaFree(count); cudaFree(part);
+    seq_len = kill = idx = nullptr; w = count = part = nullptr;
+    cap_b = cap_s = cap_bs = cap_part = 0;
+  }
+};
+
+inline int pool_nsplit(int S) {
+  int n = (S + 63) / 64;  // ~64 rows per block keeps every SM busy at B >= 32
+  return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+int launch_pool_weights(PoolScratch& ps, int64_t* mask, int B, int S, int pool_kind, int mutate,
+                        cudaStream_t st) {
+  seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
+  CUDA_TRY(cudaMemsetAsync(ps.kill, 0, sizeof(int) * S, st));
+  kill_columns_kernel<<<(B + 255) / 256, 256, 0, st>>>(ps.seq_len, ps.kill, B, S);
+  pool_weights_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, ps.kill, ps.w, ps.count, B, S,
+                                                    pool_kind == B2E_POOL_MEAN_REF ? 1 : 0, mutate);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int launch_finalize(PoolScratch& ps, float* out, int B, int H, int nsplit, int l2, int round_mode,
+                    cudaStream_t st) {
+  pool_finalize_kernel<<<B, 256, (H + 32) * sizeof(float), st>>>(ps.part, ps.count, out, H, nsplit,
+                                                                 l2, round_mode);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+thread_local PoolScratch g_pool_scratch;  // for the handle-less standalone poolers
+
+}  // namespace
+
+// ================================================================== encoder handle
+struct B2EEncoder {
+  B2EModelDesc desc;
+  std::vector<const void*> w;
+  int device = 0;
+  int sms = 0;
+  // activations (bf16)
+  size_t cap_tokens = 0;
+  bf16 *hidden = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
+  PoolScratch pool;
+  // weight tensor maps, one per layer
+  std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w1, tm_w2;
+  // host-loop staging
+  int64_t* stage_in = nullptr;
+  size_t stage_cap = 0;
+  float* stage_out = nullptr;
+  size_t stage_out_cap = 0;
+  cudaStream_t own_stream = nullptr;
+
+  // BERT weight slots
+  const float* word() const { return (const float*)w[0]; }
+  const float* pos() const { return (const float*)w[1]; }
+  const float* type() const { return (const float*)w[2]; }
+  const float* emb_g() const { return (const float*)w[3]; }
+  const float* emb_b() const { return (const float*)w[4]; }
+  const void* L(int l, int k) const { return w[5 + 12 * l + k]; }
+};
+
+namespace {
+
+size_t tokens_bytes(const B2EModelDesc& d, size_t tokens) {
+  return tokens * (size_t)(6 * d.hidden + d.intermediate) * 2;
+}
+
+int ensure_workspace(B2EEncoder* e, int B, int S) {
+  const size_t tokens = (size_t)B * S;
+  if (tokens > e->cap_tokens) {
+    cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
+    e->hidden = e->qkv = e->ctx = e->tmp = e->ffn = nullptr;
+    e->cap_tokens = 0;
+    const size_t H = e->desc.hidden, I = e->desc.intermediate;
+    CUDA_TRY(cudaMalloc(&e->hidden, tokens * H * 2));
+    CUDA_TRY(cudaMalloc(&e->qkv, tokens * 3 * H * 2));
+    CUDA_TRY(cudaMalloc(&e->ctx, tokens * H * 2));
+    CUDA_TRY(cudaMalloc(&e->tmp, tokens * H * 2));
+    CUDA_TRY(cudaMalloc(&e->ffn, tokens * I * 2));
+    e->cap_tokens = tokens;
+  }
+  return e->pool.ensure(B, S, (size_t)B * pool_nsplit(S) * e->desc.hidden);
+}
+
+int validate_batch(const B2EEncoder* e, int B, int S) {
+  if (!e) return fail(B2E_ERR_INVALID, "null encoder handle");
+  if (B <= 0 || S <= 0) return fail(B2E_ERR_INVALID, "empty batch B=%d S=%d", B, S);
+  if (S > e->desc.max_pos)
+    return fail(B2E_ERR_INVALID, "S=%d exceeds max_position_embeddings=%d", S, e->desc.max_pos);
+  if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d not supported yet", S, ATT_MAX_S);
+  return B2E_OK;
+}
+
+// Layers 0..L-1 up to (and including) the last FFN-down GEMM: leaves the pre-LayerNorm residual sum
+// of the final layer in e->tmp; every earlier LayerNorm output lives in e->hidden.
+int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types,
+                   int B, int S, cudaStream_t st) {
+  const B2EModelDesc& d = e->desc;
+  const int M = B * S, H = d.hidden, I = d.intermediate;
+  int rc;
+  DISPATCH_NV(H, (embed_layernorm_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     ids, types, e->word(), e->pos(), e->type(), e->emb_g(), e->emb_b(), e->hidden,
+                     M, S, d.eps)));
+  CUDA_TRY(cudaGetLastError());
+
+  CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv;
+  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
+
+  for (int l = 0; l < d.num_layers; ++l) {
+    if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->L(l, 1), nullptr, M,
+                          3 * H, H, B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+    if ((rc = launch_attention(tm_qkv, mask, e->ctx, B, S, d.heads, nullptr, st))) return rc;
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), e->hidden, M, H,
+                          H, B2E_EPI_BIAS_RESID, e->sms, st)))
+      return rc;
+    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->tmp, (const float*)e->L(l, 4), (const float*)e->L(l, 5), e->hidden, M,
+                       d.eps)));
+    if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->L(l, 7), nullptr, M, I,
+                          H, B2E_EPI_BIAS_GELU, e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->L(l, 9), e->hidden, M, H, I,
+                          B2E_EPI_BIAS_RESID, e->sms, st)))
+      return rc;
+    if (l + 1 < d.num_layers) {
+      DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11), e->hidden, M,
+                         d.eps)));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int b2e_version(void) { return B2E_ABI_VERSION; }
+const char* b2e_last_error(void) { return g_err.c_str(); }
+
+int b2e_num_weights(const B2EModelDesc* desc) {
+  if (!desc) return -1;
+  if (desc->arch == B2E_ARCH_BERT) return 5 + 12 * desc->num_layers;
+  return -1;
+}
+
+int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int n_weights,
+                       int device, B2EEncoder** out) {
+  if (!desc || !weights || !out) return fail(B2E_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (desc->arch != B2E_ARCH_BERT)
+    return fail(B2E_ERR_UNSUPPORTED, "arch %d: only B2E_ARCH_BERT is built in this round", desc->arch);
+  if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
+    return fail(B2E_ERR_UNSUPPORTED, "need head_dim 64 and heads*64 == hidden (got %d x %d, H=%d)",
+                desc->heads, desc->head_dim, desc->hidden);
+  int rc;
+  if ((rc = check_h(desc->hidden))) return rc;
+  if ((rc = check_gemm_shape(128, 3 * desc->hidden, desc->hidden))) return rc;
+  if ((rc = check_gemm_shape(128, desc->intermediate, desc->hidden))) return rc;
+  if ((rc = check_gemm_shape(128, desc->hidden, desc->intermediate))) return rc;
+  if (n_weights != b2e_num_weights(desc))
+    return fail(B2E_ERR_INVALID, "expected %d weight pointers, got %d", b2e_num_weights(desc),
+                n_weights);
+  for (int i = 0; i < n_weights; ++i)
+    if (!weights[i]) return fail(B2E_ERR_INVALID, "weight pointer %d is null", i);
+  DeviceInfo info;
+  if ((rc = device_info(device, &info))) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+
+  B2EEncoder* e = new B2EEncoder();
+  e->desc = *desc;
+  e->w.assign(weights, weights + n_weights);
+  e->device = device;
+  e->sms = info.sms;
+  const int L = desc->num_layers, H = desc->hidden, I = desc->intermediate;
+  e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
+  for (int l = 0; l < L; ++l) {
+    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], e->L(l, 0), 3 * H, H, gemm_bn_for(3 * H))) ||
+        (rc = make_tmap_bf16(&e->tm_wo[l], e->L(l, 2), H, H, gemm_bn_for(H))) ||
+        (rc = make_tmap_bf16(&e->tm_w1[l], e->L(l, 6), I, H, gemm_bn_for(I))) ||
+        (rc = make_tmap_bf16(&e->tm_w2[l], e->L(l, 8), H, I, gemm_bn_for(H)))) {
+      delete e;
+      return rc;
+    }
+  }
+  *out = e;
+  return B2E_OK;
+}
+
+void b2e_encoder_destroy(B2EEncoder* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
+  cudaFree(e->stage_in); cudaFree(e->stage_out);
+  e->pool.release();
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int64_t b2e_workspace_bytes(const B2EEncoder* e, int B, int S) {
+  if (!e || B <= 0 || S <= 0) return -1;
+  const size_t tokens = (size_t)B * S;
+  size_t bytes = tokens_bytes(e->desc, tokens);
+  bytes += tokens * sizeof(float) + (size_t)S * sizeof(int) + (size_t)B * (2 * sizeof(int) + sizeof(float));
+  bytes += (size_t)B * pool_nsplit(S) * e->desc.hidden * sizeof(float);
+  return (int64_t)bytes;
+}
+
+int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types, int B,
+               int S, void* out_hidden, int out_dtype, void* stream) {
+  int rc;
+  if ((rc = validate_batch(e, B, S))) return rc;
+  if (!ids || !mask || !out_hidden) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (out_dtype != B2E_DTYPE_F32 && out_dtype != B2E_DTYPE_BF16)
+    return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or BF16");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_workspace(e, B, S))) return rc;
+  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
+  const B2EModelDesc& d = e->desc;
+  const int M = B * S, H = d.hidden, l = d.num_layers - 1;
+  if (out_dtype == B2E_DTYPE_F32) {
+    DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
+                       (float*)out_hidden, M, d.eps)));
+  } else {
+    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
+                       (bf16*)out_hidden, M, d.eps)));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types,
+                      int B, int S, int pool_kind, int l2, float* out, void* stream) {
+  int rc;
+  if ((rc = validate_batch(e, B, S))) return rc;
+  if (!ids || !mask || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (pool_kind < B2E_POOL_MEAN_REF || pool_kind > B2E_POOL_LAST_TOKEN)
+    return fail(B2E_ERR_INVALID, "unknown pool_kind %d", pool_kind);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_workspace(e, B, S))) return rc;
+  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
+  const B2EModelDesc& d = e->desc;
+  const int H = d.hidden, l = d.num_layers - 1;
+  const float* g = (const float*)e->L(l, 10);
+  const float* bt = (const float*)e->L(l, 11);
+  PoolScratch& ps = e->pool;
+  if (pool_kind == B2E_POOL_LAST_TOKEN) {
+    seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
+    last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
+    DISPATCH_NV(H, (layernorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
+                       e->tmp, ps.idx, g, bt, out, B, S, d.eps)));
+    if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
+    CUDA_TRY(cudaGetLastError());
+    return B2E_OK;
+  }
+  // the fused path never edits the caller's mask: weights are built from a read-only view
+  if ((rc = launch_pool_weights(ps, const_cast<int64_t*>(mask), B, S, pool_kind, /*mutate=*/0, st)))
+    return rc;
+  const int nsplit = pool_nsplit(S);
+  const int rows_per = (S + nsplit - 1) / nsplit;
+  dim3 grid(B, nsplit);
+  DISPATCH_NV(H, (layernorm_pool_kernel<NV><<<grid, ROW_THREADS, 0, st>>>(e->tmp, g, bt, ps.w,
+                                                                        ps.part, S, rows_per, d.eps)));
+  CUDA_TRY(cudaGetLastError());
+  return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
+}
+
+int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types,
+                   int64_t n_rows, int S, int batch, int pool_kind, int l2, float* out_host) {
+  if (!e) return fail(B2E_ERR_INVALID, "null encoder handle");
+  if (n_rows < 0 || batch <= 0) return fail(B2E_ERR_INVALID, "bad n_rows/batch");
+  if (n_rows == 0) return B2E_OK;
+  if (!ids || !mask || !out_host) return fail(B2E_ERR_INVALID, "null host pointer");
+  int rc;
+  if ((rc = validate_batch(e, batch, S))) return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!e->own_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = e->own_stream;
+  const int H = e->desc.hidden;
+  // two input slots (ids | mask | types) so batch i+1 uploads while batch i computes
+  const size_t slot = (size_t)batch * S * 3;
+  if (2 * slot > e->stage_cap) {
+    cudaFree(e->stage_in);
+    e->stage_in = nullptr;
+    CUDA_TRY(cudaMalloc(&e->stage_in, 2 * slot * sizeof(int64_t)));
+    e->stage_cap = 2 * slot;
+  }
+  const size_t out_elems = (size_t)batch * H * 2;
+  if (out_elems > e->stage_out_cap) {
+    cudaFree(e->stage_out);
+    e->stage_out = nullptr;
+    CUDA_TRY(cudaMalloc(&e->stage_out, out_elems * sizeof(float)));
+    e->stage_out_cap = out_elems;
+  }
+  int which = 0;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += batch, which ^= 1) {
+    const int B = (int)((n_rows - r0 < batch) ? (n_rows - r0) : batch);
+    const size_t n = (size_t)B * S;
+    int64_t* d_ids = e->stage_in + which * slot;
+    int64_t* d_mask = d_ids + (size_t)batch * S;
+    int64_t* d_types = d_mask + (size_t)batch * S;
+    float* d_out = e->stage_out + (size_t)which * batch * H;
+    CUDA_TRY(cudaMemcpyAsync(d_ids, ids + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_mask, mask + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
+    if (types) CUDA_TRY(cudaMemcpyAsync(d_types, types + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = b2e_encode_pooled(e, d_ids, d_mask, types ? d_types : nullptr, B, S, pool_kind, l2,
+                                d_out, st)))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host + r0 * H, d_out, (size_t)B * H * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return B2E_OK;
+}
+
+int b2e_pool_mean(const void* hidden, int dtype, int64_t* mask, int B, int S, int H, int pool_kind,
+                  int quirk_mutate, float* out, void* stream) {
+  if (!hidden || !mask || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || S <= 0) return fail(B2E_ERR_INVALID, "empty batch B=%d S=%d", B, S);
+  if (pool_kind != B2E_POOL_MEAN_REF && pool_kind != B2E_POOL_MEAN_PER_ROW)
+    return fail(B2E_ERR_INVALID, "pool_mean: pool_kind %d", pool_kind);
+  int rc;
+  if ((rc = check_h(H))) return rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PoolScratch& ps = g_pool_scratch;
+  const int nsplit = pool_nsplit(S);
+  const int rows_per = (S + nsplit - 1) / nsplit;
+  if ((rc = ps.ensure(B, S, (size_t)B * nsplit * H))) return rc;
+  if ((rc = launch_pool_weights(ps, mask, B, S, pool_kind, quirk_mutate, st))) return rc;
+  dim3 grid(B, nsplit);
+  int round_mode = 0;
+  switch (dtype) {
+    case B2E_DTYPE_F32:
+      DISPATCH_NV(H, (pool_sum_kernel<NV, float><<<grid, ROW_THREADS, 0, st>>>(
+                         (const float*)hidden, ps.w, ps.part, S, rows_per)));
+      break;
+    case B2E_DTYPE_BF16:
+      round_mode = 1;
+      DISPATCH_NV(H, (pool_sum_kernel<NV, bf16><<<grid, ROW_THREADS, 0, st>>>(
+                         (const bf16*)hidden, ps.w, ps.part, S, rows_per)));
+      break;
+    case B2E_DTYPE_F16:
+      round_mode = 2;
+      DISPATCH_NV(H, (pool_sum_kernel<NV, __half><<<grid, ROW_THREADS, 0, st>>>(
+                         (const __half*)hidden, ps.w, ps.part, S, rows_per)));
+      break;
+    default:
+      return fail(B2E_ERR_INVALID, "pool_mean: dtype %d", dtype);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return launch_finalize(ps, out, B, H, nsplit, 0, round_mode, st);
+}
+
+int b2e_pool_last_token(const void* hidden, int dtype, const int64_t* mask, int B, int S, int H,
+                        float* out, void* stream) {
+  if (!hidden || !mask || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || S <= 0) return fail(B2E_ERR_INVALID, "empty batch B=%d S=%d", B, S);
+  if (H % 8 != 0) return fail(B2E_ERR_INVALID, "H=%d must be a multiple of 8", H);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PoolScratch& ps = g_pool_scratch;
+  if ((rc = ps.ensure(B, S, 0))) return rc;
+  seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
+  last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
+  switch (dtype) {
+    case B2E_DTYPE_F32:
+      gather_rows_kernel<float><<<B, 128, 0, st>>>((const float*)hidden, ps.idx, out, B, S, H);
+      break;
+    case B2E_DTYPE_BF16:
+      gather_rows_kernel<bf16><<<B, 128, 0, st>>>((const bf16*)hidden, ps.idx, out, B, S, H);
+      break;
+    case B2E_DTYPE_F16:
+      gather_rows_kernel<__half><<<B, 128, 0, st>>>((const __half*)hidden, ps.idx, out, B, S, H);
+      break;
+    default:
+      return fail(B2E_ERR_INVALID, "pool_last_token: dtype %d", dtype);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int b2e_l2_normalize(float* x, int64_t n_rows, int H, void* stream) {
+  if (!x) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (n_rows <= 0) return B2E_OK;
+  if (H % 4 != 0) return fail(B2E_ERR_INVALID, "H=%d must be a multiple of 4", H);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  l2_normalize_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (int)n_rows,
+                                                                                   H);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
+                             const int32_t* doc_id, float* out, void* stream) {
+  if (n_rows <= 1) return B2E_OK;  // no adjacent pair: nothing to write (semantic_chunk.py:80-81)
+  if (!emb || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (H % 8 != 0) return fail(B2E_ERR_INVALID, "H=%d must be a multiple of 8", H);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((n_rows - 1 + 7) / 8);
+  switch (dtype) {
+    case B2E_DTYPE_F32:
+      adjacent_cosine_kernel<float><<<blocks, 256, 0, st>>>((const float*)emb, doc_id, out,
+                                                            (int)n_rows, H);
+      break;
+    case B2E_DTYPE_BF16:
+      adjacent_cosine_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)emb, doc_id, out,
+                                                           (int)n_rows, H);
+      break;
+    case B2E_DTYPE_F16:
+      adjacent_cosine_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)emb, doc_id, out,
+                                                             (int)n_rows, H);
+      break;
+    default:
+      return fail(B2E_ERR_INVALID, "adjacent_cosine_dist: dtype %d", dtype);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+                  int M, int N, int K, int epi, void* stream) {
+  if (!A || !W || !bias || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (epi == B2E_EPI_BIAS_RESID && !resid) return fail(B2E_ERR_INVALID, "resid epilogue needs resid");
+  int rc;
+  if ((rc = check_gemm_shape(M, N, K))) return rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_bf16(&ta, A, M, K, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tb, W, N, K, gemm_bn_for(N)))) return rc;
+  return launch_gemm(ta, tb, out, bias, resid, M, N, K, epi, info.sms, (cudaStream_t)stream);
+}
+
+int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int heads,
+                      float* dbg, void* stream) {
+  if (!qkv || !mask || !ctx) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || S <= 0 || heads <= 0) return fail(B2E_ERR_INVALID, "empty attention problem");
+  if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d not supported yet", S, ATT_MAX_S);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  CUtensorMap tq;
+  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, 128))) return rc;
+  return launch_attention(tq, mask, ctx, B, S, heads, dbg, (cudaStream_t)stream);
+}
+
+int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* out, int rows, int H,
+                  float eps, int out_dtype, void* stream) {
+  if (!in || !gamma || !beta || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (rows <= 0) return B2E_OK;
+  int rc;
+  if ((rc = check_h(H))) return rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == B2E_DTYPE_F32) {
+    DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
+                       (const bf16*)in, gamma, beta, (float*)out, rows, eps)));
+  } else if (out_dtype == B2E_DTYPE_BF16) {
+    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
+                       (const bf16*)in, gamma, beta, (bf16*)out, rows, eps)));
+  } else {
+    return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or BF16");
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+}  // extern "C"

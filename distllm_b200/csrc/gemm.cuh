@@ -1,0 +1,205 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias)
+//
+//   warp 0      TMA producer   (one elected lane): A/W tiles -> 128B-swizzled smem ring
+//   warp 1      MMA issuer     (one elected lane): tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld -> +bias (-> erf-GELU | +residual) -> bf16 -> global
+//
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  This replaces the cuBLAS nn.Linear calls HF BERT issues from
+// transformers/models/bert/modeling_bert.py:180-182 (q,k,v), :294-298 (attn out), :339-342 (FFN up +
+// GELU), :352-356 (FFN down), reached from distllm/embed/encoders/auto.py:135.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2e {
+
+enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
+
+template <int BN, int STAGES>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
+                         const __grid_constant__ CUtensorMap tm_b, bf16* __restrict__ out,
+                         const float* __restrict__ bias, const bf16* __restrict__ resid, int M,
+                         int N, int K) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw + pad;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
+  const uint32_t full_bar = smem_base + Cfg::BAR_OFFSET;
+  const uint32_t empty_bar = full_bar + 8u * STAGES;
+  const uint32_t tfull_bar = empty_bar + 8u * STAGES;
+  const uint32_t tempty_bar = tfull_bar + 16u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8u * s, 1);
+      mbar_init(empty_bar + 8u * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8u * s, 1);
+      mbar_init(tempty_bar + 8u * s, GEMM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = N / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kblocks = K / GEMM_BK;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar + 8u * stage, phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t fb = full_bar + 8u * stage;
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          tma_load_2d(a_dst, &tm_a, fb, kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &tm_b, fb, kb * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1u;
+        mbar_wait(tempty_bar + 8u * as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes along K inside the swizzle atom == +2 in the (addr >> 4) field
+            tc_mma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc,
+                          static_cast<uint32_t>((kb | k) != 0));
+          }
+          tc_commit(empty_bar + 8u * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar + 8u * as);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;               // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;     // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1u;
+      mbar_wait(tfull_bar + 8u * as, aphase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const size_t row_off = static_cast<size_t>(row) * static_cast<size_t>(N);
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+        const int col_in_tile = half * COLS_PER_WARP + c * 32;
+        const int gcol = n_blk * BN + col_in_tile;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                      static_cast<uint32_t>(as * BN + col_in_tile),
+                  r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j + 4));
+          float v[8];
+          v[0] = __uint_as_float(r[j + 0]) + b0.x;
+          v[1] = __uint_as_float(r[j + 1]) + b0.y;
+          v[2] = __uint_as_float(r[j + 2]) + b0.z;
+          v[3] = __uint_as_float(r[j + 3]) + b0.w;
+          v[4] = __uint_as_float(r[j + 4]) + b1.x;
+          v[5] = __uint_as_float(r[j + 5]) + b1.y;
+          v[6] = __uint_as_float(r[j + 6]) + b1.z;
+          v[7] = __uint_as_float(r[j + 7]) + b1.w;
+          if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+          }
+          if (EPI == EPI_BIAS_RESID) {
+            if (row_ok) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(resid + row_off + gcol + j);
+              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y),
+                           r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            }
+          }
+          if (row_ok) {
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]);
+            o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(out + row_off + gcol + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8u * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace b2e

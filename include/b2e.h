@@ -1,0 +1,127 @@
+/* b2e.h -- C ABI of libb2e.so, the B200-native embedding hot path for distllm.
+ *
+ * Every entry point is plain C: caller-owned pointers and sizes, no C++/torch types, no exceptions.
+ * Functions return 0 on success or a B2E_ERR_* code; b2e_last_error() gives the thread-local
+ * message.  Device pointers come from torch.Tensor.data_ptr(); work is enqueued on the supplied
+ * cudaStream_t (passed as void*) and never synchronises, except b2e_embed_host which owns its
+ * copies and returns with the host output complete.
+ *
+ * Reference interfaces replaced (paths relative to the distllm tree):
+ *   b2e_encoder_create      distllm/embed/encoders/auto.py:37-97   (AutoEncoder.__init__)
+ *   b2e_encode              distllm/embed/encoders/auto.py:119-138 (AutoEncoder.encode ->
+ *                           HF BertModel.forward, transformers/models/bert/modeling_bert.py:628-690)
+ *   b2e_encode_pooled       distllm/embed/embedders/full_sequence.py:59-69 (encode + pool + normalize)
+ *   b2e_embed_host          distllm/embed/embedders/full_sequence.py:57-78 (the whole batch loop,
+ *                           host buffers in / host matrix out)
+ *   b2e_pool_mean           distllm/embed/poolers/mean.py:13-49    (average_pool, incl. in-place mask edit)
+ *   b2e_pool_last_token     distllm/embed/poolers/last_token.py:12-39
+ *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
+ *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
+ *   b2e_gemm_bf16 / b2e_attention_d64 / b2e_layernorm: the building blocks, exported so the parity
+ *                           tests can pin each kernel separately.
+ */
+#ifndef B2E_H_
+#define B2E_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2E_ABI_VERSION 1
+
+enum {
+  B2E_OK = 0,
+  B2E_ERR_INVALID = 1,      /* bad argument / unsupported shape */
+  B2E_ERR_CUDA = 2,         /* a CUDA runtime or driver call failed */
+  B2E_ERR_UNSUPPORTED = 3,  /* architecture or feature not built yet */
+  B2E_ERR_NO_DEVICE = 4     /* no sm_100 device: there is no CPU fallback */
+};
+
+enum { B2E_ARCH_BERT = 0, B2E_ARCH_ESM2 = 1, B2E_ARCH_MISTRAL = 2 };
+enum { B2E_DTYPE_F32 = 0, B2E_DTYPE_BF16 = 1, B2E_DTYPE_F16 = 2 };
+enum {
+  B2E_POOL_MEAN_REF = 0,     /* mean.py semantics incl. the cross-row end-token quirk (mean.py:36) */
+  B2E_POOL_MEAN_PER_ROW = 1, /* drop only each row's own first/last token */
+  B2E_POOL_LAST_TOKEN = 2
+};
+enum { B2E_EPI_BIAS = 0, B2E_EPI_BIAS_GELU = 1, B2E_EPI_BIAS_RESID = 2 };
+
+typedef struct B2EModelDesc {
+  int32_t arch;          /* B2E_ARCH_* */
+  int32_t num_layers;
+  int32_t hidden;        /* H, multiple of 256 */
+  int32_t heads;
+  int32_t kv_heads;
+  int32_t head_dim;
+  int32_t intermediate;  /* I */
+  int32_t vocab;
+  int32_t max_pos;
+  int32_t type_vocab;
+  float eps;             /* LayerNorm / RMSNorm epsilon */
+  float rope_theta;      /* unused for BERT */
+  int32_t sliding_window;
+  int32_t reserved;
+} B2EModelDesc;
+
+typedef struct B2EEncoder B2EEncoder;
+
+int b2e_version(void);
+const char* b2e_last_error(void);
+
+/* Number of device weight pointers b2e_encoder_create expects for `desc` (BERT: 5 + 12*L, order in
+ * distllm_b200/embed/encoders/weights.py).  Matrices are bf16 [out,in] row-major, vectors and
+ * embedding tables fp32.  The pointers stay owned by the caller and must outlive the handle. */
+int b2e_num_weights(const B2EModelDesc* desc);
+int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int n_weights,
+                       int device, B2EEncoder** out);
+void b2e_encoder_destroy(B2EEncoder* enc);
+
+/* Bytes of device workspace the handle holds for a [B,S] batch (grown lazily, never shrunk). */
+int64_t b2e_workspace_bytes(const B2EEncoder* enc, int B, int S);
+
+/* Full forward pass; writes the final hidden state [B,S,H] as out_dtype (F32 or BF16). */
+int b2e_encode(B2EEncoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
+               const int64_t* token_type_ids /* nullable */, int B, int S, void* out_hidden,
+               int out_dtype, void* stream);
+
+/* Forward pass with the pooler fused into the final LayerNorm: writes fp32 [B,H]; the [B,S,H]
+ * hidden state never reaches HBM.  attention_mask is NOT modified. */
+int b2e_encode_pooled(B2EEncoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
+                      const int64_t* token_type_ids /* nullable */, int B, int S, int pool_kind,
+                      int l2_normalize, float* out_pooled, void* stream);
+
+/* Host-buffer batch loop: n_rows sequences of S tokens in host memory (pinned for full speed),
+ * processed `batch` at a time in order (the batch composition matters for B2E_POOL_MEAN_REF);
+ * fp32 [n_rows,H] written to host memory.  Synchronous. */
+int b2e_embed_host(B2EEncoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
+                   const int64_t* token_type_ids /* nullable */, int64_t n_rows, int S, int batch,
+                   int pool_kind, int l2_normalize, float* out_host);
+
+/* Standalone poolers over a materialised hidden state (dtype F32/BF16/F16), fp32 [B,H] out.
+ * b2e_pool_mean rewrites attention_mask in place like the reference when quirk_mutate != 0. */
+int b2e_pool_mean(const void* hidden, int dtype, int64_t* attention_mask, int B, int S, int H,
+                  int pool_kind, int quirk_mutate, float* out, void* stream);
+int b2e_pool_last_token(const void* hidden, int dtype, const int64_t* attention_mask, int B, int S,
+                        int H, float* out, void* stream);
+int b2e_l2_normalize(float* x, int64_t n_rows, int H, void* stream);
+
+/* out[i] = 1 - cos(emb[i], emb[i+1]) for i in [0, n_rows-1); pairs with doc_id[i] != doc_id[i+1]
+ * (doc_id nullable) are written as NaN. */
+int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
+                             const int32_t* doc_id, float* out, void* stream);
+
+/* Building blocks (bf16 row-major): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
+int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+                  int M, int N, int K, int epilogue, void* stream);
+/* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; dbg_scores nullable ([128,512] fp32 of CTA 0). */
+int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
+                      int heads, float* dbg_scores, void* stream);
+int b2e_layernorm(const void* in_bf16, const float* gamma, const float* beta, void* out, int rows,
+                  int H, float eps, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2E_H_ */
