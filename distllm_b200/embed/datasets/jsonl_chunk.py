@@ -1,0 +1,116 @@
+"""jsonl documents -> sentence buffers for semantic chunking.
+
+Follows distllm/embed/datasets/jsonl_chunk.py:24-179: split each document into sentences keeping
+the whitespace that follows a sentence attached to it, build one buffer per sentence from the
+sentences within ``buffer_size`` of it, carry a copy of the document metadata plus the sentence on
+every row, and drop buffers of ``min_buffer_length`` characters or fewer.
+"""
+
+from __future__ import annotations
+
+import re
+from pathlib import Path
+from typing import Any
+from typing import Callable
+from typing import Literal
+
+from pydantic import Field
+from torch.utils.data import DataLoader
+
+from distllm_b200.embed.datasets.jsonl import read_jsonl
+from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import make_dataloader
+from distllm_b200.embed.encoders.base import Encoder
+from distllm_b200.utils import BaseConfig
+
+# sentence end = . ! or ? (plus closing quotes/brackets), whitespace, then an upper-case/digit start
+_BOUNDARY = re.compile(r'[.!?]["\')\]]*\s+(?=[A-Z0-9"\'(\[])')
+
+
+def _regex_spans(text: str) -> list[tuple[int, int]]:
+    """Dependency-free stand-in for Punkt ``span_tokenize`` (used only when nltk is absent)."""
+    spans = []
+    start = 0
+    for m in _BOUNDARY.finditer(text):
+        end = m.end()
+        stop = m.start() + len(m.group().rstrip())
+        spans.append((start, stop))
+        start = end
+    if start < len(text):
+        spans.append((start, len(text.rstrip()) if text.rstrip() else len(text)))
+    return [(s, e) for s, e in spans if e > s]
+
+
+def _span_tokenizer() -> Callable[[str], list[tuple[int, int]]]:
+    try:
+        import nltk
+
+        punkt = nltk.tokenize.PunktSentenceTokenizer()
+        return lambda text: list(punkt.span_tokenize(text))
+    except ImportError:
+        return _regex_spans
+
+
+def split_by_sentence_tokenizer() -> Callable[[str], list[str]]:
+    """Sentence splitter whose pieces concatenate back to the original text (minus leading junk):
+    piece ``i`` runs from the start of sentence ``i`` to the start of sentence ``i+1``."""
+    spans_of = _span_tokenizer()
+
+    def split(text: str) -> list[str]:
+        starts = [s for s, _ in spans_of(text)]
+        stops = starts[1:] + [len(text)]
+        return [text[a:b] for a, b in zip(starts, stops)]
+
+    return split
+
+
+def sentences_to_buffers(split: list[str], buffer_size: int) -> list[str]:
+    """Buffer ``i`` = sentences ``[i - buffer_size, i + buffer_size]`` joined (clipped at the ends)."""
+    n = len(split)
+    return [''.join(split[max(0, i - buffer_size) : min(n, i + buffer_size + 1)]) for i in range(n)]
+
+
+class JsonlChunkDatasetConfig(BaseConfig):
+    name: Literal['jsonl_chunk'] = 'jsonl_chunk'  # type: ignore[assignment]
+    # The name of the text field in the jsonl file
+    text_field: str = 'text'
+    # Number of data workers for batching.
+    num_data_workers: int = 4
+    # Inference batch size.
+    batch_size: int = 8
+    # Whether to pin memory for the dataloader.
+    pin_memory: bool = True
+    min_buffer_length: int = Field(
+        default=750,
+        description='Buffers with this many characters or fewer are filtered out '
+        '(removes citations and other fragments).',
+    )
+    buffer_size: int = Field(
+        default=1,
+        description='Number of neighbouring sentences on each side grouped with a sentence '
+        'when evaluating semantic similarity.',
+    )
+
+
+class JsonlChunkDataset:
+    def __init__(self, config: JsonlChunkDatasetConfig):
+        self.config = config
+        self.splitter = split_by_sentence_tokenizer()
+
+    def get_dataloader(self, data_file: Path, encoder: Encoder) -> DataLoader:
+        rows: list[dict[str, Any]] = read_jsonl(data_file)
+        texts = [row.pop(self.config.text_field) for row in rows]
+        # whatever is left of each row is that document's metadata
+        if not rows or any(not row for row in rows):
+            raise ValueError('Metadata is empty. Please check the jsonl file.')
+
+        buffers: list[str] = []
+        metadatas: list[dict[str, Any]] = []
+        for doc_meta, text in zip(rows, texts):
+            sentences = self.splitter(text)
+            buffers.extend(sentences_to_buffers(sentences, self.config.buffer_size))
+            metadatas.extend({**doc_meta, 'sentence': sentence} for sentence in sentences)
+
+        keep = [i for i, buf in enumerate(buffers) if len(buf) > self.config.min_buffer_length]
+        dataset = InMemoryDataset([buffers[i] for i in keep], [metadatas[i] for i in keep])
+        return make_dataloader(self.config, dataset, encoder.tokenizer)

@@ -1,0 +1,102 @@
+"""Full-sequence embedder: the batch loop of the hot path.
+
+Replaces distllm/embed/embedders/full_sequence.py:20-80.  When the encoder exposes the fused native
+entry point (``encode_pooled``) and the pooler names a native epilogue (``native_pool_kind``) each
+batch is ONE call into libb2e: forward pass, pooling and optional L2 normalisation, written
+straight into a device-resident ``[N,H]`` matrix.  The reference's per-batch ``.cpu()`` sync
+(full_sequence.py:75) becomes a single device->host copy after the loop.  Batches are consumed in
+dataloader order with the dataloader's batch size, so the batch-dependent mean-pool quirk sees the
+same batch composition as the reference.
+"""
+
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+import torch
+from pydantic import Field
+from torch.utils.data import DataLoader
+from tqdm import tqdm
+
+from distllm_b200 import _native
+from distllm_b200.embed.embedders.base import EmbedderResult
+from distllm_b200.embed.encoders.base import Encoder
+from distllm_b200.embed.poolers.base import Pooler
+from distllm_b200.utils import BaseConfig
+
+
+def _fused_kind(encoder: Encoder, pooler: Pooler) -> int | None:
+    if not hasattr(encoder, 'encode_pooled'):
+        return None
+    return getattr(pooler, 'native_pool_kind', None)
+
+
+@torch.no_grad()
+def compute_embeddings_device(
+    dataloader: DataLoader,
+    encoder: Encoder,
+    pooler: Pooler,
+    normalize: bool = False,
+    progress: bool = True,
+) -> torch.Tensor:
+    """Pooled embeddings for every row of ``dataloader.dataset`` as a device fp32 ``[N,H]`` tensor."""
+    num_embeddings = len(dataloader.dataset)
+    out = torch.empty((num_embeddings, encoder.embedding_size), dtype=torch.float32,
+                      device=encoder.device)
+    kind = _fused_kind(encoder, pooler)
+    idx = 0
+    for batch in tqdm(dataloader, disable=not progress):
+        inputs = batch.to(encoder.device, non_blocking=True)
+        batch_size = inputs['attention_mask'].shape[0]
+        if kind is not None:
+            encoder.encode_pooled(inputs, kind, normalize, out=out[idx : idx + batch_size])
+        else:
+            hidden = encoder.encode(inputs)
+            pooled = pooler.pool(hidden, inputs['attention_mask']).to(torch.float32)
+            if normalize:
+                pooled = _native.l2_normalize_(pooled.contiguous())
+            out[idx : idx + batch_size] = pooled
+        idx += batch_size
+    return out
+
+
+def compute_embeddings(
+    dataloader: DataLoader,
+    encoder: Encoder,
+    pooler: Pooler,
+    normalize: bool = False,
+) -> np.ndarray:
+    """Host ``[N,H]`` array in ``encoder.dtype`` (the reference's return contract, :80)."""
+    device_out = compute_embeddings_device(dataloader, encoder, pooler, normalize)
+    return device_out.to(encoder.dtype).cpu().numpy()
+
+
+class FullSequenceEmbedderConfig(BaseConfig):
+    """Configuration for the full sequence embedder."""
+
+    name: Literal['full_sequence'] = 'full_sequence'  # type: ignore[assignment]
+    normalize_embeddings: bool = Field(
+        False,
+        description='Whether to return normalized the embeddings.',
+    )
+
+
+class FullSequenceEmbedder:
+    """One pooled embedding per input sequence."""
+
+    def __init__(self, config: FullSequenceEmbedderConfig) -> None:
+        self.config = config
+
+    def embed(self, dataloader: DataLoader, encoder: Encoder, pooler: Pooler) -> EmbedderResult:
+        embeddings = compute_embeddings(
+            dataloader=dataloader,
+            encoder=encoder,
+            pooler=pooler,
+            normalize=self.config.normalize_embeddings,
+        )
+        return EmbedderResult(
+            embeddings=embeddings,
+            text=dataloader.dataset.data,
+            metadata=dataloader.dataset.metadata,
+        )

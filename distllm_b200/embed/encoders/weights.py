@@ -1,0 +1,135 @@
+"""Weight layout handed to ``b2e_encoder_create`` (the order IS the ABI, see include/b2e.h).
+
+BERT (``B2E_ARCH_BERT``), 5 + 12*L device tensors:
+
+    0 word_embeddings [V,H] f32      1 position_embeddings [P,H] f32   2 token_type_embeddings [T,H] f32
+    3 embeddings.LayerNorm.weight    4 embeddings.LayerNorm.bias       (f32 [H])
+    per layer l, base = 5 + 12*l:
+      +0 Wqkv [3H,H] bf16 (rows: query | key | value)   +1 bqkv [3H] f32
+      +2 Wo   [H,H]  bf16                               +3 bo   [H]  f32
+      +4 attention.output.LayerNorm.weight  +5 .bias    (f32)
+      +6 W1   [I,H]  bf16 (intermediate.dense)          +7 b1   [I]  f32
+      +8 W2   [H,I]  bf16 (output.dense)                +9 b2   [H]  f32
+      +10 output.LayerNorm.weight           +11 .bias   (f32)
+
+Names on the right are HF ``BertModel`` state-dict keys (transformers/models/bert/modeling_bert.py).
+Matrices keep nn.Linear's [out_features, in_features] layout, which is the K-major B operand the
+tcgen05 GEMM wants, so no transposes are needed.
+"""
+
+from __future__ import annotations
+
+from typing import Mapping
+
+import torch
+
+from distllm_b200 import _native
+
+
+def bert_desc(hf_config) -> _native.ModelDesc:
+    """Translate a HF ``BertConfig`` into the C ``B2EModelDesc``; reject what is not built."""
+    if getattr(hf_config, 'position_embedding_type', 'absolute') not in (None, 'absolute'):
+        raise NotImplementedError('only absolute position embeddings are supported')
+    act = getattr(hf_config, 'hidden_act', 'gelu')
+    if act != 'gelu':
+        raise NotImplementedError(f"hidden_act={act!r}: only erf-GELU ('gelu') is built")
+    heads = hf_config.num_attention_heads
+    return _native.ModelDesc(
+        arch=_native.ARCH_BERT,
+        num_layers=hf_config.num_hidden_layers,
+        hidden=hf_config.hidden_size,
+        heads=heads,
+        kv_heads=heads,
+        head_dim=hf_config.hidden_size // heads,
+        intermediate=hf_config.intermediate_size,
+        vocab=hf_config.vocab_size,
+        max_pos=hf_config.max_position_embeddings,
+        type_vocab=hf_config.type_vocab_size,
+        eps=float(hf_config.layer_norm_eps),
+        rope_theta=0.0,
+        sliding_window=0,
+        reserved=0,
+    )
+
+
+def bert_weight_list(
+    state_dict: Mapping[str, torch.Tensor],
+    num_layers: int,
+    device: torch.device,
+) -> list[torch.Tensor]:
+    """HF BertModel state dict -> contiguous device tensors in ABI order."""
+    sd = {k[5:] if k.startswith('bert.') else k: v for k, v in state_dict.items()}
+
+    def f32(key: str) -> torch.Tensor:
+        return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
+
+    def b16(t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+    out = [
+        f32('embeddings.word_embeddings.weight'),
+        f32('embeddings.position_embeddings.weight'),
+        f32('embeddings.token_type_embeddings.weight'),
+        f32('embeddings.LayerNorm.weight'),
+        f32('embeddings.LayerNorm.bias'),
+    ]
+    for layer in range(num_layers):
+        p = f'encoder.layer.{layer}.'
+        qkv_w = torch.cat([sd[p + f'attention.self.{n}.weight'] for n in ('query', 'key', 'value')])
+        qkv_b = torch.cat([sd[p + f'attention.self.{n}.bias'] for n in ('query', 'key', 'value')])
+        out += [
+            b16(qkv_w),
+            qkv_b.detach().to(device=device, dtype=torch.float32).contiguous(),
+            b16(sd[p + 'attention.output.dense.weight']),
+            f32(p + 'attention.output.dense.bias'),
+            f32(p + 'attention.output.LayerNorm.weight'),
+            f32(p + 'attention.output.LayerNorm.bias'),
+            b16(sd[p + 'intermediate.dense.weight']),
+            f32(p + 'intermediate.dense.bias'),
+            b16(sd[p + 'output.dense.weight']),
+            f32(p + 'output.dense.bias'),
+            f32(p + 'output.LayerNorm.weight'),
+            f32(p + 'output.LayerNorm.bias'),
+        ]
+    return out
+
+
+def random_bert_state_dict(hf_config, seed: int = 0, device: torch.device | str = 'cpu',
+                           std: float | None = None) -> dict[str, torch.Tensor]:
+    """Seeded random weights with HF BertModel names/shapes (normal(0, initializer_range),
+    LayerNorm weight 1 / bias 0 -- HF's ``_init_weights``), generated directly on ``device``.
+
+    Used for synthetic-weight benchmarking where no checkpoint can be downloaded.
+    """
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    std = hf_config.initializer_range if std is None else std
+    h, i = hf_config.hidden_size, hf_config.intermediate_size
+
+    def normal(*shape: int) -> torch.Tensor:
+        return torch.randn(*shape, generator=gen, device=device, dtype=torch.float32) * std
+
+    sd = {
+        'embeddings.word_embeddings.weight': normal(hf_config.vocab_size, h),
+        'embeddings.position_embeddings.weight': normal(hf_config.max_position_embeddings, h),
+        'embeddings.token_type_embeddings.weight': normal(hf_config.type_vocab_size, h),
+        'embeddings.LayerNorm.weight': torch.ones(h, device=device),
+        'embeddings.LayerNorm.bias': torch.zeros(h, device=device),
+    }
+    for layer in range(hf_config.num_hidden_layers):
+        p = f'encoder.layer.{layer}.'
+        for name, (o, k) in {
+            'attention.self.query': (h, h),
+            'attention.self.key': (h, h),
+            'attention.self.value': (h, h),
+            'attention.output.dense': (h, h),
+            'intermediate.dense': (i, h),
+            'output.dense': (h, i),
+        }.items():
+            sd[p + name + '.weight'] = normal(o, k)
+            # HF zero-initialises biases; small non-zero values exercise the bias epilogues
+            sd[p + name + '.bias'] = normal(o)
+        for name in ('attention.output.LayerNorm', 'output.LayerNorm'):
+            sd[p + name + '.weight'] = torch.ones(h, device=device)
+            sd[p + name + '.bias'] = torch.zeros(h, device=device)
+    return sd

@@ -1,0 +1,181 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (``/root/reference``) on CPU.
+
+Run in the authoring container only (the reference tree does not exist on the GPU box):
+
+    python oracle/make_golden.py
+
+What is recorded (all seeded, fp32, CPU):
+  pool_golden.npz      distllm.embed.poolers.mean.average_pool / last_token.last_token_pool on ragged
+                       batches (outputs + the mask after the in-place edit)
+  semantic_golden.npz  distllm.embed.embedders.semantic_chunk.calculate_distances_between_buffer and
+                       build_chunks on random embeddings, incl. 1- and 2-row documents
+  bert_tiny_golden.npz the reference's own AutoEncoder + poolers + compute_embeddings
+                       (distllm/embed/embedders/full_sequence.py:20-80) driven through a real DataLoader
+                       and tokenizer on a tiny seeded BERT checkpoint: token batches, first-batch hidden
+                       state, pooled embeddings (mean / mean+normalize / last_token)
+
+TEST INFRASTRUCTURE ONLY.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+REFERENCE = Path('/root/reference')
+GOLDEN = REPO / 'tests' / 'golden'
+
+TINY = dict(vocab_size=200, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+            intermediate_size=512, max_position_embeddings=64, type_vocab_size=2,
+            layer_norm_eps=1e-12, hidden_act='gelu', hidden_dropout_prob=0.0,
+            attention_probs_dropout_prob=0.0, initializer_range=0.05)
+TINY_SEED = 1234
+
+
+def weights_digest(sd: dict[str, torch.Tensor]) -> str:
+    h = hashlib.sha256()
+    for key in sorted(sd):
+        h.update(key.encode())
+        h.update(sd[key].detach().cpu().float().numpy().tobytes())
+    return h.hexdigest()
+
+
+def make_pool_golden() -> None:
+    from distllm.embed.poolers.last_token import last_token_pool
+    from distllm.embed.poolers.mean import average_pool
+
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    cases = {
+        'ragged': [20, 5, 1, 2, 11, 11, 19, 0],       # includes len 0 (index -1 wraps), 1, 2, dup lens
+        'full': [12, 12, 12],
+        'single': [9],
+        'left_padded_like': [7, 16, 16],               # last column set for some rows only
+    }
+    for name, lens in cases.items():
+        s = max(max(lens), 2)
+        b = len(lens)
+        emb = torch.randn(b, s, 256, generator=g)
+        mask = (torch.arange(s)[None, :] < torch.tensor(lens)[:, None]).long()
+        m1 = mask.clone()
+        pooled = average_pool(emb, m1)
+        out[f'{name}/emb'] = emb.numpy()
+        out[f'{name}/mask'] = mask.numpy()
+        out[f'{name}/mean'] = pooled.numpy()
+        out[f'{name}/mask_after'] = m1.numpy()
+        if min(lens) > 0:
+            out[f'{name}/last'] = last_token_pool(emb, mask.clone()).numpy()
+    # left padding: every row ends attended -> column S-1 branch of last_token_pool
+    emb = torch.randn(4, 10, 256, generator=g)
+    mask = (torch.arange(10)[None, :] >= torch.tensor([0, 3, 7, 9])[:, None]).long()
+    out['leftpad/emb'] = emb.numpy()
+    out['leftpad/mask'] = mask.numpy()
+    out['leftpad/last'] = last_token_pool(emb, mask.clone()).numpy()
+    np.savez_compressed(GOLDEN / 'pool_golden.npz', **out)
+
+
+def make_semantic_golden() -> None:
+    from distllm.embed.embedders.semantic_chunk import build_chunks
+    from distllm.embed.embedders.semantic_chunk import calculate_distances_between_buffer
+
+    rng = np.random.default_rng(11)
+    emb = rng.standard_normal((64, 256)).astype(np.float32)
+    # correlated neighbours so distances spread over (0, 1)
+    for i in range(1, 64):
+        emb[i] = 0.6 * emb[i - 1] + rng.uniform(0.1, 1.0) * emb[i]
+    doc_ranges = [(0, 25), (25, 26), (26, 28), (28, 64)]
+    out = {'emb': emb, 'doc_ranges': np.array(doc_ranges)}
+    for k, (lo, hi) in enumerate(doc_ranges):
+        d = calculate_distances_between_buffer(emb[lo:hi])
+        out[f'dist/{k}'] = d
+        for pct in (50, 90, 95):
+            out[f'groups/{k}/{pct}'] = np.array(build_chunks(d, pct))
+    np.savez_compressed(GOLDEN / 'semantic_golden.npz', **out)
+
+
+def make_bert_golden() -> None:
+    from torch.utils.data import DataLoader
+    from transformers import BertConfig
+    from transformers import BertModel
+    from transformers import BertTokenizerFast
+
+    from distllm.embed.datasets.utils import DataCollator
+    from distllm.embed.datasets.utils import InMemoryDataset
+    from distllm.embed.embedders.full_sequence import compute_embeddings
+    from distllm.embed.encoders.auto import AutoEncoder
+    from distllm.embed.encoders.auto import AutoEncoderConfig
+    from distllm.embed.poolers.last_token import LastTokenPooler
+    from distllm.embed.poolers.last_token import LastTokenPoolerConfig
+    from distllm.embed.poolers.mean import MeanPooler
+    from distllm.embed.poolers.mean import MeanPoolerConfig
+    from distllm_b200.embed.encoders.weights import random_bert_state_dict
+
+    cfg = BertConfig(**TINY)
+    sd = random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
+    model = BertModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith('pooler.') for k in missing), (missing, unexpected)
+    model.eval()
+
+    words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
+    vocab = ['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]
+    rng = np.random.default_rng(5)
+    n_texts = 14
+    lengths = [3, 17, 40, 1, 25, 25, 9, 62, 80, 12, 30, 2, 44, 7]  # 80 words -> truncated to 64 tokens
+    texts = [' '.join(rng.choice(words, size=n)) for n in lengths]
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp_path = Path(tmp)
+        (tmp_path / 'vocab.txt').write_text('\n'.join(vocab) + '\n')
+        tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+        model.save_pretrained(tmp_path / 'ckpt')
+        tok.save_pretrained(tmp_path / 'ckpt')
+
+        encoder = AutoEncoder(AutoEncoderConfig(
+            pretrained_model_name_or_path=str(tmp_path / 'ckpt'), quantization=False, eval_mode=True))
+        assert encoder.tokenizer.model_max_length == TINY['max_position_embeddings']
+
+        def loader() -> DataLoader:
+            return DataLoader(InMemoryDataset(texts), batch_size=4, num_workers=0,
+                              collate_fn=DataCollator(encoder.tokenizer))
+
+        out = {'weights_sha256': np.array(weights_digest(sd)), 'n_texts': np.array(n_texts)}
+        for i, batch in enumerate(loader()):
+            out[f'batch{i}/input_ids'] = batch['input_ids'].numpy()
+            out[f'batch{i}/attention_mask'] = batch['attention_mask'].numpy()
+            out[f'batch{i}/token_type_ids'] = batch['token_type_ids'].numpy()
+            if i == 0:
+                with torch.no_grad():
+                    out['batch0/hidden'] = encoder.encode(batch).numpy()
+        out['n_batches'] = np.array(i + 1)
+        mean = MeanPooler(MeanPoolerConfig())
+        last = LastTokenPooler(LastTokenPoolerConfig())
+        out['pooled/mean'] = compute_embeddings(loader(), encoder, mean)
+        out['pooled/mean_normalized'] = compute_embeddings(loader(), encoder, mean, normalize=True)
+        out['pooled/last_token'] = compute_embeddings(loader(), encoder, last)
+    np.savez_compressed(GOLDEN / 'bert_tiny_golden.npz', **out)
+
+
+def main() -> None:
+    if not REFERENCE.exists():
+        raise SystemExit('/root/reference is not available: golden vectors can only be (re)generated '
+                         'in the authoring container')
+    sys.path.insert(0, str(REFERENCE))
+    sys.path.insert(0, str(REPO))
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+    make_pool_golden()
+    make_semantic_golden()
+    make_bert_golden()
+    for f in sorted(GOLDEN.glob('*.npz')):
+        print(f.name, f.stat().st_size, 'bytes')
+
+
+if __name__ == '__main__':
+    main()

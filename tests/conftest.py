@@ -1,0 +1,63 @@
+"""Shared fixtures.  ``-m gpu`` tests need a B200; everything else runs on CPU."""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+GOLDEN = REPO / 'tests' / 'golden'
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA sm_100 device (run with -m gpu on a B200)')
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _native_library():
+    """Compile libb2e.so when missing or stale (nvcc cross-compiles without a GPU)."""
+    from distllm_b200.build import build_native
+
+    build_native()
+
+
+@pytest.fixture(scope='session')
+def pool_golden():
+    return np.load(GOLDEN / 'pool_golden.npz')
+
+
+@pytest.fixture(scope='session')
+def semantic_golden():
+    return np.load(GOLDEN / 'semantic_golden.npz')
+
+
+@pytest.fixture(scope='session')
+def bert_golden():
+    return np.load(GOLDEN / 'bert_tiny_golden.npz')
+
+
+@pytest.fixture(scope='session')
+def tiny_bert():
+    """(HF config, seeded state dict) of the tiny checkpoint the golden vectors were made with."""
+    from transformers import BertConfig
+
+    sys.path.insert(0, str(REPO / 'oracle'))
+    from oracle.make_golden import TINY
+    from oracle.make_golden import TINY_SEED
+
+    from distllm_b200.embed.encoders.weights import random_bert_state_dict
+
+    cfg = BertConfig(**TINY)
+    return cfg, random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
+
+
+def cosine_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))

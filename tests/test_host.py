@@ -1,0 +1,253 @@
+"""Host-side mirror of the reference's plugin surface: names, defaults, errors, file formats."""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+from distllm_b200.embed import get_dataset
+from distllm_b200.embed import get_embedder
+from distllm_b200.embed import get_pooler
+from distllm_b200.embed import get_writer
+from distllm_b200.embed.datasets.fasta import read_fasta
+from distllm_b200.embed.datasets.fasta import write_fasta
+from distllm_b200.embed.datasets.fasta import Sequence
+from distllm_b200.embed.datasets.jsonl_chunk import sentences_to_buffers
+from distllm_b200.embed.datasets.jsonl_chunk import split_by_sentence_tokenizer
+from distllm_b200.embed.embedders.base import EmbedderResult
+from distllm_b200.embed.embedders.semantic_chunk import build_chunks
+from distllm_b200.embed.embedders.semantic_chunk import document_ranges
+from distllm_b200.registry import RegistrySingleton
+from distllm_b200.registry import registry
+from distllm_b200.sharding import shard_range
+from distllm_b200.timer import TimeLogger
+from distllm_b200.timer import Timer
+from distllm_b200.utils import BaseConfig
+from distllm_b200.utils import batch_data
+
+
+def test_strategy_names_and_defaults():
+    import distllm_b200.embed.datasets as ds
+    import distllm_b200.embed.embedders as em
+    import distllm_b200.embed.encoders as en
+    import distllm_b200.embed.poolers as po
+    import distllm_b200.embed.writers as wr
+
+    assert set(po.STRATEGIES) == {'mean', 'last_token'}
+    assert set(em.STRATEGIES) == {'full_sequence', 'semantic_chunk'}
+    assert set(wr.STRATEGIES) == {'huggingface', 'numpy'}
+    assert {'jsonl', 'jsonl_chunk', 'fasta', 'sequence_per_line'} <= set(ds.STRATEGIES)
+    assert 'auto' in en.STRATEGIES
+
+    sc = get_embedder({'name': 'semantic_chunk'}).config
+    assert (sc.breakpoint_percentile_threshold, sc.chunk_batch_size, sc.min_chunk_length,
+            sc.normalize_embeddings) == (90, 8, 750, False)
+    jc = get_dataset({'name': 'jsonl_chunk'}).config
+    assert (jc.text_field, jc.num_data_workers, jc.batch_size, jc.pin_memory, jc.min_buffer_length,
+            jc.buffer_size) == ('text', 4, 8, True, 750, 1)
+    auto_cfg = en.AutoEncoderConfig(pretrained_model_name_or_path='x')
+    assert (auto_cfg.half_precision, auto_cfg.eval_mode, auto_cfg.compile_model,
+            auto_cfg.quantization, auto_cfg.tokenizer_name) == (False, True, False, True, None)
+    assert get_embedder({'name': 'full_sequence'}).config.normalize_embeddings is False
+    assert get_writer({'name': 'huggingface'}).config.num_proc is None
+
+
+@pytest.mark.parametrize('factory', [get_pooler, get_embedder, get_writer, get_dataset])
+def test_unknown_name_raises_value_error(factory):
+    with pytest.raises(ValueError, match='Unknown .* name: nope'):
+        factory({'name': 'nope'})
+
+
+def test_unknown_encoder_raises_value_error():
+    from distllm_b200.embed import get_encoder
+
+    with pytest.raises(ValueError, match='Unknown encoder name'):
+        get_encoder({'name': 'nope'})
+
+
+def test_config_yaml_json_roundtrip(tmp_path):
+    from distllm_b200.distributed_embedding import Config
+
+    cfg = Config(
+        input_dir=tmp_path, output_dir=tmp_path / 'out', glob_patterns=['*.jsonl'],
+        dataset_config={'name': 'jsonl_chunk', 'batch_size': 512, 'buffer_size': 4},
+        encoder_config={'name': 'auto', 'pretrained_model_name_or_path': 'pritamdeka/S-PubMedBert-MS-MARCO',
+                        'quantization': False},
+        pooler_config={'name': 'mean'},
+        embedder_config={'name': 'semantic_chunk', 'chunk_batch_size': 512},
+        writer_config={'name': 'numpy'},
+        compute_config={'name': 'workstation', 'available_accelerators': 8},
+    )
+    cfg.write_yaml(tmp_path / 'c.yaml')
+    back = Config.from_yaml(tmp_path / 'c.yaml')
+    assert back == cfg
+    assert type(back.dataset_config).__name__ == 'JsonlChunkDatasetConfig'
+    assert type(back.embedder_config).__name__ == 'SemanticChunkEmbedderConfig'
+    cfg.write_json(tmp_path / 'c.json')
+    assert json.loads((tmp_path / 'c.json').read_text())['pooler_config']['name'] == 'mean'
+
+    class Tiny(BaseConfig):
+        x: int = 3
+
+    Tiny(x=5).write_json(tmp_path / 't.json')
+    assert Tiny.from_json(tmp_path / 't.json').x == 5
+
+
+def test_batch_data():
+    assert batch_data(list(range(7)), 3) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert batch_data([], 3) == []
+    assert batch_data([1, 2], 5) == [[1, 2]]
+
+
+def test_timer_lines_parse_back(tmp_path, capsys):
+    with Timer('computed-embeddings', 'file.jsonl'):
+        pass
+    t = Timer('loaded-encoder').start()
+    with pytest.raises(RuntimeError):
+        _ = t.elapsed_ns
+    t.stop()
+    out = capsys.readouterr().out
+    assert out.count('[timer]') == 2
+    log = tmp_path / 'log.txt'
+    log.write_text('noise\n' + out)
+    stats = TimeLogger().parse_logs(log)
+    assert [list(s.tags) for s in stats] == [['computed-embeddings', 'file.jsonl'], ['loaded-encoder']]
+    assert float(stats[0].elapsed_s) >= 0.0
+    assert float(stats[0].end_unix) >= float(stats[0].start_unix)
+
+
+def test_registry_warm_start_and_eviction():
+    assert RegistrySingleton() is registry
+    registry.clear()
+    built, closed = [], []
+
+    def factory(**kw):
+        built.append(kw)
+        return dict(kw)
+
+    registry.register(factory, shutdown_callback=closed.append)
+    a = registry.get(factory, name='auto', path='m1')
+    assert registry.get(factory, name='auto', path='m1') is a and len(built) == 1
+    b = registry.get(factory, name='auto', path='m2')
+    assert b is not a and len(built) == 2 and closed == [a]
+    with pytest.raises(ValueError, match='not registered'):
+        registry.get(lambda: None)
+    registry.clear()
+    assert closed[-1] is b
+
+
+def test_sentence_split_is_lossless_and_buffers_window():
+    text = 'Alpha beta gamma.  Delta epsilon!\nZeta eta? Theta iota.'
+    parts = split_by_sentence_tokenizer()(text)
+    assert ''.join(parts) == text
+    assert len(parts) == 4 and parts[0] == 'Alpha beta gamma.  '
+    bufs = sentences_to_buffers(list('abcde'), 1)
+    assert bufs == ['ab', 'abc', 'bcd', 'cde', 'de']
+    assert sentences_to_buffers(list('abc'), 4) == ['abc'] * 3
+    assert sentences_to_buffers([], 2) == []
+
+
+def test_jsonl_chunk_rows_and_filter(tmp_path):
+    class FakeEncoder:
+        tokenizer = staticmethod(lambda batch, **kw: batch)
+
+    sent = 'Sentence number %d has quite a few words in it. '
+    doc = ''.join(sent % i for i in range(12))
+    f = tmp_path / 'd.jsonl'
+    f.write_text('\n'.join(json.dumps({'text': doc, 'path': f'p{i}'}) for i in range(2)))
+    ds = get_dataset({'name': 'jsonl_chunk', 'buffer_size': 2, 'min_buffer_length': 150,
+                      'num_data_workers': 0, 'pin_memory': False})
+    loader = ds.get_dataloader(f, FakeEncoder())
+    data, meta = loader.dataset.data, loader.dataset.metadata
+    # buffers at the document edges (3 sentences ~ 147 chars) are filtered, the rest kept
+    assert len(data) == len(meta) == 2 * 10
+    assert all(len(d) > 150 for d in data)
+    assert meta[0]['path'] == 'p0' and meta[-1]['path'] == 'p1' and 'sentence' in meta[0]
+    assert document_ranges(meta) == [(0, 10), (10, 20)]
+    with pytest.raises(ValueError, match='Metadata is empty'):
+        f.write_text(json.dumps({'text': doc}))
+        ds.get_dataloader(f, FakeEncoder())
+
+
+def test_fasta_roundtrip(tmp_path):
+    f = tmp_path / 'x.fasta'
+    write_fasta([Sequence('MKV', 'a b'), Sequence('ACDE', 't2')], f)
+    with open(f, 'a') as h:
+        h.write('>t3\nAA\nCC\n')
+    recs = read_fasta(f)
+    assert [(r.tag, r.sequence) for r in recs] == [('a b', 'MKV'), ('t2', 'ACDE'), ('t3', 'AACC')]
+
+
+def test_numpy_writer_write_and_merge(tmp_path):
+    w = get_writer({'name': 'numpy'})
+    dirs = []
+    for k in range(2):
+        d = tmp_path / f'r{k}'
+        d.mkdir()
+        w.write(d, EmbedderResult(np.full((3, 4), k, np.float32), [f't{k}{i}' for i in range(3)],
+                                  [{'path': f'p{k}'}] * 3))
+        dirs.append(d)
+    out = tmp_path / 'merged'
+    out.mkdir()
+    w.merge(dirs, out)
+    assert np.load(out / 'embeddings.npy').shape == (6, 4)
+    assert list(np.load(out / 'text.npy'))[3] == 't10'
+    assert np.load(out / 'metadata.npy', allow_pickle=True)[5]['path'] == 'p1'
+
+
+def test_huggingface_writer_schema(tmp_path):
+    from datasets import Dataset
+
+    w = get_writer({'name': 'huggingface'})
+    w.write(tmp_path / 'ds', EmbedderResult(np.arange(8, dtype=np.float32).reshape(2, 4), ['a', 'b'],
+                                            [{'path': 'p', 'k': 1}, {'path': 'q', 'k': 2}]))
+    ds = Dataset.load_from_disk(tmp_path / 'ds')
+    assert ds.column_names == ['text', 'embeddings', 'path', 'k']
+    assert ds[1]['embeddings'] == [4.0, 5.0, 6.0, 7.0] and ds[1]['path'] == 'q'
+
+
+def test_build_chunks_matches_reference_groups(semantic_golden):
+    """The product's vectorised build_chunks against groups produced by the reference."""
+    for k in range(len(semantic_golden['doc_ranges'])):
+        for pct in (50, 90, 95):
+            want = [tuple(int(v) for v in g) for g in semantic_golden[f'groups/{k}/{pct}']]
+            assert build_chunks(semantic_golden[f'dist/{k}'], pct) == want
+    assert build_chunks(np.zeros(0), 90) == [(0, 0)]
+
+
+def test_shard_range_partitions_everything():
+    for n in (0, 1, 7, 8, 9, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_cli_embed_flags_match_reference():
+    import typer
+
+    from distllm_b200.cli import app
+
+    group = typer.main.get_command(app)
+    embed = group.commands['embed']
+    opts = {o for p in embed.params for o in p.opts}
+    want = {'--encoder_name': '-mn', '--pretrained_model_name_or_path': '-m', '--data_path': '-d',
+            '--data_extension': '-de', '--output_path': '-o', '--dataset_name': '-dn',
+            '--batch_size': '-b', '--chunk_batch_size': '-cb', '--buffer_size': '-bs',
+            '--pooler_name': '-pn', '--embedder_name': '-en', '--writer_name': '-wn',
+            '--half_precision': '-hp', '--eval_mode': '-em', '--compile_model': '-cm',
+            '--quantization': '-q'}
+    for long, short in want.items():
+        assert long in opts and short in opts, (long, short)
+    defaults = {p.name: p.default for p in embed.params}
+    assert (defaults['dataset_name'], defaults['batch_size'], defaults['pooler_name'],
+            defaults['embedder_name'], defaults['writer_name'], defaults['quantization']) == (
+        'jsonl', 1, 'mean', 'full_sequence', 'huggingface', False)
+    merge_opts = {o for p in group.commands['merge'].params for o in p.opts}
+    assert {'--writer_name', '--num_proc', '--dataset_dir', '--output_dir'} <= merge_opts

@@ -1,0 +1,117 @@
+"""Pin the CPU oracle: against vectors produced by the unmodified reference (tests/golden, made by
+oracle/make_golden.py) and against HuggingFace BertModel, which holds the reference's arithmetic."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert as obert
+from oracle import pooling as opool
+from oracle import semantic as osem
+from oracle.make_golden import weights_digest
+
+POOL_CASES = ['ragged', 'full', 'single', 'left_padded_like']
+
+
+@pytest.mark.parametrize('case', POOL_CASES)
+def test_average_pool_matches_reference(pool_golden, case):
+    emb = torch.from_numpy(pool_golden[f'{case}/emb'])
+    mask = torch.from_numpy(pool_golden[f'{case}/mask']).clone()
+    got = opool.average_pool(emb, mask)
+    np.testing.assert_allclose(got.numpy(), pool_golden[f'{case}/mean'], rtol=1e-5, atol=1e-6)
+    # the in-place edit of the caller's mask is part of the contract
+    np.testing.assert_array_equal(mask.numpy(), pool_golden[f'{case}/mask_after'])
+
+
+@pytest.mark.parametrize('case', ['full', 'single', 'left_padded_like', 'leftpad'])
+def test_last_token_pool_matches_reference(pool_golden, case):
+    emb = torch.from_numpy(pool_golden[f'{case}/emb'])
+    mask = torch.from_numpy(pool_golden[f'{case}/mask'])
+    got = opool.last_token_pool(emb, mask)
+    np.testing.assert_array_equal(got.numpy(), pool_golden[f'{case}/last'])
+
+
+def test_mean_quirk_is_cross_row(pool_golden):
+    """mean.py:36 clears column len_j-1 of EVERY row: row 0 (len 20) loses columns 4, 0, 1, 10, 18
+    and, through the zero-length row's index -1, its own last column."""
+    after = pool_golden['ragged/mask_after']
+    assert after[0].sum() == 20 - len({0, 19, 4, 1, 10, 18})
+
+
+def test_semantic_distances_and_groups_match_reference(semantic_golden):
+    emb = semantic_golden['emb']
+    for k, (lo, hi) in enumerate(semantic_golden['doc_ranges']):
+        d = osem.calculate_distances_between_buffer(emb[lo:hi])
+        assert d.dtype == np.float64
+        np.testing.assert_allclose(d, semantic_golden[f'dist/{k}'], rtol=0, atol=2e-7)
+        for pct in (50, 90, 95):
+            groups = osem.build_chunks(semantic_golden[f'dist/{k}'], pct)
+            assert [tuple(g) for g in semantic_golden[f'groups/{k}/{pct}']] == groups
+
+
+def test_semantic_edge_documents(semantic_golden):
+    # 1-row document: no distances -> the empty group (0, 0); 2-row document: one distance,
+    # never strictly above its own percentile -> a single group
+    assert osem.build_chunks(np.zeros(0), 90) == [(0, 0)]
+    assert [tuple(g) for g in semantic_golden['groups/1/90']] == [(0, 0)]
+    assert [tuple(g) for g in semantic_golden['groups/2/90']] == [(0, 2)]
+
+
+def test_tiny_weights_are_reproducible(bert_golden, tiny_bert):
+    _, sd = tiny_bert
+    assert weights_digest(sd) == str(bert_golden['weights_sha256'])
+
+
+def _batches(golden):
+    for i in range(int(golden['n_batches'])):
+        yield {k: torch.from_numpy(golden[f'batch{i}/{k}'])
+               for k in ('input_ids', 'attention_mask', 'token_type_ids')}
+
+
+def test_oracle_forward_matches_reference_hidden(bert_golden, tiny_bert):
+    cfg, sd = tiny_bert
+    batch = next(_batches(bert_golden))
+    hidden = obert.bert_forward(sd, cfg, batch['input_ids'], batch['attention_mask'],
+                                batch['token_type_ids'])
+    np.testing.assert_allclose(hidden.numpy(), bert_golden['batch0/hidden'], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('kind', ['mean', 'mean_normalized', 'last_token'])
+def test_oracle_loop_matches_reference_embeddings(bert_golden, tiny_bert, kind):
+    """oracle forward + oracle pooler + oracle loop == the reference's compute_embeddings output."""
+    cfg, sd = tiny_bert
+
+    def encode(batch):
+        return obert.bert_forward(sd, cfg, batch['input_ids'], batch['attention_mask'],
+                                  batch['token_type_ids'])
+
+    pool = opool.last_token_pool if kind == 'last_token' else opool.average_pool
+    got = opool.compute_embeddings(_batches(bert_golden), encode, pool,
+                                   do_normalize=(kind == 'mean_normalized'))
+    ref = bert_golden[f'pooled/{kind}']
+    assert got.shape == ref.shape == (int(bert_golden['n_texts']), cfg.hidden_size)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_oracle_forward_matches_hf_bertmodel(tiny_bert):
+    """Independent of the fixtures: the restatement against transformers' BertModel, ragged batch."""
+    from transformers import BertModel
+
+    cfg, sd = tiny_bert
+    model = BertModel(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(5, cfg.vocab_size, (5, 33), generator=g)
+    lens = torch.tensor([33, 1, 17, 2, 30])
+    mask = (torch.arange(33)[None] < lens[:, None]).long()
+    types = torch.randint(0, 2, (5, 33), generator=g)
+    with torch.no_grad():
+        ref = model(input_ids=ids, attention_mask=mask, token_type_ids=types,
+                    output_hidden_states=True).hidden_states
+    got = obert.bert_forward(sd, cfg, ids, mask, types, return_all=True)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=2e-5)
