@@ -1,0 +1,194 @@
+"""-m gpu: each native kernel, called through the C ABI, against a torch fp32 reference or the
+golden vectors produced by the reference.  Tolerances: bf16 outputs carry 2^-9 relative rounding."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from distllm_b200 import _native as nv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail('-m gpu tests need a CUDA device')
+    return torch.device('cuda:0')
+
+
+GEMM_SHAPES = [(128, 256, 64), (300, 768, 768), (1000, 2304, 768), (517, 3072, 768), (517, 768, 3072),
+               (200, 384, 128), (1, 768, 768), (20000, 768, 768)]
+
+
+@pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
+@pytest.mark.parametrize('epi', [nv.EPI_BIAS, nv.EPI_BIAS_GELU, nv.EPI_BIAS_RESID])
+def test_gemm_epilogues(dev, m, n, k, epi):
+    g = torch.Generator(device=dev).manual_seed(m * 7 + n + k + epi)
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=dev, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(n, device=dev, generator=g) * 0.1
+    resid = torch.randn(m, n, device=dev, generator=g).bfloat16()
+    out = nv.gemm_bf16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
+    ref = a.float() @ w.float().T + bias
+    if epi == nv.EPI_BIAS_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == nv.EPI_BIAS_RESID:
+        ref = ref + resid.float()
+    assert out.dtype == torch.bfloat16 and out.shape == (m, n)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_rejects_bad_shapes(dev):
+    a = torch.zeros(8, 100, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(128, 100, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(nv.NativeError, match='K=100'):
+        nv.gemm_bf16(a, w, torch.zeros(128, device=dev))
+    with pytest.raises(nv.NativeError, match='N=100'):
+        nv.gemm_bf16(torch.zeros(8, 64, device=dev, dtype=torch.bfloat16),
+                     torch.zeros(100, 64, device=dev, dtype=torch.bfloat16), torch.zeros(100, device=dev))
+
+
+def ref_attention(qkv, mask, b, s, heads):
+    q, k, v = qkv.float().view(b, s, 3, heads, 64).unbind(2)
+    q, k, v = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    scores = q @ k.transpose(-1, -2) / 8.0
+    bias = torch.zeros(b, 1, 1, s, device=qkv.device)
+    bias.masked_fill_(mask.view(b, 1, 1, s) == 0, torch.finfo(torch.float32).min)
+    p = torch.softmax(scores + bias, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(b * s, heads * 64)
+
+
+@pytest.mark.parametrize('b,s,heads,ragged', [(2, 128, 2, False), (2, 512, 12, False), (3, 200, 12, True),
+                                              (2, 512, 12, True), (4, 37, 4, True), (5, 1, 4, False),
+                                              (2, 129, 4, True), (1, 384, 12, True)])
+def test_attention_matches_reference(dev, b, s, heads, ragged):
+    g = torch.Generator(device=dev).manual_seed(b * 1000 + s)
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).bfloat16()
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    if ragged:
+        for i in range(b):
+            mask[i, max(1, s - 17 * (i + 1)):] = 0
+    ctx = nv.attention_d64(qkv, mask, b, s, heads)
+    torch.testing.assert_close(ctx.float(), ref_attention(qkv, mask, b, s, heads), rtol=2e-2, atol=1e-2)
+
+
+def test_attention_mask_with_holes_and_fully_masked_row(dev):
+    """Arbitrary 0/1 masks (left padding, holes); an all-zero mask degenerates to a uniform
+    distribution over the S keys exactly like HF's additive most-negative-finite mask."""
+    b, s, heads = 3, 96, 4
+    g = torch.Generator(device=dev).manual_seed(9)
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).bfloat16()
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    mask[0, :40] = 0            # left padding
+    mask[1, 10:20] = 0          # a hole
+    mask[2, :] = 0              # nothing attended
+    ctx = nv.attention_d64(qkv, mask, b, s, heads)
+    ref = ref_attention(qkv, mask, b, s, heads)
+    assert torch.isfinite(ctx.float()).all()
+    torch.testing.assert_close(ctx.float(), ref, rtol=2e-2, atol=1e-2)
+
+
+def test_attention_rejects_long_sequences(dev):
+    with pytest.raises(nv.NativeError, match='S=513'):
+        nv.attention_d64(torch.zeros(513, 192, device=dev, dtype=torch.bfloat16),
+                         torch.ones(1, 513, dtype=torch.int64, device=dev), 1, 513, 1)
+
+
+@pytest.mark.parametrize('h', [256, 768, 1024, 1280])
+def test_layernorm(dev, h):
+    g = torch.Generator(device=dev).manual_seed(h)
+    x = (torch.randn(1003, h, device=dev, generator=g) * 3 + 1).bfloat16()
+    gamma = torch.randn(h, device=dev, generator=g)
+    beta = torch.randn(h, device=dev, generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (h,), gamma, beta, 1e-12)
+    torch.testing.assert_close(nv.layernorm(x, gamma, beta, 1e-12, torch.float32), ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nv.layernorm(x, gamma, beta, 1e-12, torch.bfloat16).float(), ref,
+                               rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('case', ['ragged', 'full', 'single', 'left_padded_like'])
+def test_pool_mean_matches_reference_vectors(dev, pool_golden, case):
+    emb = torch.from_numpy(pool_golden[f'{case}/emb']).to(dev)
+    mask = torch.from_numpy(pool_golden[f'{case}/mask']).to(dev)
+    got = nv.pool_mean(emb, mask)
+    np.testing.assert_allclose(got.cpu().numpy(), pool_golden[f'{case}/mean'], rtol=1e-5, atol=1e-6)
+    # the caller's mask is rewritten exactly like distllm/embed/poolers/mean.py:35-36
+    np.testing.assert_array_equal(mask.cpu().numpy(), pool_golden[f'{case}/mask_after'])
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_pool_mean_half_inputs(dev, dtype):
+    from oracle import pooling as opool
+
+    g = torch.Generator().manual_seed(4)
+    emb = torch.randn(6, 50, 512, generator=g).to(dtype)
+    lens = torch.tensor([50, 3, 17, 17, 1, 44])
+    mask = (torch.arange(50)[None] < lens[:, None]).long()
+    ref = opool.average_pool(emb.float(), mask.clone())
+    got = nv.pool_mean(emb.to(dev), mask.to(dev))
+    assert got.dtype == torch.float32
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_pool_mean_per_row_mode_and_no_mutation(dev):
+    g = torch.Generator().manual_seed(5)
+    emb = torch.randn(4, 30, 256, generator=g)
+    lens = [30, 7, 12, 2]
+    mask = (torch.arange(30)[None] < torch.tensor(lens)[:, None]).long()
+    ref = torch.stack([emb[i, 1:n - 1].mean(0) if n > 2 else torch.zeros(256) for i, n in enumerate(lens)])
+    m = mask.to(dev)
+    got = nv.pool_mean(emb.to(dev), m, nv.POOL_MEAN_PER_ROW, mutate_mask=False)
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=1e-6)
+    assert torch.equal(m.cpu(), mask)
+
+
+@pytest.mark.parametrize('case', ['full', 'single', 'left_padded_like', 'leftpad'])
+def test_pool_last_token_matches_reference_vectors(dev, pool_golden, case):
+    emb = torch.from_numpy(pool_golden[f'{case}/emb']).to(dev)
+    mask = torch.from_numpy(pool_golden[f'{case}/mask']).to(dev)
+    got = nv.pool_last_token(emb, mask)
+    np.testing.assert_array_equal(got.cpu().numpy(), pool_golden[f'{case}/last'])
+
+
+def test_adjacent_cosine_matches_reference_vectors(dev, semantic_golden):
+    emb = torch.from_numpy(semantic_golden['emb']).to(dev)
+    ranges = [tuple(r) for r in semantic_golden['doc_ranges']]
+    doc_id = torch.empty(len(emb), dtype=torch.int32)
+    for k, (lo, hi) in enumerate(ranges):
+        doc_id[lo:hi] = k
+    d = nv.adjacent_cosine_dist(emb, doc_id.to(dev)).cpu().numpy()
+    for k, (lo, hi) in enumerate(ranges):
+        np.testing.assert_allclose(d[lo:hi - 1], semantic_golden[f'dist/{k}'], rtol=0, atol=5e-7)
+        if hi < len(emb):
+            assert np.isnan(d[hi - 1]), 'pairs across a document boundary must be NaN'
+    # no doc ids: plain consecutive distances; 0/1-row inputs: nothing to compute
+    plain = nv.adjacent_cosine_dist(emb).cpu().numpy()
+    assert not np.isnan(plain).any() and plain.shape == (len(emb) - 1,)
+    assert nv.adjacent_cosine_dist(emb[:1]).shape == (0,)
+
+
+def test_product_split_equals_oracle_split_on_same_embeddings(dev, semantic_golden):
+    """Discrete output: on identical embeddings the native distance kernel + host percentile split
+    must give exactly the reference's row groups."""
+    from distllm_b200.embed.embedders.semantic_chunk import build_chunks
+    from oracle import semantic as osem
+
+    emb = semantic_golden['emb']
+    ranges = [tuple(int(v) for v in r) for r in semantic_golden['doc_ranges']]
+    dev_emb = torch.from_numpy(emb).to(dev)
+    for pct in (50, 90, 95):
+        got = []
+        for lo, hi in ranges:
+            d = nv.adjacent_cosine_dist(dev_emb[lo:hi].contiguous()).cpu().numpy().astype(np.float64)
+            got.extend((lo + s, lo + e) for s, e in build_chunks(d, pct))
+        assert got == osem.split_rows(emb, ranges, pct)
+
+
+def test_l2_normalize(dev):
+    x = torch.randn(33, 768, device=dev)
+    x[5] = 0
+    ref = torch.nn.functional.normalize(x, p=2, dim=-1)
+    torch.testing.assert_close(nv.l2_normalize_(x.clone()), ref, rtol=1e-6, atol=1e-7)

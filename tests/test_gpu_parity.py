@@ -1,0 +1,241 @@
+"""-m gpu: the CUDA path against the CPU oracle / the reference's golden vectors.
+
+north_star tolerance: pooled embeddings within 1e-3 cosine of the reference's fp32 CPU encoder
+(the native path multiplies in bf16 with fp32 accumulation)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+from transformers import BatchEncoding
+from transformers import BertConfig
+
+from distllm_b200 import _native as nv
+from distllm_b200.embed.encoders.auto import AutoEncoder
+from distllm_b200.embed.encoders.native import NativeBertEncoder
+from distllm_b200.embed.encoders.weights import random_bert_state_dict
+from distllm_b200.embed import get_embedder
+from distllm_b200.embed import get_pooler
+from oracle import bert as obert
+from oracle import pooling as opool
+
+from conftest import cosine_rows
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-3
+
+
+class TokenBatches(torch.utils.data.Dataset):
+    """Pre-tokenised batches behind the DataLoader interface the embedders consume."""
+
+    def __init__(self, batches):
+        self.batches = batches
+        self.data = [f'row{i}' for i in range(sum(len(b['input_ids']) for b in batches))]
+        self.metadata = None
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, i):
+        return BatchEncoding(self.batches[i])
+
+
+def loader_of(batches):
+    ds = TokenBatches(batches)
+    return torch.utils.data.DataLoader(ds, batch_size=None, sampler=range(len(batches)))
+
+
+def golden_batches(golden):
+    return [{k: torch.from_numpy(golden[f'batch{i}/{k}']) for k in ('input_ids', 'attention_mask', 'token_type_ids')}
+            for i in range(int(golden['n_batches']))]
+
+
+@pytest.fixture(scope='module')
+def tiny_native(tiny_bert):
+    cfg, sd = tiny_bert
+    enc = NativeBertEncoder(cfg, sd)
+    yield enc
+    enc.close()
+
+
+def test_hidden_state_matches_reference(tiny_native, bert_golden):
+    b = golden_batches(bert_golden)[0]
+    hidden = tiny_native.encode(b['input_ids'], b['attention_mask'], b['token_type_ids']).cpu().numpy()
+    ref = bert_golden['batch0/hidden']
+    assert hidden.shape == ref.shape
+    cos = cosine_rows(hidden.reshape(-1, ref.shape[-1]), ref.reshape(-1, ref.shape[-1]))
+    assert cos.min() > 1 - COS_TOL, cos.min()
+    assert np.abs(hidden - ref).max() < 0.15  # post-LayerNorm values are O(1)
+
+
+@pytest.mark.parametrize('kind,pooler,normalize', [('mean', 'mean', False), ('mean_normalized', 'mean', True),
+                                                   ('last_token', 'last_token', False)])
+@pytest.mark.parametrize('fused', [True, False])
+def test_embedder_matches_reference_embeddings(tiny_native, bert_golden, kind, pooler, normalize, fused):
+    """full_sequence embedder through the plugin API == the reference's compute_embeddings output,
+    both via the fused encode_pooled path and via encode() + Pooler.pool()."""
+    encoder = AutoEncoder.from_native(tiny_native)
+    if not fused:
+        class Unfused:  # hides encode_pooled so the embedder takes the generic path
+            dtype, device, embedding_size = encoder.dtype, encoder.device, encoder.embedding_size
+            tokenizer = None
+            encode = staticmethod(encoder.encode)
+        encoder = Unfused()
+    embedder = get_embedder({'name': 'full_sequence', 'normalize_embeddings': normalize})
+    result = embedder.embed(loader_of(golden_batches(bert_golden)), encoder, get_pooler({'name': pooler}))
+    ref = bert_golden[f'pooled/{kind}']
+    assert result.embeddings.shape == ref.shape and result.embeddings.dtype == np.float32
+    cos = cosine_rows(result.embeddings, ref)
+    assert cos.min() > 1 - COS_TOL, cos
+    if normalize:
+        np.testing.assert_allclose(np.linalg.norm(result.embeddings, axis=-1), 1.0, atol=1e-5)
+
+
+def test_fused_pool_does_not_touch_the_mask_but_pooler_does(tiny_native, bert_golden):
+    b = golden_batches(bert_golden)[1]
+    mask = b['attention_mask'].cuda()
+    keep = mask.clone()
+    tiny_native.encode_pooled(b['input_ids'], mask, b['token_type_ids'], nv.POOL_MEAN_REF, False)
+    assert torch.equal(mask, keep)
+    hidden = tiny_native.encode(b['input_ids'], mask, b['token_type_ids'])
+    get_pooler({'name': 'mean'}).pool(hidden, mask)
+    ref_mask = b['attention_mask'].clone()
+    opool.average_pool(torch.zeros(*ref_mask.shape, 1), ref_mask)
+    assert torch.equal(mask.cpu(), ref_mask)
+
+
+def test_embed_host_equals_device_path_bitwise(tiny_native, bert_golden):
+    batches = golden_batches(bert_golden)
+    s = max(b['input_ids'].shape[1] for b in batches)
+    b0 = batches[2]  # one batch, fed as host tensors
+    ids, mask, types = (b0[k].contiguous().pin_memory() for k in ('input_ids', 'attention_mask', 'token_type_ids'))
+    host = tiny_native.embed_host(ids, mask, types, batch=ids.shape[0], pool_kind=nv.POOL_MEAN_REF, normalize=False)
+    devp = tiny_native.encode_pooled(ids, mask, types, nv.POOL_MEAN_REF, False)
+    torch.cuda.synchronize()
+    assert torch.equal(host, devp.cpu())
+    # several batches in one call: batch composition (hence the quirk) follows `batch`
+    n = 2 * ids.shape[0]
+    ids2, mask2, types2 = (torch.cat([t, t]).contiguous() for t in (ids, mask, types))
+    host2 = tiny_native.embed_host(ids2, mask2, types2, batch=ids.shape[0], pool_kind=nv.POOL_MEAN_REF, normalize=False)
+    assert torch.equal(host2[: n // 2], host) and torch.equal(host2[n // 2:], host)
+    assert s >= 1
+
+
+@pytest.fixture(scope='module')
+def base_model():
+    """BERT-base shape (S-PubMedBert-MS-MARCO: L=12, H=768, 12 heads, I=3072), seeded random weights."""
+    cfg = BertConfig(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                     intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2,
+                     layer_norm_eps=1e-12, initializer_range=0.02)
+    sd = random_bert_state_dict(cfg, seed=0, device='cpu')
+    enc = NativeBertEncoder(cfg, sd)
+    yield cfg, sd, enc
+    enc.close()
+
+
+def test_bert_base_pooled_vs_oracle(base_model):
+    cfg, sd, enc = base_model
+    g = torch.Generator().manual_seed(1)
+    b, s = 6, 128
+    ids = torch.randint(7, cfg.vocab_size, (b, s), generator=g)
+    lens = torch.tensor([128, 128, 64, 9, 100, 31])
+    mask = (torch.arange(s)[None] < lens[:, None]).long()
+    hidden_ref = obert.bert_forward(sd, cfg, ids, mask)
+    for kind, pool in ((nv.POOL_MEAN_REF, opool.average_pool), (nv.POOL_LAST_TOKEN, opool.last_token_pool)):
+        ref = pool(hidden_ref, mask.clone()).numpy()
+        got = enc.encode_pooled(ids, mask, None, kind, False).cpu().numpy()
+        cos = cosine_rows(got, ref)
+        assert cos.min() > 1 - COS_TOL, (kind, cos)
+    hidden = enc.encode(ids, mask).cpu().numpy()
+    valid = mask.bool().numpy()
+    cos_tok = cosine_rows(hidden[valid], hidden_ref.numpy()[valid])
+    assert cos_tok.min() > 1 - COS_TOL, cos_tok.min()
+
+
+def test_full_size_properties(base_model):
+    """BASELINE config C2 sizes (S=512, batch cut to 64 rows): properties that need no oracle."""
+    cfg, _, enc = base_model
+    g = torch.Generator().manual_seed(2)
+    b, s = 64, 512
+    ids = torch.randint(7, cfg.vocab_size, (b, s), generator=g).cuda()
+    lens = torch.randint(64, 513, (b,), generator=g)
+    lens[0] = 512
+    mask = (torch.arange(s)[None] < lens[:, None]).long().cuda()
+    a = enc.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, True)
+    # determinism
+    assert torch.equal(a, enc.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, True))
+    # unit norm
+    torch.testing.assert_close(a.norm(dim=-1), torch.ones(b, device=a.device), rtol=0, atol=1e-5)
+    # rows are independent: permuting the batch permutes the result bit for bit
+    perm = torch.randperm(b, generator=g).cuda()
+    assert torch.equal(enc.encode_pooled(ids[perm], mask[perm], None, nv.POOL_MEAN_PER_ROW, True), a[perm])
+    # padding invariance: a sequence alone at its own length == inside the padded batch
+    i = 5
+    n = int(lens[i])
+    alone = enc.encode_pooled(ids[i:i + 1, :n].contiguous(), mask[i:i + 1, :n].contiguous(), None,
+                              nv.POOL_MEAN_PER_ROW, True)
+    assert torch.nn.functional.cosine_similarity(alone, a[i:i + 1]).item() > 1 - 1e-5
+    # reference-quirk pooling on an unpadded batch == "drop first and last token" per row
+    full = torch.ones(8, s, dtype=torch.int64, device='cuda')
+    q = enc.encode_pooled(ids[:8], full, None, nv.POOL_MEAN_REF, False)
+    p = enc.encode_pooled(ids[:8], full, None, nv.POOL_MEAN_PER_ROW, False)
+    assert torch.equal(q, p)
+
+
+def test_semantic_chunk_embedder_end_to_end(tmp_path, tiny_bert, tiny_native):
+    """jsonl_chunk dataset -> semantic_chunk embedder through the plugin API with a real tokenizer.
+    The split is checked against the oracle on the SAME pass-1 embeddings (exact), the final chunk
+    embeddings against the oracle forward (cosine)."""
+    import json
+
+    from transformers import BertTokenizerFast
+
+    from distllm_b200.embed import get_dataset
+    from distllm_b200.embed.embedders import semantic_chunk as sc
+    from distllm_b200.embed.embedders.full_sequence import compute_embeddings_device
+    from oracle import semantic as osem
+    from oracle.make_golden import TINY
+
+    cfg, sd = tiny_bert
+    words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
+    (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
+    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok.model_max_length = cfg.max_position_embeddings
+    rng = np.random.default_rng(0)
+    docs = []
+    for d in range(3):
+        sents = [('S' + ' '.join(rng.choice(words, size=rng.integers(5, 9))) + '. ') for _ in range(12 + d)]
+        docs.append({'text': ''.join(sents), 'path': f'doc{d}'})
+    f = tmp_path / 'docs.jsonl'
+    f.write_text('\n'.join(json.dumps(d) for d in docs))
+
+    encoder = AutoEncoder.from_native(tiny_native, tokenizer=tok)
+    dataset = get_dataset({'name': 'jsonl_chunk', 'buffer_size': 1, 'min_buffer_length': 20, 'batch_size': 5,
+                           'num_data_workers': 0, 'pin_memory': False})
+    pooler = get_pooler({'name': 'mean'})
+    loader = dataset.get_dataloader(f, encoder)
+    n_buffers = len(loader.dataset)
+    assert n_buffers == sum(12 + d for d in range(3))
+    pass1 = compute_embeddings_device(loader, encoder, pooler, progress=False)
+    ranges = sc.document_ranges(loader.dataset.metadata)
+    want_groups = osem.split_rows(pass1.cpu().numpy(), ranges, 80)
+
+    embedder = get_embedder({'name': 'semantic_chunk', 'breakpoint_percentile_threshold': 80,
+                             'chunk_batch_size': 4, 'min_chunk_length': 10})
+    loader = dataset.get_dataloader(f, encoder)  # fresh metadata ('sentence' is popped in place)
+    sentences = [m['sentence'] for m in loader.dataset.metadata]
+    result = embedder.embed(loader, encoder, pooler)
+    want_texts = [''.join(sentences[s:e]) for s, e in want_groups]
+    assert result.text == want_texts
+    assert all('sentence' not in m for m in result.metadata)
+    assert result.embeddings.shape == (len(want_texts), cfg.hidden_size)
+
+    # final embeddings vs the oracle forward on the same chunk texts, same batching (4 per batch)
+    ref = []
+    for i in range(0, len(want_texts), 4):
+        enc_b = tok(want_texts[i:i + 4], padding=True, truncation=True, return_tensors='pt')
+        hidden = obert.bert_forward(sd, cfg, enc_b['input_ids'], enc_b['attention_mask'], enc_b['token_type_ids'])
+        ref.append(opool.average_pool(hidden, enc_b['attention_mask'].clone()))
+    cos = cosine_rows(result.embeddings, torch.cat(ref).numpy())
+    assert cos.min() > 1 - COS_TOL, cos
