@@ -133,6 +133,32 @@ class ClockSampler:
 
 
 _CPU_WEIGHTS: dict = {}
+_CPU_THREADS: list = []
+
+
+def pick_cpu_threads() -> int:
+    """Thread count that makes the CPU port fastest on this box.
+
+    "All host threads" is not always best for torch CPU GEMMs (SMT siblings, cgroup quotas), so the
+    candidates -- every schedulable CPU, then halves of it -- are timed on a 1-chunk forward and the
+    fastest is kept (the baseline should be the CPU at its best, not at its most oversubscribed)."""
+    if _CPU_THREADS:
+        return _CPU_THREADS[0]
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    candidates = sorted({max(1, avail >> k) for k in range(0, 5)}, reverse=True)
+    best, best_t = candidates[0], float('inf')
+    for n in candidates:
+        torch.set_num_threads(n)
+        cpu_oracle_run(1, 1)  # warm this thread count
+        sec, _ = cpu_oracle_run(2, 2)
+        if sec < best_t:
+            best, best_t = n, sec
+    torch.set_num_threads(best)
+    _CPU_THREADS.append(best)
+    return best
 
 
 def cpu_oracle_run(n_chunks: int, batch: int, seed: int = 0):
@@ -162,8 +188,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    pick_cpu_threads()
     per_step = 8  # chunks per step: bounded sample of the 512-chunk batch (reference default batch_size)
     if args.warmup > 0:
         cpu_oracle_run(per_step, 8)  # one warm-up step is enough for a CPU loop
@@ -310,7 +335,7 @@ def run_native(args) -> None:
                 'flops_per_chunk': fpc, 'dominant_kernel': time_dominant_kernel(device, peaks)}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count() or 1)
+            pick_cpu_threads()
             n_chunks = 16
             sec, n = cpu_oracle_run(n_chunks, 8)
             cpu_base = {'value': n / sec, 'unit': 'chunks/s', 'cores': torch.get_num_threads(), 'kind': 'port',

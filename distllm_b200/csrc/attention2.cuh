@@ -1,0 +1,313 @@
+// Pipelined bidirectional self-attention for head_dim 64, S <= 512 on sm_100a (second generation).
+//
+// One CTA = one (sequence b, head h).  K and V of the head are loaded ONCE (TMA, 128B swizzle) and
+// stay in smem; the CTA walks the 128-row query tiles two at a time ("slots" A/B), so that while
+// one slot's softmax warpgroup is busy on the MUFU/FMA pipes the tensor core runs the other
+// slot's MMAs:
+//
+//   warp 9      TMA loader       K_j / V_j chunks (128 keys each), Q tiles into 2 smem slots
+//   warp 8      MMA issuer       S = Q K_j^T   (tcgen05.mma SS, 128x128x16, S in TMEM)
+//                                O += P V_j    (tcgen05.mma TS: A = P straight from TMEM,
+//                                               B = V_j as MN-major smem operand, 128x64x16)
+//   warps 0-3   softmax, slot A  one query row per thread: tcgen05.ld S -> online softmax with lazy
+//   warps 4-7   softmax, slot B  rescale -> bf16 P written over S's own TMEM columns (tcgen05.st)
+//                                -> final O / rowsum -> ctx
+//
+// TMEM (512 columns): slot A: S/P [0,128) O [128,192); slot B: S/P [256,384) O [384,448).
+// The online softmax keeps a "used" maximum per row and only rescales O (tcgen05.ld/st of the 64
+// O columns by the row's own thread) when a later key chunk exceeds it by more than 2^8; the
+// in-order execution of the MMA pipe makes that safe without extra barriers (the S_j commit the
+// softmax waits on also covers P V_{j-1}).  Key chunks that are entirely padding are skipped.
+//
+// Semantics: HF BERT SDPA (transformers/models/bert/modeling_bert.py:192-205, mask :692-716);
+// padded keys get the most negative finite score, keys beyond S get -inf.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2e {
+
+constexpr int AT2_D = 64;
+constexpr int AT2_MAX_S = 512;
+constexpr int AT2_THREADS = 320;
+constexpr int AT2_TILE = 128 * AT2_D * 2;           // 16 KiB
+constexpr int AT2_SMEM_Q = 0;                       // 2 slots
+constexpr int AT2_SMEM_K = AT2_SMEM_Q + 2 * AT2_TILE;
+constexpr int AT2_SMEM_V = AT2_SMEM_K + 4 * AT2_TILE;
+constexpr int AT2_SMEM_BIAS = AT2_SMEM_V + 4 * AT2_TILE;   // 512 floats
+constexpr int AT2_SMEM_BAR = AT2_SMEM_BIAS + AT2_MAX_S * 4;
+constexpr int AT2_SMEM_BYTES = AT2_SMEM_BAR + 256 + 1024;
+
+constexpr float AT2_MASKED = -3.0e38f;
+constexpr float AT2_RESCALE_THRESHOLD = 8.0f;  // log2 units: p stays <= 2^8 without a rescale
+
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf16, box 64 x 128
+                      const int64_t* __restrict__ attn_mask,        // [B, S]
+                      bf16* __restrict__ ctx,                       // [T, H]
+                      int S, int H, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sb = raw + pad;
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (S + 127) / 128;  // query tiles == key chunks when nothing is padded
+
+  float* sbias = reinterpret_cast<float*>(smem + AT2_SMEM_BIAS);
+  const uint32_t bar0 = sb + AT2_SMEM_BAR;
+  const uint32_t k_full = bar0;             // [4]
+  const uint32_t v_full = bar0 + 32;        // [4]
+  const uint32_t q_full = bar0 + 64;        // [2]
+  const uint32_t q_empty = bar0 + 80;       // [2]
+  const uint32_t s_ready = bar0 + 96;       // [2]
+  const uint32_t p_ready = bar0 + 112;      // [2]
+  const uint32_t o_ready = bar0 + 128;      // [2]
+  const uint32_t o_empty = bar0 + 144;      // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + AT2_SMEM_BAR + 160);
+  int* kv_len_s = reinterpret_cast<int*>(smem + AT2_SMEM_BAR + 164);
+
+  if (threadIdx.x == 0) *kv_len_s = 0;
+  if (warp == 8) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_qkv);
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(k_full + 8u * i, 1);
+        mbar_init(v_full + 8u * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(q_full + 8u * i, 1);
+        mbar_init(q_empty + 8u * i, 1);
+        mbar_init(s_ready + 8u * i, 1);
+        mbar_init(p_ready + 8u * i, 128);
+        mbar_init(o_ready + 8u * i, 1);
+        mbar_init(o_empty + 8u * i, 128);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+  }
+  __syncthreads();
+  {
+    // additive key bias (exp2 domain) and the index just past the last attended key
+    int last = 0;
+    for (int j = threadIdx.x; j < nq * 128; j += AT2_THREADS) {
+      float v = -INFINITY;
+      if (j < S) {
+        const bool on = attn_mask[static_cast<size_t>(b) * S + j] != 0;
+        v = on ? 0.0f : AT2_MASKED;
+        if (on) last = j + 1;
+      }
+      sbias[j] = v;
+    }
+    if (last > 0) atomicMax(kv_len_s, last);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kv_len = *kv_len_s;
+  // chunks that hold at least one attended key; an all-zero mask keeps every chunk (uniform softmax)
+  const int nkc = kv_len > 0 ? (kv_len + 127) / 128 : nq;
+  const int row_base = b * S;
+
+  if (warp == 9) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- TMA loader
+      auto load_k = [&](int j) {
+        mbar_expect_tx(k_full + 8u * j, AT2_TILE);
+        tma_load_2d(sb + AT2_SMEM_K + j * AT2_TILE, &tm_qkv, k_full + 8u * j, H + h * AT2_D,
+                    row_base + j * 128);
+      };
+      auto load_q = [&](int t) {
+        const int slot = t & 1;
+        mbar_expect_tx(q_full + 8u * slot, AT2_TILE);
+        tma_load_2d(sb + AT2_SMEM_Q + slot * AT2_TILE, &tm_qkv, q_full + 8u * slot, h * AT2_D,
+                    row_base + t * 128);
+      };
+      load_k(0);
+      load_q(0);
+      if (nq > 1) load_q(1);
+      for (int j = 1; j < nkc; ++j) load_k(j);
+      for (int j = 0; j < nkc; ++j) {
+        mbar_expect_tx(v_full + 8u * j, AT2_TILE);
+        tma_load_2d(sb + AT2_SMEM_V + j * AT2_TILE, &tm_qkv, v_full + 8u * j, 2 * H + h * AT2_D,
+                    row_base + j * 128);
+      }
+      for (int t = 2; t < nq; ++t) {
+        const int slot = t & 1;
+        mbar_wait(q_empty + 8u * slot, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+        load_q(t);
+      }
+    }
+  } else if (warp == 8) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, AT2_D, 0, 1);  // B (= V) is MN-major
+      auto issue_qk = [&](int slot, int j) {
+        const uint64_t q_desc = make_smem_desc_sw128(sb + AT2_SMEM_Q + slot * AT2_TILE, 16, 1024);
+        const uint64_t k_desc = make_smem_desc_sw128(sb + AT2_SMEM_K + j * AT2_TILE, 16, 1024);
+        const uint32_t d = tmem_base + static_cast<uint32_t>(slot * 256);
+#pragma unroll
+        for (int k = 0; k < AT2_D / 16; ++k)
+          tc_mma_f16_ss(d, q_desc + 2u * k, k_desc + 2u * k, idesc_s, static_cast<uint32_t>(k != 0));
+      };
+      auto issue_pv = [&](int slot, int j) {
+        const uint32_t p = tmem_base + static_cast<uint32_t>(slot * 256);        // P over S
+        const uint32_t o = tmem_base + static_cast<uint32_t>(slot * 256 + 128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // 16 keys: 8 packed TMEM columns of P, 16 rows (two 8-row swizzle atoms) of V
+          const uint64_t v_desc =
+              make_smem_desc_sw128(sb + AT2_SMEM_V + (j * 128 + k * 16) * 128, 1024, 1024);
+          tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
+                        static_cast<uint32_t>((j | k) != 0));
+        }
+      };
+      uint32_t p_cnt[2] = {0, 0};
+      const int npairs = (nq + 1) / 2;
+      for (int pr = 0; pr < npairs; ++pr) {
+        const int n_active = (2 * pr + 1 < nq) ? 2 : 1;
+        for (int slot = 0; slot < n_active; ++slot) {
+          mbar_wait(q_full + 8u * slot, static_cast<uint32_t>(pr & 1));
+          mbar_wait(k_full, 0);
+          tc_fence_after();
+          issue_qk(slot, 0);
+          tc_commit(s_ready + 8u * slot);
+          if (nkc == 1) tc_commit(q_empty + 8u * slot);
+        }
+        for (int j = 0; j < nkc; ++j) {
+          for (int slot = 0; slot < n_active; ++slot) {
+            mbar_wait(p_ready + 8u * slot, p_cnt[slot] & 1u);
+            ++p_cnt[slot];
+            if (j == 0 && pr > 0) mbar_wait(o_empty + 8u * slot, static_cast<uint32_t>((pr - 1) & 1));
+            mbar_wait(v_full + 8u * j, 0);
+            tc_fence_after();
+            issue_pv(slot, j);
+            if (j + 1 < nkc) {
+              mbar_wait(k_full + 8u * (j + 1), 0);
+              tc_fence_after();
+              issue_qk(slot, j + 1);
+              tc_commit(s_ready + 8u * slot);
+              if (j + 2 == nkc) tc_commit(q_empty + 8u * slot);
+            } else {
+              tc_commit(o_ready + 8u * slot);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int slot = warp >> 2;                 // 0: warps 0-3, 1: warps 4-7
+    const int r = threadIdx.x & 127;            // query row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + static_cast<uint32_t>(slot * 256);
+    const uint32_t t_o = t_s + 128u;
+    uint32_t s_cnt = 0, o_cnt = 0;
+    for (int t = slot; t < nq; t += 2) {
+      float m_used = 0.0f, l = 0.0f;
+      for (int j = 0; j < nkc; ++j) {
+        mbar_wait(s_ready + 8u * slot, s_cnt & 1u);
+        ++s_cnt;
+        tc_fence_after();
+        const float* bias_j = sbias + j * 128;
+        // ---- pass 1: chunk maximum of scale*s + bias
+        float cmax = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld32(t_s + static_cast<uint32_t>(c * 32), s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bz = *reinterpret_cast<const float4*>(bias_j + c * 32 + i);
+            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 0]), scale_log2e, bz.x));
+            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 1]), scale_log2e, bz.y));
+            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 2]), scale_log2e, bz.z));
+            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 3]), scale_log2e, bz.w));
+          }
+        }
+        if (j == 0) {
+          m_used = cmax;  // finite: key 0 always exists (bias is never -inf for j < S)
+        } else {
+          const bool need = cmax > m_used + AT2_RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? cmax : m_used;
+            const float sc = fast_exp2(m_used - m_new);  // 1 when this row keeps its maximum
+            m_used = m_new;
+            l *= sc;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld32(t_o + static_cast<uint32_t>(c * 32), o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+              tmem_st32(t_o + static_cast<uint32_t>(c * 32), o);
+            }
+          }
+        }
+        // ---- pass 2: p = exp2(x - m_used) -> bf16 pairs written over S's own columns
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld32(t_s + static_cast<uint32_t>(c * 32), s);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bz = *reinterpret_cast<const float4*>(bias_j + c * 32 + i);
+            const float p0 = fast_exp2(fmaf(__uint_as_float(s[i + 0]), scale_log2e, bz.x) - m_used);
+            const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2e, bz.y) - m_used);
+            const float p2 = fast_exp2(fmaf(__uint_as_float(s[i + 2]), scale_log2e, bz.z) - m_used);
+            const float p3 = fast_exp2(fmaf(__uint_as_float(s[i + 3]), scale_log2e, bz.w) - m_used);
+            l += (p0 + p1) + (p2 + p3);
+            pk[i / 2] = pack_bf16x2(p0, p1);
+            pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st16(t_s + static_cast<uint32_t>(c * 16), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready + 8u * slot);
+      }
+      // ---- epilogue: O / l -> ctx
+      mbar_wait(o_ready + 8u * slot, o_cnt & 1u);
+      ++o_cnt;
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int q = t * 128 + r;
+      bf16* dst = ctx + static_cast<size_t>(row_base + q) * H + h * AT2_D;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(t_o + static_cast<uint32_t>(c * 32), o);
+        tmem_ld_wait();
+        if (q < S) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + i) = w;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty + 8u * slot);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b2e

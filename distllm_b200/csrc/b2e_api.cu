@@ -8,11 +8,13 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rowops.cuh"
@@ -170,8 +172,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
                                 static_cast<const bf16*>(resid), M, N, K, epi, sms, st);
 }
 
-int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
-                     int heads, float* dbg, cudaStream_t st) {
+int launch_attention_v1(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
+                        int heads, float* dbg, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(attention_d64_tcgen05_kernel,
@@ -182,6 +184,29 @@ int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, in
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   attention_d64_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(
       tqkv, mask, static_cast<bf16*>(ctx), S, heads * ATT_D, scale_log2e, dbg);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+// Pipelined kernel (attention2.cuh) unless B2E_ATTENTION=v1 or a score dump is requested.
+int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
+                     int heads, float* dbg, cudaStream_t st) {
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("B2E_ATTENTION");
+    use_v1 = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+  }
+  if (use_v1 || dbg) return launch_attention_v1(tqkv, mask, ctx, B, S, heads, dbg, st);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(attention2_d64_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid(heads, B);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
+      tqkv, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }

@@ -28,12 +28,26 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;         // [2][BN] fp32 bias slices
+  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * BN * 4 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
+// erf-GELU, x * Phi(x), with Phi from the Abramowitz-Stegun 7.1.26 erfc polynomial
+// (|erf error| <= 1.5e-7): gelu(x) = max(x,0) - 0.5*|x|*poly(t)*exp(-x^2/2), t = 1/(1 + p*|x|/sqrt2).
+// ~14 FP instructions + 2 MUFU per element instead of libdevice erff's ~35: the FFN-up epilogue
+// is issue-bound, and the output is rounded to bf16 (2^-9) anyway.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678f, ax, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float e = fast_exp2(ax * ax * (-0.5f * 1.4426950408889634f));
+  return fmaxf(x, 0.0f) - 0.5f * ax * p * e;
 }
 
 template <int BN, int STAGES, int EPI>
@@ -136,50 +150,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
     const int q = warp & 3;               // TMEM lane quarter this warp may touch
     const int half = (warp - 4) >> 2;     // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    const int etid = threadIdx.x - 128;   // 0..255 among the epilogue threads
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);  // [2][BN]
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
-      mbar_wait(tfull_bar + 8u * as, aphase);
-      tc_fence_after();
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < M;
       const size_t row_off = static_cast<size_t>(row) * static_cast<size_t>(N);
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-        const int col_in_tile = half * COLS_PER_WARP + c * 32;
-        const int gcol = n_blk * BN + col_in_tile;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                      static_cast<uint32_t>(as * BN + col_in_tile),
-                  r);
-        tmem_ld_wait();
+      const int col0 = half * COLS_PER_WARP;       // first column of this warp inside the tile
+      const int gcol0 = n_blk * BN + col0;
+
+      // Everything that does not depend on the accumulator is fetched BEFORE waiting for it:
+      // the tile's bias slice goes to smem, the residual rows of this thread to registers.
+      for (int i = etid; i < BN; i += GEMM_EPI_WARPS * 32)
+        sbias[as * BN + i] = __ldg(bias + n_blk * BN + i);
+      uint4 rres[NCHUNK][4];
+      if (EPI == EPI_BIAS_RESID) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j + 4));
+        for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            rres[c][j] = row_ok ? *reinterpret_cast<const uint4*>(resid + row_off + gcol0 + c * 32 + j * 8)
+                                : make_uint4(0u, 0u, 0u, 0u);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+
+      mbar_wait(tfull_bar + 8u * as, aphase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                              static_cast<uint32_t>(as * BN + col0);
+      uint32_t r[2][32];
+      tmem_ld32(t_base, r[0]);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < NCHUNK) tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), r[(c + 1) & 1]);
+        const float* bptr = sbias + as * BN + col0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bptr + j * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bptr + j * 8 + 4);
           float v[8];
-          v[0] = __uint_as_float(r[j + 0]) + b0.x;
-          v[1] = __uint_as_float(r[j + 1]) + b0.y;
-          v[2] = __uint_as_float(r[j + 2]) + b0.z;
-          v[3] = __uint_as_float(r[j + 3]) + b0.w;
-          v[4] = __uint_as_float(r[j + 4]) + b1.x;
-          v[5] = __uint_as_float(r[j + 5]) + b1.y;
-          v[6] = __uint_as_float(r[j + 6]) + b1.z;
-          v[7] = __uint_as_float(r[j + 7]) + b1.w;
+          v[0] = __uint_as_float(r[c & 1][j * 8 + 0]) + b0.x;
+          v[1] = __uint_as_float(r[c & 1][j * 8 + 1]) + b0.y;
+          v[2] = __uint_as_float(r[c & 1][j * 8 + 2]) + b0.z;
+          v[3] = __uint_as_float(r[c & 1][j * 8 + 3]) + b0.w;
+          v[4] = __uint_as_float(r[c & 1][j * 8 + 4]) + b1.x;
+          v[5] = __uint_as_float(r[c & 1][j * 8 + 5]) + b1.y;
+          v[6] = __uint_as_float(r[c & 1][j * 8 + 6]) + b1.z;
+          v[7] = __uint_as_float(r[c & 1][j * 8 + 7]) + b1.w;
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
           }
           if (EPI == EPI_BIAS_RESID) {
-            if (row_ok) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(resid + row_off + gcol + j);
-              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y),
-                           r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
-              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-            }
+            const float2 r0 = unpack_bf16x2(rres[c][j].x), r1 = unpack_bf16x2(rres[c][j].y),
+                         r2 = unpack_bf16x2(rres[c][j].z), r3 = unpack_bf16x2(rres[c][j].w);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
           }
           if (row_ok) {
             uint4 o;
@@ -187,7 +219,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
             o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]);
             o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(out + row_off + gcol + j) = o;
+            *reinterpret_cast<uint4*>(out + row_off + gcol0 + c * 32 + j * 8) = o;
           }
         }
       }
