@@ -29,7 +29,7 @@ namespace b2e {
 
 constexpr int AT2_D = 64;
 constexpr int AT2_MAX_S = 512;
-constexpr int AT2_THREADS = 320;
+constexpr int AT2_THREADS = 384;  // 3 warpgroups: softmax A, softmax B, {MMA, loader, 2 idle}
 constexpr int AT2_TILE = 128 * AT2_D * 2;           // 16 KiB
 constexpr int AT2_SMEM_Q = 0;                       // 2 slots
 constexpr int AT2_SMEM_K = AT2_SMEM_Q + 2 * AT2_TILE;
@@ -41,11 +41,68 @@ constexpr int AT2_SMEM_BYTES = AT2_SMEM_BAR + 256 + 1024;
 constexpr float AT2_MASKED = -3.0e38f;
 constexpr float AT2_RESCALE_THRESHOLD = 8.0f;  // log2 units: p stays <= 2^8 without a rescale
 
+// ---- per-row softmax helpers over 32 register-resident scores
+// x = scale*s + bias written back in place; running maximum returned (chunks with padded keys)
+__device__ __forceinline__ float att2_bias_max(uint32_t (&s)[32], const float* __restrict__ bias,
+                                               float scale, float m) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 bz = *reinterpret_cast<const float4*>(bias + i);
+    const float x0 = fmaf(__uint_as_float(s[i + 0]), scale, bz.x);
+    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale, bz.y);
+    const float x2 = fmaf(__uint_as_float(s[i + 2]), scale, bz.z);
+    const float x3 = fmaf(__uint_as_float(s[i + 3]), scale, bz.w);
+    s[i + 0] = __float_as_uint(x0);
+    s[i + 1] = __float_as_uint(x1);
+    s[i + 2] = __float_as_uint(x2);
+    s[i + 3] = __float_as_uint(x3);
+    m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
+  }
+  return m;
+}
+// maximum of the raw scores (fully attended chunks: no bias, scale applied by the caller)
+__device__ __forceinline__ float att2_raw_max(const uint32_t (&s)[32], float m) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1]))),
+              fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+  return m;
+}
+// p = exp2(x - m) packed to bf16 pairs; returns the fp32 sum of the 32 probabilities.
+// BIASED: s already holds x = scale*s + bias;  otherwise x is formed here in one FFMA with -m.
+template <bool BIASED>
+__device__ __forceinline__ float att2_exp_pack(const uint32_t (&s)[32], float scale, float m,
+                                               uint32_t (&pk)[16]) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float p0, p1, p2, p3;
+    if (BIASED) {
+      p0 = fast_exp2(__uint_as_float(s[i + 0]) - m);
+      p1 = fast_exp2(__uint_as_float(s[i + 1]) - m);
+      p2 = fast_exp2(__uint_as_float(s[i + 2]) - m);
+      p3 = fast_exp2(__uint_as_float(s[i + 3]) - m);
+    } else {
+      p0 = fast_exp2(fmaf(__uint_as_float(s[i + 0]), scale, -m));
+      p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale, -m));
+      p2 = fast_exp2(fmaf(__uint_as_float(s[i + 2]), scale, -m));
+      p3 = fast_exp2(fmaf(__uint_as_float(s[i + 3]), scale, -m));
+    }
+    sum += (p0 + p1) + (p2 + p3);
+    pk[i / 2] = pack_bf16x2(p0, p1);
+    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  return sum;
+}
+
+__device__ __forceinline__ int slot_of_warp(int warp) { return warp >> 2; }
+
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf16, box 64 x 128
                       const int64_t* __restrict__ attn_mask,        // [B, S]
                       bf16* __restrict__ ctx,                       // [T, H]
-                      int S, int H, float scale_log2e) {
+                      int S, int H, float scale_log2e,
+                      long long* __restrict__ dbg_clock /* nullptr unless profiling */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -68,8 +125,10 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
   const uint32_t o_empty = bar0 + 144;      // [2]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + AT2_SMEM_BAR + 160);
   int* kv_len_s = reinterpret_cast<int*>(smem + AT2_SMEM_BAR + 164);
+  int* mflag = reinterpret_cast<int*>(smem + AT2_SMEM_BAR + 168);  // [4] chunk has padded/OOB keys
 
   if (threadIdx.x == 0) *kv_len_s = 0;
+  if (threadIdx.x < 4) mflag[threadIdx.x] = 0;
   if (warp == 8) {
     if (elect_one()) {
       tma_prefetch_desc(&tm_qkv);
@@ -102,6 +161,7 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
         if (on) last = j + 1;
       }
       sbias[j] = v;
+      if (v != 0.0f) atomicOr(&mflag[j >> 7], 1);
     }
     if (last > 0) atomicMax(kv_len_s, last);
   }
@@ -113,7 +173,17 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
   // chunks that hold at least one attended key; an all-zero mask keeps every chunk (uniform softmax)
   const int nkc = kv_len > 0 ? (kv_len + 127) / 128 : nq;
   const int row_base = b * S;
+  // optional timeline of CTA (0,0): dbg_clock[role*128 + n] = clock64() at the n-th event of a role
+  const bool stamp_on = dbg_clock != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  int stamp_n = 0;
+#define AT2_STAMP(role)                                                          \
+  do {                                                                          \
+    if (stamp_on && stamp_n < 128) dbg_clock[(role) * 128 + stamp_n++] = clock64(); \
+  } while (0)
 
+  if (warp >= 8) {
+    // the control warpgroup hands its registers to the two softmax warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 9) {
     if (elect_one()) {
       // ---------------------------------------------------------------- TMA loader
@@ -137,6 +207,7 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
         tma_load_2d(sb + AT2_SMEM_V + j * AT2_TILE, &tm_qkv, v_full + 8u * j, 2 * H + h * AT2_D,
                     row_base + j * 128);
       }
+      AT2_STAMP(3);
       for (int t = 2; t < nq; ++t) {
         const int slot = t & 1;
         mbar_wait(q_empty + 8u * slot, static_cast<uint32_t>(((t >> 1) - 1) & 1));
@@ -168,25 +239,37 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
                         static_cast<uint32_t>((j | k) != 0));
         }
       };
-      uint32_t p_cnt[2] = {0, 0};
-      const int npairs = (nq + 1) / 2;
-      for (int pr = 0; pr < npairs; ++pr) {
-        const int n_active = (2 * pr + 1 < nq) ? 2 : 1;
-        for (int slot = 0; slot < n_active; ++slot) {
-          mbar_wait(q_full + 8u * slot, static_cast<uint32_t>(pr & 1));
-          mbar_wait(k_full, 0);
-          tc_fence_after();
-          issue_qk(slot, 0);
-          tc_commit(s_ready + 8u * slot);
-          if (nkc == 1) tc_commit(q_empty + 8u * slot);
-        }
-        for (int j = 0; j < nkc; ++j) {
-          for (int slot = 0; slot < n_active; ++slot) {
-            mbar_wait(p_ready + 8u * slot, p_cnt[slot] & 1u);
+      // Dynamic issue order: each slot is a small state machine polled without blocking, so a slot
+      // whose softmax finished is served at once instead of waiting for its neighbour (lock-step
+      // would leave the MUFU pipes idle during every MMA phase and vice versa).
+      int tile[2] = {0, 1};   // query tile the slot works on
+      int jj[2] = {-1, -1};   // -1: Q K_0^T of `tile` not issued yet, else the chunk whose P is awaited
+      uint32_t p_cnt[2] = {0, 0}, q_cnt[2] = {0, 0};
+      int remaining = nq;
+      while (remaining > 0) {
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          if (tile[slot] >= nq) continue;
+          if (jj[slot] < 0) {
+            if (!mbar_test(q_full + 8u * slot, q_cnt[slot] & 1u)) continue;
+            ++q_cnt[slot];
+            mbar_wait(k_full, 0);
+            tc_fence_after();
+            AT2_STAMP(2);
+            issue_qk(slot, 0);
+            tc_commit(s_ready + 8u * slot);
+            if (nkc == 1) tc_commit(q_empty + 8u * slot);
+            jj[slot] = 0;
+          } else {
+            if (!mbar_test(p_ready + 8u * slot, p_cnt[slot] & 1u)) continue;
             ++p_cnt[slot];
-            if (j == 0 && pr > 0) mbar_wait(o_empty + 8u * slot, static_cast<uint32_t>((pr - 1) & 1));
+            const int j = jj[slot];
+            // the epilogue of the slot's previous tile arrives on o_empty before this p_ready
+            if (j == 0 && tile[slot] >= 2)
+              mbar_wait(o_empty + 8u * slot, static_cast<uint32_t>(((tile[slot] >> 1) - 1) & 1));
             mbar_wait(v_full + 8u * j, 0);
             tc_fence_after();
+            AT2_STAMP(2);
             issue_pv(slot, j);
             if (j + 1 < nkc) {
               mbar_wait(k_full + 8u * (j + 1), 0);
@@ -194,15 +277,21 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
               issue_qk(slot, j + 1);
               tc_commit(s_ready + 8u * slot);
               if (j + 2 == nkc) tc_commit(q_empty + 8u * slot);
+              jj[slot] = j + 1;
             } else {
               tc_commit(o_ready + 8u * slot);
+              tile[slot] += 2;
+              jj[slot] = -1;
+              --remaining;
             }
           }
         }
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");  // 128 scores per thread live in registers
     const int slot = warp >> 2;                 // 0: warps 0-3, 1: warps 4-7
     const int r = threadIdx.x & 127;            // query row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -212,25 +301,34 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
     for (int t = slot; t < nq; t += 2) {
       float m_used = 0.0f, l = 0.0f;
       for (int j = 0; j < nkc; ++j) {
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
         mbar_wait(s_ready + 8u * slot, s_cnt & 1u);
         ++s_cnt;
         tc_fence_after();
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
         const float* bias_j = sbias + j * 128;
-        // ---- pass 1: chunk maximum of scale*s + bias
+        const bool masked = mflag[j] != 0;  // CTA-uniform: does this chunk hold padded / OOB keys?
+        // ---- the 128 scores of this row, read once
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld32(t_s, s0);
+        tmem_ld32(t_s + 32u, s1);
+        tmem_ld32(t_s + 64u, s2);
+        tmem_ld32(t_s + 96u, s3);
+        tmem_ld_wait();
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
+        // ---- pass 1: chunk maximum of scale*s + bias (registers only)
         float cmax = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld32(t_s + static_cast<uint32_t>(c * 32), s);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bz = *reinterpret_cast<const float4*>(bias_j + c * 32 + i);
-            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 0]), scale_log2e, bz.x));
-            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 1]), scale_log2e, bz.y));
-            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 2]), scale_log2e, bz.z));
-            cmax = fmaxf(cmax, fmaf(__uint_as_float(s[i + 3]), scale_log2e, bz.w));
-          }
+        if (masked) {
+          cmax = att2_bias_max(s0, bias_j, scale_log2e, cmax);
+          cmax = att2_bias_max(s1, bias_j + 32, scale_log2e, cmax);
+          cmax = att2_bias_max(s2, bias_j + 64, scale_log2e, cmax);
+          cmax = att2_bias_max(s3, bias_j + 96, scale_log2e, cmax);
+        } else {
+          cmax = att2_raw_max(s0, cmax);
+          cmax = att2_raw_max(s1, cmax);
+          cmax = att2_raw_max(s2, cmax);
+          cmax = att2_raw_max(s3, cmax);
+          cmax *= scale_log2e;  // scale > 0 commutes with max
         }
         if (j == 0) {
           m_used = cmax;  // finite: key 0 always exists (bias is never -inf for j < S)
@@ -252,29 +350,25 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
             }
           }
         }
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
         // ---- pass 2: p = exp2(x - m_used) -> bf16 pairs written over S's own columns
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld32(t_s + static_cast<uint32_t>(c * 32), s);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bz = *reinterpret_cast<const float4*>(bias_j + c * 32 + i);
-            const float p0 = fast_exp2(fmaf(__uint_as_float(s[i + 0]), scale_log2e, bz.x) - m_used);
-            const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2e, bz.y) - m_used);
-            const float p2 = fast_exp2(fmaf(__uint_as_float(s[i + 2]), scale_log2e, bz.z) - m_used);
-            const float p3 = fast_exp2(fmaf(__uint_as_float(s[i + 3]), scale_log2e, bz.w) - m_used);
-            l += (p0 + p1) + (p2 + p3);
-            pk[i / 2] = pack_bf16x2(p0, p1);
-            pk[i / 2 + 1] = pack_bf16x2(p2, p3);
-          }
-          tmem_st16(t_s + static_cast<uint32_t>(c * 16), pk);
+        uint32_t pk[16];
+        if (masked) {
+          l += att2_exp_pack<true>(s0, scale_log2e, m_used, pk);  tmem_st16(t_s, pk);
+          l += att2_exp_pack<true>(s1, scale_log2e, m_used, pk);  tmem_st16(t_s + 16u, pk);
+          l += att2_exp_pack<true>(s2, scale_log2e, m_used, pk);  tmem_st16(t_s + 32u, pk);
+          l += att2_exp_pack<true>(s3, scale_log2e, m_used, pk);  tmem_st16(t_s + 48u, pk);
+        } else {
+          l += att2_exp_pack<false>(s0, scale_log2e, m_used, pk); tmem_st16(t_s, pk);
+          l += att2_exp_pack<false>(s1, scale_log2e, m_used, pk); tmem_st16(t_s + 16u, pk);
+          l += att2_exp_pack<false>(s2, scale_log2e, m_used, pk); tmem_st16(t_s + 32u, pk);
+          l += att2_exp_pack<false>(s3, scale_log2e, m_used, pk); tmem_st16(t_s + 48u, pk);
         }
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_ready + 8u * slot);
+        if ((threadIdx.x & 127) == 0) AT2_STAMP(slot);
       }
       // ---- epilogue: O / l -> ctx
       mbar_wait(o_ready + 8u * slot, o_cnt & 1u);
@@ -305,6 +399,8 @@ attention2_d64_kernel(const __grid_constant__ CUtensorMap tm_qkv,  // [T, 3H] bf
     }
   }
 
+  if ((threadIdx.x & 127) == 0 && warp < 8) AT2_STAMP(slot_of_warp(warp));
+#undef AT2_STAMP
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 512);

@@ -194,9 +194,11 @@ int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, in
   static int use_v1 = -1;
   if (use_v1 < 0) {
     const char* e = getenv("B2E_ATTENTION");
-    use_v1 = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+    use_v1 = (e && strcmp(e, "v1") == 0) ? 1 : ((e && strcmp(e, "v2clock") == 0) ? 2 : 0);
   }
-  if (use_v1 || dbg) return launch_attention_v1(tqkv, mask, ctx, B, S, heads, dbg, st);
+  // B2E_ATTENTION=v2clock reinterprets the debug buffer as the pipelined kernel's clock64 timeline
+  if (use_v1 == 1 || (dbg && use_v1 != 2))
+    return launch_attention_v1(tqkv, mask, ctx, B, S, heads, dbg, st);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(attention2_d64_kernel,
@@ -206,7 +208,8 @@ int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, in
   dim3 grid(heads, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
-      tqkv, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e);
+      tqkv, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e,
+      use_v1 == 2 ? reinterpret_cast<long long*>(dbg) : nullptr);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
