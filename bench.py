@@ -257,6 +257,8 @@ def run_native(args) -> None:
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
+        # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
+        os.environ['NCCL_DEBUG'] = os.environ.get('B2E_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=device)
 
     peaks, peak_src = load_peaks()

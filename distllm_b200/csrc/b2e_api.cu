@@ -17,6 +17,7 @@
 #include "attention2.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "rowops.cuh"
 
 using namespace b2e;
@@ -121,8 +122,9 @@ int current_device_info(DeviceInfo* info) {
 
 // ---------------------------------------------------------------- launches
 template <int BN, int STAGES, int EPI>
-int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
-                    const bf16* resid, int M, int N, int K, int sms, cudaStream_t st) {
+int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                    const float* bias, const bf16* resid, int M, int N, int K, int sms,
+                    cudaStream_t st) {
   using Cfg = GemmCfg<BN, STAGES>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, EPI>;
   static bool attr_done = false;
@@ -133,27 +135,39 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, con
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, out, bias, resid, M, N, K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
 
 template <int BN, int STAGES>
-int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
-                   const bf16* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                   const float* bias, const bf16* resid, int M, int N, int K, int epi, int sms,
+                   cudaStream_t st) {
   switch (epi) {
     case B2E_EPI_BIAS:
-      return launch_gemm_cfg<BN, STAGES, EPI_BIAS>(ta, tb, out, bias, resid, M, N, K, sms, st);
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS>(ta, tb, tout, bias, resid, M, N, K, sms, st);
     case B2E_EPI_BIAS_GELU:
-      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_GELU>(ta, tb, out, bias, resid, M, N, K, sms, st);
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_GELU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
     case B2E_EPI_BIAS_RESID:
-      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_RESID>(ta, tb, out, bias, resid, M, N, K, sms,
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_RESID>(ta, tb, tout, bias, resid, M, N, K, sms,
                                                          st);
   }
   return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
-inline int gemm_bn_for(int N) { return (N % 256 == 0) ? 256 : 128; }
+// B2E_GEMM=pair selects the experimental CTA-pair kernel (gemm2.cuh) when N is a multiple of 256;
+// the default is the single-CTA kernel with TMA-store epilogue.
+inline bool gemm_use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2E_GEMM");
+    v = (e && strcmp(e, "pair") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+// rows of the W tile one TMA box covers: the pair kernel stages half of the 256-row tile per CTA
+inline int gemm_bn_for(int N) { return (N % 256 == 0 && !gemm_use_pair()) ? 256 : 128; }
 
 int check_gemm_shape(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(B2E_ERR_INVALID, "gemm: empty shape %dx%dx%d", M, N, K);
@@ -162,14 +176,44 @@ int check_gemm_shape(int M, int N, int K) {
   return B2E_OK;
 }
 
-// A map: [M,K] box 128 rows; W map: [N,K] box BN rows.
+template <int STAGES, int EPI>
+int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
+                     const bf16* resid, int M, int N, int K, int sms, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<STAGES>;
+  auto kern = gemm2_bf16_pair_kernel<STAGES, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((M + 255) / 256) * (N / G2_BN);
+  int grid = 2 * tiles;
+  if (grid > (sms & ~1)) grid = sms & ~1;
+  kern<<<grid, G2_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, out, bias, resid, M, N, K);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+// A map: [M,K] box 128 rows; W map: [N,K] box gemm_bn_for(N) rows.
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const float* bias,
                 const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
-  if (gemm_bn_for(N) == 256)
-    return launch_gemm_bn<256, 4>(ta, tb, static_cast<bf16*>(out), bias,
-                                  static_cast<const bf16*>(resid), M, N, K, epi, sms, st);
-  return launch_gemm_bn<128, 6>(ta, tb, static_cast<bf16*>(out), bias,
-                                static_cast<const bf16*>(resid), M, N, K, epi, sms, st);
+  bf16* o = static_cast<bf16*>(out);
+  const bf16* r = static_cast<const bf16*>(resid);
+  if (N % 256 == 0 && gemm_use_pair()) {
+    switch (epi) {
+      case B2E_EPI_BIAS: return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, o, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<6, EPI_BIAS_GELU>(ta, tb, o, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<6, EPI_BIAS_RESID>(ta, tb, o, bias, r, M, N, K, sms, st);
+    }
+    return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
+  }
+  // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
+  CUtensorMap tout;
+  int rc;
+  if ((rc = make_tmap_bf16(&tout, out, M, N, GEMM_OUT_BOX_ROWS))) return rc;
+  if (N % 256 == 0) return launch_gemm_bn<256, 4>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
+  return launch_gemm_bn<128, 6>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
 }
 
 int launch_attention_v1(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
@@ -367,7 +411,8 @@ int validate_batch(const B2EEncoder* e, int B, int S) {
 }
 
 // Layers 0..L-1 up to (and including) the last FFN-down GEMM: leaves the pre-LayerNorm residual sum
-// of the final layer in e->tmp; every earlier LayerNorm output lives in e->hidden.
+// of the final layer split as e->tmp (FFN-down output + bias) and e->hidden (the residual it still has
+// to be added to); every earlier LayerNorm output lives in e->hidden.
 int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types,
                    int B, int S, cudaStream_t st) {
   const B2EModelDesc& d = e->desc;
@@ -389,22 +434,23 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
                           3 * H, H, B2E_EPI_BIAS, e->sms, st)))
       return rc;
     if ((rc = launch_attention(tm_qkv, mask, e->ctx, B, S, d.heads, nullptr, st))) return rc;
-    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), e->hidden, M, H,
-                          H, B2E_EPI_BIAS_RESID, e->sms, st)))
+    // the residual add rides on the LayerNorm's coalesced reads, not on the GEMM epilogue
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), nullptr, M, H, H,
+                          B2E_EPI_BIAS, e->sms, st)))
       return rc;
     DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->tmp, (const float*)e->L(l, 4), (const float*)e->L(l, 5), e->hidden, M,
-                       d.eps)));
+                       e->tmp, e->hidden, (const float*)e->L(l, 4), (const float*)e->L(l, 5),
+                       e->hidden, M, d.eps)));
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->L(l, 7), nullptr, M, I,
                           H, B2E_EPI_BIAS_GELU, e->sms, st)))
       return rc;
-    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->L(l, 9), e->hidden, M, H, I,
-                          B2E_EPI_BIAS_RESID, e->sms, st)))
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->L(l, 9), nullptr, M, H, I,
+                          B2E_EPI_BIAS, e->sms, st)))
       return rc;
     if (l + 1 < d.num_layers) {
       DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                         e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11), e->hidden, M,
-                         d.eps)));
+                         e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
+                         e->hidden, M, d.eps)));
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -417,6 +463,14 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
 extern "C" {
 
 int b2e_version(void) { return B2E_ABI_VERSION; }
+
+// Profiling aid (not part of include/b2e.h): device buffer of 4 x 256 int64 that CTAs 0 and 1 of
+// the CTA-pair GEMM fill with clock64() stamps ([cta*2 + role][n], role 0 = producer, 1 = MMA).
+int b2e_debug_set_clock_buffer(void* device_buffer) {
+  long long* p = static_cast<long long*>(device_buffer);
+  CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_clock, &p, sizeof(p)));
+  return B2E_OK;
+}
 const char* b2e_last_error(void) { return g_err.c_str(); }
 
 int b2e_num_weights(const B2EModelDesc* desc) {
@@ -501,11 +555,11 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
   const int M = B * S, H = d.hidden, l = d.num_layers - 1;
   if (out_dtype == B2E_DTYPE_F32) {
     DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
+                       e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
                        (float*)out_hidden, M, d.eps)));
   } else {
     DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->tmp, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
+                       e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
                        (bf16*)out_hidden, M, d.eps)));
   }
   CUDA_TRY(cudaGetLastError());
@@ -531,7 +585,7 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
     last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
     DISPATCH_NV(H, (layernorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
-                       e->tmp, ps.idx, g, bt, out, B, S, d.eps)));
+                       e->tmp, e->hidden, ps.idx, g, bt, out, B, S, d.eps)));
     if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
@@ -542,8 +596,8 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
   const int nsplit = pool_nsplit(S);
   const int rows_per = (S + nsplit - 1) / nsplit;
   dim3 grid(B, nsplit);
-  DISPATCH_NV(H, (layernorm_pool_kernel<NV><<<grid, ROW_THREADS, 0, st>>>(e->tmp, g, bt, ps.w,
-                                                                        ps.part, S, rows_per, d.eps)));
+  DISPATCH_NV(H, (layernorm_pool_kernel<NV><<<grid, ROW_THREADS, 0, st>>>(
+                     e->tmp, e->hidden, g, bt, ps.w, ps.part, S, rows_per, d.eps)));
   CUDA_TRY(cudaGetLastError());
   return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
 }
@@ -747,10 +801,10 @@ int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* o
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == B2E_DTYPE_F32) {
     DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
-                       (const bf16*)in, gamma, beta, (float*)out, rows, eps)));
+                       (const bf16*)in, nullptr, gamma, beta, (float*)out, rows, eps)));
   } else if (out_dtype == B2E_DTYPE_BF16) {
     DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
-                       (const bf16*)in, gamma, beta, (bf16*)out, rows, eps)));
+                       (const bf16*)in, nullptr, gamma, beta, (bf16*)out, rows, eps)));
   } else {
     return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or BF16");
   }

@@ -3,10 +3,16 @@
 //   warp 0      TMA producer   (one elected lane): A/W tiles -> 128B-swizzled smem ring
 //   warp 1      MMA issuer     (one elected lane): tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld -> +bias (-> erf-GELU | +residual) -> bf16 -> global
+//   warps 4-11  epilogue: tcgen05.ld -> +bias (-> erf-GELU | +residual) -> bf16 -> per-warp
+//               swizzled smem tile (32 rows x 64 cols) -> TMA store (cp.async.bulk.tensor)
 //
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
-// the MMAs of tile i+1.  This replaces the cuBLAS nn.Linear calls HF BERT issues from
+// the MMAs of tile i+1.  Output goes through TMA stores because direct "one row per lane" global
+// stores cost 32 L1 wavefronts per instruction and, at 4096 wavefronts per 128x256 tile, fought the
+// tensor core's own shared-memory operand reads for the L1/smem data pipe (ncu: lsu wavefronts
+// 40-55 % + tc wavefronts 20-52 % of the pipe, profiles/r01_ncu_v1_summary.md).
+//
+// This replaces the cuBLAS nn.Linear calls HF BERT issues from
 // transformers/models/bert/modeling_bert.py:180-182 (q,k,v), :294-298 (attn out), :339-342 (FFN up +
 // GELU), :352-356 (FFN down), reached from distllm/embed/encoders/auto.py:135.
 #pragma once
@@ -21,16 +27,20 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_OUT_BOX_ROWS = 32;   // TMA store box: 64 columns x 32 rows (one warp's chunk)
+constexpr int GEMM_STAGING_BYTES = GEMM_OUT_BOX_ROWS * 128;  // 4 KiB per epilogue warp
 
 template <int BN, int STAGES>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 1024-aligned (stage sizes are)
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + GEMM_EPI_WARPS * GEMM_STAGING_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;         // [2][BN] fp32 bias slices
-  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * BN * 4 + 1024;  // + alignment slack
+  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * BN * 4;  // dynamic smem must start 1024-aligned
   static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 };
 
 // erf-GELU, x * Phi(x), with Phi from the Abramowitz-Stegun 7.1.26 erfc polynomial
@@ -50,25 +60,70 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaxf(x, 0.0f) - 0.5f * ax * p * e;
 }
 
+// Epilogue of one 32-row x 64-column chunk held as two 32-column TMEM reads: bias (+GELU / +resid),
+// bf16, into the warp's swizzled staging tile (row = lane).  `resid_row` points at this lane's
+// row, first column of the chunk (only read when EPI == EPI_BIAS_RESID and the row exists).
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32],
+                                                    const float* __restrict__ bias_smem,
+                                                    const bf16* __restrict__ resid_row, bool row_ok,
+                                                    uint8_t* staging, int lane) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {  // 16-byte unit = 8 columns
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_smem + u * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_smem + u * 8 + 4);
+    const uint32_t* a = &acc[u >> 2][(u & 3) * 8];
+    float v[8];
+    v[0] = __uint_as_float(a[0]) + b0.x;
+    v[1] = __uint_as_float(a[1]) + b0.y;
+    v[2] = __uint_as_float(a[2]) + b0.z;
+    v[3] = __uint_as_float(a[3]) + b0.w;
+    v[4] = __uint_as_float(a[4]) + b1.x;
+    v[5] = __uint_as_float(a[5]) + b1.y;
+    v[6] = __uint_as_float(a[6]) + b1.z;
+    v[7] = __uint_as_float(a[7]) + b1.w;
+    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+    }
+    if (EPI == EPI_BIAS_RESID) {
+      if (row_ok) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(resid_row + u * 8);
+        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                     r3 = unpack_bf16x2(rr.w);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+        v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    // 128B-swizzle: unit index XOR (row & 7) -- conflict-free for "one row per lane" writes and
+    // exactly the layout the SWIZZLE_128B tensor map expects
+    *reinterpret_cast<uint4*>(staging + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
+  }
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
-                         const __grid_constant__ CUtensorMap tm_b, bf16* __restrict__ out,
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] box 64 x 128
+                         const __grid_constant__ CUtensorMap tm_b,    // [N,K] box 64 x BN
+                         const __grid_constant__ CUtensorMap tm_out,  // [M,N] box 64 x 32
                          const float* __restrict__ bias, const bf16* __restrict__ resid, int M,
                          int N, int K) {
   using Cfg = GemmCfg<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad;
-  const uint32_t smem_base = raw + pad;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) __trap();  // the swizzled tiles need a 1024-byte aligned base
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
   const uint32_t full_bar = smem_base + Cfg::BAR_OFFSET;
   const uint32_t empty_bar = full_bar + 8u * STAGES;
   const uint32_t tfull_bar = empty_bar + 8u * STAGES;
   const uint32_t tempty_bar = tfull_bar + 16u;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * STAGES + 4);
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFFSET + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,6 +131,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
@@ -150,83 +206,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
     const int q = warp & 3;               // TMEM lane quarter this warp may touch
     const int half = (warp - 4) >> 2;     // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
-    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    constexpr int NCHUNK = COLS_PER_WARP / 64;  // 64-column chunks (one swizzle atom wide)
     const int etid = threadIdx.x - 128;   // 0..255 among the epilogue threads
     float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);  // [2][BN]
+    uint8_t* staging = smem + Cfg::STAGING_OFFSET + (warp - 4) * GEMM_STAGING_BYTES;
+    const uint32_t staging_addr = smem_base + Cfg::STAGING_OFFSET + (warp - 4) * GEMM_STAGING_BYTES;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const int row0 = m_blk * GEMM_BM + q * 32;   // first row of this warp's 32-row band
+      const int row = row0 + lane;
       const bool row_ok = row < M;
-      const size_t row_off = static_cast<size_t>(row) * static_cast<size_t>(N);
       const int col0 = half * COLS_PER_WARP;       // first column of this warp inside the tile
       const int gcol0 = n_blk * BN + col0;
+      const bf16* resid_row =
+          (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
-      // Everything that does not depend on the accumulator is fetched BEFORE waiting for it:
-      // the tile's bias slice goes to smem, the residual rows of this thread to registers.
+      // the tile's bias slice goes to smem before the accumulator wait (double-buffered by `as`)
       for (int i = etid; i < BN; i += GEMM_EPI_WARPS * 32)
         sbias[as * BN + i] = __ldg(bias + n_blk * BN + i);
-      uint4 rres[NCHUNK][4];
-      if (EPI == EPI_BIAS_RESID) {
-#pragma unroll
-        for (int c = 0; c < NCHUNK; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            rres[c][j] = row_ok ? *reinterpret_cast<const uint4*>(resid + row_off + gcol0 + c * 32 + j * 8)
-                                : make_uint4(0u, 0u, 0u, 0u);
-      }
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
 
       mbar_wait(tfull_bar + 8u * as, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(as * BN + col0);
-      uint32_t r[2][32];
-      tmem_ld32(t_base, r[0]);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t acc[2][32];
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 64), acc[0]);
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 64 + 32), acc[1]);
+        // the previous TMA store must have finished READING the staging tile before we overwrite it
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
         tmem_ld_wait();
-        if (c + 1 < NCHUNK) tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), r[(c + 1) & 1]);
-        const float* bptr = sbias + as * BN + col0 + c * 32;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bptr + j * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bptr + j * 8 + 4);
-          float v[8];
-          v[0] = __uint_as_float(r[c & 1][j * 8 + 0]) + b0.x;
-          v[1] = __uint_as_float(r[c & 1][j * 8 + 1]) + b0.y;
-          v[2] = __uint_as_float(r[c & 1][j * 8 + 2]) + b0.z;
-          v[3] = __uint_as_float(r[c & 1][j * 8 + 3]) + b0.w;
-          v[4] = __uint_as_float(r[c & 1][j * 8 + 4]) + b1.x;
-          v[5] = __uint_as_float(r[c & 1][j * 8 + 5]) + b1.y;
-          v[6] = __uint_as_float(r[c & 1][j * 8 + 6]) + b1.z;
-          v[7] = __uint_as_float(r[c & 1][j * 8 + 7]) + b1.w;
-          if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-          }
-          if (EPI == EPI_BIAS_RESID) {
-            const float2 r0 = unpack_bf16x2(rres[c][j].x), r1 = unpack_bf16x2(rres[c][j].y),
-                         r2 = unpack_bf16x2(rres[c][j].z), r3 = unpack_bf16x2(rres[c][j].w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-          }
-          if (row_ok) {
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(out + row_off + gcol0 + c * 32 + j * 8) = o;
-          }
+        gemm_epilogue_chunk<EPI>(acc, sbias + as * BN + col0 + c * 64, resid_row + c * 64, row_ok,
+                                 staging, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out, staging_addr, gcol0 + c * 64, row0);  // rows >= M are clipped
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8u * as);
     }
+    if (lane == 0) tma_store_wait_all();  // stores complete before the CTA's smem goes away
   }
 
   tc_fence_before();

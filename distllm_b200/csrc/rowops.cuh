@@ -110,18 +110,34 @@ embed_layernorm_kernel(const int64_t* __restrict__ ids, const int64_t* __restric
   for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
 }
 
-// Plain LayerNorm over rows of a bf16 matrix (the residual add already happened in the GEMM epilogue).
+// x = in (+ resid when given): the residual add of the transformer block rides on the LayerNorm's
+// coalesced row reads instead of the GEMM epilogue's one-row-per-lane accesses.
+__device__ __forceinline__ void load8_residual(const bf16* in, const bf16* resid, float (&x)[8]) {
+  load8(in, x);
+  if (resid != nullptr) {
+    float r[8];
+    load8(resid, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += r[e];
+  }
+}
+
+// LayerNorm over rows of a bf16 matrix, optionally of (in + resid).  `out` may alias `resid`
+// (each warp reads its whole row before writing it).
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_kernel(const bf16* __restrict__ in, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps) {
+layernorm_kernel(const bf16* __restrict__ in, const bf16* resid, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, OutT* out, int rows, float eps) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   float x[NV][8];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) load8(in + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = static_cast<size_t>(row) * H + v * 256 + lane * 8;
+    load8_residual(in + off, resid ? resid + off : nullptr, x[v]);
+  }
   warp_layernorm<NV>(x, gamma, beta, lane, eps);
 #pragma unroll
   for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
@@ -130,9 +146,10 @@ layernorm_kernel(const bf16* __restrict__ in, const float* __restrict__ gamma,
 // LayerNorm of selected rows only: out[b] = LN(in[b*S + idx[b]])  (last-token pooling).
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_gather_kernel(const bf16* __restrict__ in, const int* __restrict__ idx,
-                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                        float* __restrict__ out, int B, int S, float eps) {
+layernorm_gather_kernel(const bf16* __restrict__ in, const bf16* __restrict__ resid,
+                        const int* __restrict__ idx, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ out, int B, int S,
+                        float eps) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -140,7 +157,10 @@ layernorm_gather_kernel(const bf16* __restrict__ in, const int* __restrict__ idx
   const size_t row = static_cast<size_t>(b) * S + idx[b];
   float x[NV][8];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) load8(in + row * H + v * 256 + lane * 8, x[v]);
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = row * H + v * 256 + lane * 8;
+    load8_residual(in + off, resid ? resid + off : nullptr, x[v]);
+  }
   warp_layernorm<NV>(x, gamma, beta, lane, eps);
 #pragma unroll
   for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(b) * H + v * 256 + lane * 8, x[v]);
@@ -246,8 +266,9 @@ __device__ __forceinline__ void block_store_partial(float (&acc)[NV][8], float* 
 // written.  grid = (B, nsplit); each warp walks rows s = split*rows_per + warp, += ROW_WARPS.
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_pool_kernel(const bf16* __restrict__ in, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, const float* __restrict__ w,
+layernorm_pool_kernel(const bf16* __restrict__ in, const bf16* __restrict__ resid,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ w,
                       float* __restrict__ part, int S, int rows_per, float eps) {
   constexpr int H = NV * 256;
   __shared__ float red[H];
@@ -265,7 +286,10 @@ layernorm_pool_kernel(const bf16* __restrict__ in, const float* __restrict__ gam
     float x[NV][8];
     const size_t row = static_cast<size_t>(b) * S + s;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) load8(in + row * H + v * 256 + lane * 8, x[v]);
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = row * H + v * 256 + lane * 8;
+      load8_residual(in + off, resid ? resid + off : nullptr, x[v]);
+    }
     warp_layernorm<NV>(x, gamma, beta, lane, eps);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
