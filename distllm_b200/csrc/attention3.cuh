@@ -1,0 +1,409 @@
+// Streaming bidirectional self-attention for head_dim 64 on sm_100a (third generation, any S).
+//
+// Persistent CTAs (one per SM) walk work items (sequence b, head h, pair of 128-row query tiles).
+// K/V of the head stream through a shared-memory ring in 64-key chunks, so the TMA loader runs
+// ahead across items (no load latency at item boundaries) and S is not limited by shared memory.
+//
+//   warp 9      loader      Q tiles (double-buffered across items) and {K_j, V_j, mask-bias_j}
+//                           ring stages: cp.async.bulk.tensor + one 256 B cp.async.bulk
+//   warp 8      MMA issuer  S_j = Q K_j^T (SS, 128x64x16) and O += P_j V_j (TS: P read from TMEM,
+//                           V_j as MN-major smem operand); per-slot state machines polled without
+//                           blocking; S is DOUBLE-buffered per slot, so Q K_{j+1}^T is issued
+//                           before softmax_j finishes and the MMA round trip leaves the softmax
+//                           critical path
+//   warps 0-3   softmax for query tile A (slot 0)    one row per thread; scores of a chunk live in
+//   warps 4-7   softmax for query tile B (slot 1)    registers; online softmax with lazy rescale;
+//                                                    bf16 P written over S's own TMEM columns
+//
+// TMEM: slot s at column 256*s: S/P buffer 0 [0,64), S/P buffer 1 [64,128), O [128,192).
+// Semantics: HF SDPA with an additive key-padding mask (transformers/models/bert/
+// modeling_bert.py:192-205, :692-716; the same call pattern serves ESM's attention).  The bias row
+// (0 attended / most-negative-finite padded / -inf beyond S) and the number of key chunks that hold
+// an attended key are prepared once per forward pass by attn_prep_kernel.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2e {
+
+constexpr int AT3_D = 64;
+constexpr int AT3_KC = 64;                            // keys per chunk
+constexpr int AT3_THREADS = 384;
+constexpr int AT3_NST = 8;                            // K/V ring stages
+constexpr int AT3_QTILE = 128 * AT3_D * 2;            // 16 KiB
+constexpr int AT3_KVTILE = AT3_KC * AT3_D * 2;        // 8 KiB
+constexpr int AT3_SMEM_Q = 0;                         // [2 item buffers][2 slots]
+constexpr int AT3_SMEM_KV = AT3_SMEM_Q + 4 * AT3_QTILE;            // stage: K | V
+constexpr int AT3_SMEM_BIAS = AT3_SMEM_KV + AT3_NST * 2 * AT3_KVTILE;
+constexpr int AT3_SMEM_BAR = AT3_SMEM_BIAS + AT3_NST * AT3_KC * 4;
+constexpr int AT3_SMEM_BYTES = AT3_SMEM_BAR + 512;
+
+constexpr float AT3_MASKED = -3.0e38f;
+constexpr float AT3_RESCALE_THRESHOLD = 8.0f;
+
+// bias[b, j] for j < S_pad (multiple of 64) and kv_chunks[b] = chunks holding an attended key
+// (all chunks when nothing is attended, so that such a row degenerates to HF's uniform softmax).
+__global__ void attn_prep_kernel(const int64_t* __restrict__ mask, float* __restrict__ bias,
+                                 int* __restrict__ kv_chunks, int B, int S, int S_pad) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  int last = 0;
+  for (int j = lane; j < S_pad; j += 32) {
+    float v = -INFINITY;
+    if (j < S) {
+      const bool on = mask[static_cast<size_t>(b) * S + j] != 0;
+      v = on ? 0.0f : AT3_MASKED;
+      if (on) last = j + 1;
+    }
+    bias[static_cast<size_t>(b) * S_pad + j] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) kv_chunks[b] = last > 0 ? (last + AT3_KC - 1) / AT3_KC : S_pad / AT3_KC;
+}
+
+// ---- softmax helpers over 32 register-resident scores (x = scale*s + bias formed on the fly)
+__device__ __forceinline__ float at3_max(const uint32_t (&s)[32], const float* __restrict__ bias,
+                                         float scale, float m) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 bz = *reinterpret_cast<const float4*>(bias + i);
+    m = fmaxf(m, fmaf(__uint_as_float(s[i + 0]), scale, bz.x));
+    m = fmaxf(m, fmaf(__uint_as_float(s[i + 1]), scale, bz.y));
+    m = fmaxf(m, fmaf(__uint_as_float(s[i + 2]), scale, bz.z));
+    m = fmaxf(m, fmaf(__uint_as_float(s[i + 3]), scale, bz.w));
+  }
+  return m;
+}
+// p = exp2(x - m) -> bf16 pairs; returns the fp32 row-sum contribution and tracks max(x)
+__device__ __forceinline__ float at3_exp_pack(const uint32_t (&s)[32], const float* __restrict__ bias,
+                                              float scale, float m, uint32_t* pk, float& xmax) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 bz = *reinterpret_cast<const float4*>(bias + i);
+    const float x0 = fmaf(__uint_as_float(s[i + 0]), scale, bz.x);
+    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale, bz.y);
+    const float x2 = fmaf(__uint_as_float(s[i + 2]), scale, bz.z);
+    const float x3 = fmaf(__uint_as_float(s[i + 3]), scale, bz.w);
+    xmax = fmaxf(fmaxf(xmax, fmaxf(x0, x1)), fmaxf(x2, x3));
+    const float p0 = fast_exp2(x0 - m), p1 = fast_exp2(x1 - m);
+    const float p2 = fast_exp2(x2 - m), p3 = fast_exp2(x3 - m);
+    sum += (p0 + p1) + (p2 + p3);
+    pk[i / 2] = pack_bf16x2(p0, p1);
+    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(AT3_THREADS, 1)
+attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
+                      const __grid_constant__ CUtensorMap tm_kv,  // [T, 3H] bf16, box 64 x 64
+                      const float* __restrict__ bias,             // [B, S_pad]
+                      const int* __restrict__ kv_chunks,          // [B]
+                      bf16* __restrict__ ctx,                     // [T, H]
+                      int B, int S, int S_pad, int heads, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  if ((sb & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5;
+  const int H = heads * AT3_D;
+  const int nq = (S + 127) / 128;
+  const int npairs = (nq + 1) / 2;
+  const int n_items = B * heads * npairs;
+
+  // barriers (8 B each)
+  const uint32_t bar0 = sb + AT3_SMEM_BAR;
+  const uint32_t kv_full = bar0;                       // [NST]
+  const uint32_t kv_empty = kv_full + 8 * AT3_NST;     // [NST]
+  const uint32_t q_full = kv_empty + 8 * AT3_NST;      // [2 buf][2 slot]
+  const uint32_t q_empty = q_full + 32;                // [2][2]
+  const uint32_t s_ready = q_empty + 32;               // [2 slot][2 sbuf]
+  const uint32_t p_ready = s_ready + 32;               // [2][2]
+  const uint32_t pv_done = p_ready + 32;               // [2][2]  P_j V_j has completed
+  const uint32_t o_ready = pv_done + 32;               // [2 slot]
+  const uint32_t o_empty = o_ready + 16;               // [2 slot]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + AT3_SMEM_BAR + 384);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_kv);
+      for (int i = 0; i < AT3_NST; ++i) {
+        mbar_init(kv_full + 8u * i, 1);
+        mbar_init(kv_empty + 8u * i, 1);
+      }
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(q_full + 8u * i, 1);
+        mbar_init(q_empty + 8u * i, 1);
+        mbar_init(s_ready + 8u * i, 1);
+        mbar_init(p_ready + 8u * i, 128);
+        mbar_init(pv_done + 8u * i, 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(o_ready + 8u * i, 1);
+        mbar_init(o_empty + 8u * i, 128);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 9) {
+      if (elect_one()) {
+        // ------------------------------------------------------------ loader
+        uint32_t chunk_ctr = 0;          // ring position, runs across items
+        uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+          const int pr = item % npairs, bh = item / npairs;
+          const int h = bh % heads, b = bh / heads;
+          const int row_base = b * S;
+          const int buf = it & 1;
+          for (int slot = 0; slot < 2; ++slot) {
+            const int t = 2 * pr + slot;
+            if (t >= nq) break;
+            const int idx = buf * 2 + slot;
+            const uint32_t bit = 1u << idx;
+            // the buffer is free once the last Q K^T of its previous tile has completed
+            if (q_any & bit) mbar_wait(q_empty + 8u * idx, ((q_par >> idx) & 1u) ^ 1u);
+            const uint32_t qb = q_full + 8u * idx;
+            mbar_expect_tx(qb, AT3_QTILE);
+            tma_load_2d(sb + AT3_SMEM_Q + idx * AT3_QTILE, &tm_q, qb, h * AT3_D, row_base + t * 128);
+            q_par ^= bit;
+            q_any |= bit;
+          }
+          const int n = kv_chunks[b];
+          for (int j = 0; j < n; ++j, ++chunk_ctr) {
+            const int st = chunk_ctr % AT3_NST;
+            const uint32_t use = chunk_ctr / AT3_NST;
+            if (use > 0) mbar_wait(kv_empty + 8u * st, (use - 1) & 1u);
+            const uint32_t fb = kv_full + 8u * st;
+            mbar_expect_tx(fb, 2 * AT3_KVTILE + AT3_KC * 4);
+            const uint32_t dst = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE;
+            tma_load_2d(dst, &tm_kv, fb, H + h * AT3_D, row_base + j * AT3_KC);
+            tma_load_2d(dst + AT3_KVTILE, &tm_kv, fb, 2 * H + h * AT3_D, row_base + j * AT3_KC);
+            bulk_load_1d(sb + AT3_SMEM_BIAS + st * AT3_KC * 4,
+                         bias + static_cast<size_t>(b) * S_pad + j * AT3_KC, AT3_KC * 4, fb);
+          }
+        }
+      }
+    } else if (warp == 8) {
+      if (elect_one()) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, AT3_KC, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, AT3_D, 0, 1);  // B (= V) is MN-major
+        uint32_t chunk_base = 0;   // ring position of this item's chunk 0
+        uint32_t q_par = 0;        // per (buf,slot) bit: parity of the q_full phase to wait for
+        uint32_t p_par = 0;        // per (slot,sbuf) bit: parity of the p_ready phase to wait for
+        uint32_t tile_cnt[2] = {0, 0};
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+          const int pr = item % npairs, bh = item / npairs;
+          const int b = bh / heads;
+          const int n = kv_chunks[b];
+          const int buf = it & 1;
+          const int n_active = (2 * pr + 1 < nq) ? 2 : 1;
+          int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
+          bool q_ok[2] = {false, false};
+          int released = 0;
+          int remaining = n_active;
+          while (remaining > 0) {
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+              if (slot >= n_active || pv_next[slot] >= n) continue;
+              const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
+              const int qidx = buf * 2 + slot;
+              // ---- S_j = Q K_j^T into S buffer j&1 (at most one chunk ahead of P_j V_j)
+              if (qk_next[slot] < n && qk_next[slot] < pv_next[slot] + 2) {
+                const int j = qk_next[slot];
+                const uint32_t c = chunk_base + j;
+                const int st = c % AT3_NST;
+                bool ready = q_ok[slot] || mbar_test(q_full + 8u * qidx, (q_par >> qidx) & 1u);
+                ready = ready && mbar_test(kv_full + 8u * st, (c / AT3_NST) & 1u);
+                if (ready) {
+                  if (!q_ok[slot]) {
+                    q_ok[slot] = true;
+                    q_par ^= 1u << qidx;
+                  }
+                  tc_fence_after();
+                  const uint64_t q_desc =
+                      make_smem_desc_sw128(sb + AT3_SMEM_Q + qidx * AT3_QTILE, 16, 1024);
+                  const uint64_t k_desc =
+                      make_smem_desc_sw128(sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE, 16, 1024);
+                  const uint32_t d = t_slot + static_cast<uint32_t>((j & 1) * 64);
+#pragma unroll
+                  for (int k = 0; k < AT3_D / 16; ++k)
+                    tc_mma_f16_ss(d, q_desc + 2u * k, k_desc + 2u * k, idesc_s,
+                                  static_cast<uint32_t>(k != 0));
+                  tc_commit(s_ready + 8u * (slot * 2 + (j & 1)));
+                  if (j + 1 == n) tc_commit(q_empty + 8u * qidx);
+                  ++qk_next[slot];
+                }
+              }
+              // ---- O += P_j V_j once the softmax warpgroup has published P_j
+              if (pv_next[slot] < qk_next[slot]) {
+                const int j = pv_next[slot];
+                const int sbuf = j & 1;
+                const int pidx = slot * 2 + sbuf;
+                if (mbar_test(p_ready + 8u * pidx, (p_par >> pidx) & 1u)) {
+                  p_par ^= 1u << pidx;
+                  // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
+                  if (j == 0 && tile_cnt[slot] > 0)
+                    mbar_wait(o_empty + 8u * slot, (tile_cnt[slot] - 1) & 1u);
+                  tc_fence_after();
+                  const uint32_t c = chunk_base + j;
+                  const int st = c % AT3_NST;
+                  const uint32_t p = t_slot + static_cast<uint32_t>(sbuf * 64);
+                  const uint32_t o = t_slot + 128u;
+                  const uint32_t v_base = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE + AT3_KVTILE;
+#pragma unroll
+                  for (int k = 0; k < AT3_KC / 16; ++k) {
+                    const uint64_t v_desc = make_smem_desc_sw128(v_base + k * 16 * 128, 1024, 1024);
+                    tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
+                                  static_cast<uint32_t>((j | k) != 0));
+                  }
+                  tc_commit(pv_done + 8u * pidx);
+                  ++pv_next[slot];
+                  if (pv_next[slot] == n) {
+                    tc_commit(o_ready + 8u * slot);
+                    ++tile_cnt[slot];
+                    --remaining;
+                  }
+                }
+              }
+            }
+            // ring stages whose chunk has been consumed by every active slot go back to the loader
+            const int done = (n_active == 2) ? min(pv_next[0], pv_next[1]) : pv_next[0];
+            while (released < done) {
+              tc_commit(kv_empty + 8u * ((chunk_base + released) % AT3_NST));
+              ++released;
+            }
+          }
+          chunk_base += static_cast<uint32_t>(n);
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int slot = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_slot = tmem_base + lane_base + static_cast<uint32_t>(slot * 256);
+    const uint32_t t_o = t_slot + 128u;
+    uint32_t chunk_base = 0;
+    uint32_t s_par = 0;   // bit sbuf: parity of the s_ready[slot][sbuf] phase to wait for
+    uint32_t o_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int pr = item % npairs, bh = item / npairs;
+      const int h = bh % heads, b = bh / heads;
+      const int n = kv_chunks[b];
+      const int t = 2 * pr + slot;
+      if (t < nq) {
+        float m_used = 0.0f, l = 0.0f;
+        for (int j = 0; j < n; ++j) {
+          const int sbuf = j & 1;
+          const uint32_t c = chunk_base + j;
+          const int st = c % AT3_NST;
+          mbar_wait(s_ready + 8u * (slot * 2 + sbuf), (s_par >> sbuf) & 1u);
+          s_par ^= 1u << sbuf;
+          mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);  // already complete: acquires the bias bytes
+          tc_fence_after();
+          const float* bias_j = reinterpret_cast<const float*>(smem + AT3_SMEM_BIAS + st * AT3_KC * 4);
+          const uint32_t t_s = t_slot + static_cast<uint32_t>(sbuf * 64);
+          uint32_t s0[32], s1[32];
+          tmem_ld32(t_s, s0);
+          tmem_ld32(t_s + 32u, s1);
+          tmem_ld_wait();
+          uint32_t pk[32];
+          if (j == 0) {
+            // first chunk of the row: exact maximum first (always finite: key 0 exists)
+            float cmax = at3_max(s0, bias_j, scale_log2e, -INFINITY);
+            cmax = at3_max(s1, bias_j + 32, scale_log2e, cmax);
+            m_used = cmax;
+            float dummy = -INFINITY;
+            l = at3_exp_pack(s0, bias_j, scale_log2e, m_used, pk, dummy);
+            l += at3_exp_pack(s1, bias_j + 32, scale_log2e, m_used, pk + 16, dummy);
+          } else {
+            // single pass with the running maximum; redo only if this chunk exceeds it by > 2^8
+            float xmax = -INFINITY;
+            float sum = at3_exp_pack(s0, bias_j, scale_log2e, m_used, pk, xmax);
+            sum += at3_exp_pack(s1, bias_j + 32, scale_log2e, m_used, pk + 16, xmax);
+            const bool need = xmax > m_used + AT3_RESCALE_THRESHOLD;
+            if (__any_sync(0xffffffffu, need)) {
+              const float m_new = need ? xmax : m_used;
+              const float sc = fast_exp2(m_used - m_new);  // 1 for rows that keep their maximum
+              m_used = m_new;
+              l *= sc;
+              float dummy = -INFINITY;
+              sum = at3_exp_pack(s0, bias_j, scale_log2e, m_used, pk, dummy);
+              sum += at3_exp_pack(s1, bias_j + 32, scale_log2e, m_used, pk + 16, dummy);
+              // O = sum_{i<j} P_i V_i must be complete before it is rescaled: S_j was issued ahead
+              // of P_{j-1} V_{j-1}, so wait for that MMA explicitly (its barrier has seen exactly
+              // as many phases as this warpgroup has published P chunks on that buffer)
+              const int pb = sbuf ^ 1;
+              mbar_wait(pv_done + 8u * (slot * 2 + pb), ((s_par >> pb) & 1u) ^ 1u);
+              tc_fence_after();
+#pragma unroll 1
+              for (int cc = 0; cc < 2; ++cc) {
+                uint32_t o[32];
+                tmem_ld32(t_o + static_cast<uint32_t>(cc * 32), o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                tmem_st32(t_o + static_cast<uint32_t>(cc * 32), o);
+              }
+            }
+            l += sum;
+          }
+          tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_ready + 8u * (slot * 2 + sbuf));
+        }
+        // ---- epilogue: O / l -> ctx
+        mbar_wait(o_ready + 8u * slot, o_cnt & 1u);
+        ++o_cnt;
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const int q = t * 128 + r;
+        bf16* dst = ctx + (static_cast<size_t>(b) * S + q) * H + h * AT3_D;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t o[32];
+          tmem_ld32(t_o + static_cast<uint32_t>(cc * 32), o);
+          tmem_ld_wait();
+          if (q < S) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+              w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+              w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+              w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + cc * 32 + i) = w;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(o_empty + 8u * slot);
+      }
+      chunk_base += static_cast<uint32_t>(n);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b2e

@@ -15,6 +15,7 @@
 
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -177,8 +178,9 @@ int check_gemm_shape(int M, int N, int K) {
 }
 
 template <int STAGES, int EPI>
-int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* bias,
-                     const bf16* resid, int M, int N, int K, int sms, cudaStream_t st) {
+int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                     const float* bias, const bf16* resid, int M, int N, int K, int sms,
+                     cudaStream_t st) {
   using Cfg = Gemm2Cfg<STAGES>;
   auto kern = gemm2_bf16_pair_kernel<STAGES, EPI>;
   static bool attr_done = false;
@@ -190,7 +192,7 @@ int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, co
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
   int grid = 2 * tiles;
   if (grid > (sms & ~1)) grid = sms & ~1;
-  kern<<<grid, G2_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, out, bias, resid, M, N, K);
+  kern<<<grid, G2_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -198,20 +200,19 @@ int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, co
 // A map: [M,K] box 128 rows; W map: [N,K] box gemm_bn_for(N) rows.
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const float* bias,
                 const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
-  bf16* o = static_cast<bf16*>(out);
   const bf16* r = static_cast<const bf16*>(resid);
-  if (N % 256 == 0 && gemm_use_pair()) {
-    switch (epi) {
-      case B2E_EPI_BIAS: return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, o, bias, r, M, N, K, sms, st);
-      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<6, EPI_BIAS_GELU>(ta, tb, o, bias, r, M, N, K, sms, st);
-      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<6, EPI_BIAS_RESID>(ta, tb, o, bias, r, M, N, K, sms, st);
-    }
-    return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
-  }
   // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
   CUtensorMap tout;
   int rc;
   if ((rc = make_tmap_bf16(&tout, out, M, N, GEMM_OUT_BOX_ROWS))) return rc;
+  if (N % 256 == 0 && gemm_use_pair()) {
+    switch (epi) {
+      case B2E_EPI_BIAS: return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<6, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<6, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
+    }
+    return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
+  }
   if (N % 256 == 0) return launch_gemm_bn<256, 4>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
   return launch_gemm_bn<128, 6>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
 }
@@ -232,28 +233,97 @@ int launch_attention_v1(const CUtensorMap& tqkv, const int64_t* mask, void* ctx,
   return B2E_OK;
 }
 
-// Pipelined kernel (attention2.cuh) unless B2E_ATTENTION=v1 or a score dump is requested.
-int launch_attention(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
-                     int heads, float* dbg, cudaStream_t st) {
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
+// Per-forward attention inputs derived from the mask (attention3.cuh): additive key bias rows and
+// the number of 64-key chunks that hold an attended key.
+struct AttnScratch {
+  float* bias = nullptr;   // [B, S_pad]
+  int* kv_chunks = nullptr;  // [B]
+  size_t cap_bias = 0, cap_b = 0;
+  int ensure(int B, int S_pad) {
+    if ((size_t)B * S_pad > cap_bias) {
+      if (bias) cudaFree(bias);
+      bias = nullptr;
+      CUDA_TRY(cudaMalloc(&bias, sizeof(float) * (size_t)B * S_pad));
+      cap_bias = (size_t)B * S_pad;
+    }
+    if ((size_t)B > cap_b) {
+      if (kv_chunks) cudaFree(kv_chunks);
+      kv_chunks = nullptr;
+      CUDA_TRY(cudaMalloc(&kv_chunks, sizeof(int) * B));
+      cap_b = B;
+    }
+    return B2E_OK;
+  }
+  void release() {
+    cudaFree(bias); cudaFree(kv_chunks);
+    bias = nullptr; kv_chunks = nullptr; cap_bias = cap_b = 0;
+  }
+};
+
+inline int attn_s_pad(int S) { return (S + AT3_KC - 1) / AT3_KC * AT3_KC; }
+
+// B2E_ATTENTION selects the kernel generation: default v3 (streaming, any S); v2 / v2clock
+// (K/V resident, S <= 512), v1 (first serialized kernel, S <= 512; also used for score dumps).
+inline int attention_mode() {
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("B2E_ATTENTION");
-    use_v1 = (e && strcmp(e, "v1") == 0) ? 1 : ((e && strcmp(e, "v2clock") == 0) ? 2 : 0);
+    mode = 3;
+    if (e && strcmp(e, "v1") == 0) mode = 1;
+    if (e && strcmp(e, "v2") == 0) mode = 2;
+    if (e && strcmp(e, "v2clock") == 0) mode = 4;
   }
-  // B2E_ATTENTION=v2clock reinterprets the debug buffer as the pipelined kernel's clock64 timeline
-  if (use_v1 == 1 || (dbg && use_v1 != 2))
-    return launch_attention_v1(tqkv, mask, ctx, B, S, heads, dbg, st);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(attention2_d64_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
-    attr_done = true;
-  }
-  dim3 grid(heads, B);
+  return mode;
+}
+inline bool attention_supports(int S) { return attention_mode() == 3 || S <= ATT_MAX_S; }
+
+int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaStream_t st) {
+  if (attention_mode() != 3) return B2E_OK;
+  int rc;
+  const int S_pad = attn_s_pad(S);
+  if ((rc = sc.ensure(B, S_pad))) return rc;
+  attn_prep_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, sc.bias, sc.kv_chunks, B, S, S_pad);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+// tq: [T,3H] box 64x128, tkv: [T,3H] box 64x64 (v3 only).  `sc` must have been prepared for `mask`.
+int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
+                     const int64_t* mask, void* ctx, int B, int S, int heads, float* dbg, int sms,
+                     cudaStream_t st) {
+  const int mode = attention_mode();
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
-      tqkv, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e,
-      use_v1 == 2 ? reinterpret_cast<long long*>(dbg) : nullptr);
+  if (mode == 1 || (dbg && mode != 4)) {
+    if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "attention v1: S=%d > %d", S, ATT_MAX_S);
+    return launch_attention_v1(tq, mask, ctx, B, S, heads, dbg, st);
+  }
+  if (mode == 2 || mode == 4) {
+    if (S > AT2_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "attention v2: S=%d > %d", S, AT2_MAX_S);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(attention2_d64_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
+      attr_done = true;
+    }
+    dim3 grid(heads, B);
+    attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
+        tq, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e,
+        mode == 4 ? reinterpret_cast<long long*>(dbg) : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return B2E_OK;
+  }
+  static bool attr3_done = false;
+  if (!attr3_done) {
+    CUDA_TRY(cudaFuncSetAttribute(attention3_d64_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
+    attr3_done = true;
+  }
+  const int nq = (S + 127) / 128;
+  const long long items = (long long)B * heads * ((nq + 1) / 2);
+  const int grid = items < sms ? (int)items : sms;
+  attention3_d64_kernel<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(
+      tq, tkv, sc.bias, sc.kv_chunks, static_cast<bf16*>(ctx), B, S, attn_s_pad(S), heads,
+      scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -347,6 +417,7 @@ int launch_finalize(PoolScratch& ps, float* out, int B, int H, int nsplit, int l
 }
 
 thread_local PoolScratch g_pool_scratch;  // for the handle-less standalone poolers
+thread_local AttnScratch g_attn_scratch;  // for the standalone attention op
 
 }  // namespace
 
@@ -360,6 +431,7 @@ struct B2EEncoder {
   size_t cap_tokens = 0;
   bf16 *hidden = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
   PoolScratch pool;
+  AttnScratch attn;
   // weight tensor maps, one per layer
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w1, tm_w2;
   // host-loop staging
@@ -406,7 +478,8 @@ int validate_batch(const B2EEncoder* e, int B, int S) {
   if (B <= 0 || S <= 0) return fail(B2E_ERR_INVALID, "empty batch B=%d S=%d", B, S);
   if (S > e->desc.max_pos)
     return fail(B2E_ERR_INVALID, "S=%d exceeds max_position_embeddings=%d", S, e->desc.max_pos);
-  if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d not supported yet", S, ATT_MAX_S);
+  if (!attention_supports(S))
+    return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d needs the streaming attention kernel", S, ATT_MAX_S);
   return B2E_OK;
 }
 
@@ -423,7 +496,9 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
                      M, S, d.eps)));
   CUDA_TRY(cudaGetLastError());
 
-  CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv;
+  if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
+  CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
+  if ((rc = make_tmap_bf16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
   if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
   if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, H, 128))) return rc;
   if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
@@ -433,7 +508,9 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->L(l, 1), nullptr, M,
                           3 * H, H, B2E_EPI_BIAS, e->sms, st)))
       return rc;
-    if ((rc = launch_attention(tm_qkv, mask, e->ctx, B, S, d.heads, nullptr, st))) return rc;
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, mask, e->ctx, B, S, d.heads, nullptr,
+                               e->sms, st)))
+      return rc;
     // the residual add rides on the LayerNorm's coalesced reads, not on the GEMM epilogue
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), nullptr, M, H, H,
                           B2E_EPI_BIAS, e->sms, st)))
@@ -528,6 +605,7 @@ void b2e_encoder_destroy(B2EEncoder* e) {
   cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
   cudaFree(e->stage_in); cudaFree(e->stage_out);
   e->pool.release();
+  e->attn.release();
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -781,13 +859,17 @@ int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, in
                       float* dbg, void* stream) {
   if (!qkv || !mask || !ctx) return fail(B2E_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || S <= 0 || heads <= 0) return fail(B2E_ERR_INVALID, "empty attention problem");
-  if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d not supported yet", S, ATT_MAX_S);
+  if (!attention_supports(S) || (dbg && S > ATT_MAX_S))
+    return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d needs the streaming attention kernel", S, ATT_MAX_S);
   int rc;
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;
-  CUtensorMap tq;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq, tkv;
   if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, 128))) return rc;
-  return launch_attention(tq, mask, ctx, B, S, heads, dbg, (cudaStream_t)stream);
+  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, AT3_KC))) return rc;
+  if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
+  return launch_attention(tq, tkv, g_attn_scratch, mask, ctx, B, S, heads, dbg, info.sms, st);
 }
 
 int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* out, int rows, int H,

@@ -47,6 +47,22 @@ struct GemmCfg {
 // (|erf error| <= 1.5e-7): gelu(x) = max(x,0) - 0.5*|x|*poly(t)*exp(-x^2/2), t = 1/(1 + p*|x|/sqrt2).
 // ~14 FP instructions + 2 MUFU per element instead of libdevice erff's ~35: the FFN-up epilogue
 // is issue-bound, and the output is rounded to bf16 (2^-9) anyway.
+// Cheaper variant used by the FFN-up epilogue: erf(x/sqrt2) ~= tanh(x * Q(x^2)) with a cubic Q fitted
+// to erf itself (max |erf error| 1.4e-5 before the hardware tanh), one MUFU (tanh.approx.f32, abs error
+// ~5e-4) instead of two.  gelu(x) = 0.5 x (1 + erf(x/sqrt2)).  Total absolute error <= ~3e-4 |x|,
+// i.e. below the bf16 rounding (2^-9 relative) the output goes through anyway.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float xc = fminf(fmaxf(x, -5.65685f), 5.65685f);  // |x|/sqrt2 <= 4: the fit's range
+  const float v = xc * xc;
+  float q = fmaf(v, -1.35688221e-05f, -1.95764464e-04f);
+  q = fmaf(v, q, 3.65498251e-02f);
+  q = fmaf(v, q, 7.97818838e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * q));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
   float t;
@@ -84,7 +100,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32]
     v[7] = __uint_as_float(a[7]) + b1.w;
     if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+      for (int e = 0; e < 8; ++e) {
+#ifdef B2E_GELU_TWO_MUFU
+        v[e] = gelu_erf(v[e]);
+#else
+        v[e] = gelu_erf_fast(v[e]);
+#endif
+      }
     }
     if (EPI == EPI_BIAS_RESID) {
       if (row_ok) {
@@ -161,6 +183,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] b
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        // (An L2 prefetch of the next tile's A rows -- cp.async.bulk.prefetch.tensor, burst or paced
+        // one per K block -- was measured 8-12 % SLOWER than no prefetch: profiles/r01_gemm_notes.md.)
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar + 8u * stage, phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;

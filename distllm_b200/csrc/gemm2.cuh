@@ -1,17 +1,18 @@
 // CTA-pair bf16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias),  N % 256 == 0.
+// EXPERIMENTAL (B2E_GEMM=pair): correct, but not yet faster than the single-CTA kernel.
 //
 // Two CTAs of one cluster (the two SMs of a TPC) cooperate on a 256 x 256 output tile with
 // tcgen05.mma.cta_group::2 (256 x 256 x 16): each CTA stages its own 128 rows of A and only HALF of
-// the W tile (128 of the 256 rows), so the shared-memory fill per SM drops from 48 KiB to 32 KiB per
-// 64-wide K block.  The single-CTA kernel (gemm.cuh) is bound by exactly that L2->SM fill rate
-// (~45-50 B/clk/SM measured: 1.0 PF/s at K=768), see DESIGN.md section 5.
+// the W tile (128 of the 256 rows), i.e. 32 KiB instead of 48 KiB per 64-wide K block, so six stages
+// fit where the single-CTA kernel has four -- 50 % more load latency can be hidden.
 //
 // Roles per CTA (384 threads):
-//   warp 0      TMA producer: A rows of this CTA + its half of W; bytes are credited to the LEADER
-//               CTA's full barrier (cp.async.bulk.tensor ... .cta_group::2)
-//   warp 1      MMA issuer, leader CTA only; completion is multicast to both CTAs' barriers
+//   warp 0      TMA producer: A rows of this CTA + its half of W, credited to the CTA's own barrier
+//   warp 1      leader CTA: MMA issuer (completion multicast to both CTAs' barriers)
+//               peer CTA:   forwards "my stage has landed" to the leader's barrier
 //   warp 2      TMEM allocator (cta_group::2: one warp in each CTA)
-//   warps 4-11  epilogue of this CTA's 128 rows (accumulator double-buffered in TMEM, 2 x 256 cols)
+//   warps 4-11  epilogue of this CTA's 128 rows: TMEM -> bias/GELU/residual -> swizzled staging
+//               -> TMA store (same code as gemm.cuh)
 #pragma once
 
 #include "common.cuh"
@@ -28,10 +29,12 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * GEMM_BK * 2;            // this CTA's 128 rows of A
   static constexpr int B_BYTES = (G2_BN / 2) * GEMM_BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KiB
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + G2_EPI_WARPS * GEMM_STAGING_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
-  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * G2_BN * 4 + 1024;
+  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * G2_BN * 4;
   static constexpr int TMEM_COLS = 2 * G2_BN;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 };
 
 // profiling aid: when set (b2e_debug_set_clock_buffer) CTAs 0/1 record clock64() timelines here
@@ -39,16 +42,15 @@ __device__ long long* g_gemm2_clock = nullptr;
 
 template <int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,   // [M,K], box 64 x 128
-                       const __grid_constant__ CUtensorMap tm_b,   // [N,K], box 64 x 128
-                       bf16* __restrict__ out, const float* __restrict__ bias,
-                       const bf16* __restrict__ resid, int M, int N, int K) {
+gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box 64 x 128
+                       const __grid_constant__ CUtensorMap tm_b,    // [N,K], box 64 x 128
+                       const __grid_constant__ CUtensorMap tm_out,  // [M,N], box 64 x 32
+                       const float* __restrict__ bias, const bf16* __restrict__ resid, int M, int N,
+                       int K) {
   using Cfg = Gemm2Cfg<STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad;
-  const uint32_t smem_base = raw + pad;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) __trap();
 
   const uint32_t full_bar = smem_base + Cfg::BAR_OFFSET;
   const uint32_t empty_bar = full_bar + 8u * STAGES;
@@ -66,6 +68,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,   // [M,K], box
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
@@ -111,9 +114,6 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,   // [M,K], box
           mbar_wait(empty_bar + 8u * stage, phase ^ 1u);
           G2_STAMP(0);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-          // Each CTA's bytes are credited to its OWN barrier: crediting the leader's barrier from
-          // the peer's TMA (cp.async.bulk.tensor...cta_group::2) measured 27 B/clk/SM of fill, far
-          // below the 45+ B/clk/SM a local barrier sustains (profiles/r01_gemm2_timeline.txt).
           const uint32_t fb = full_bar + 8u * stage;
           mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           tma_load_2d(a_dst, &tm_a, fb, kb * GEMM_BK, row_a);
@@ -168,75 +168,47 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,   // [M,K], box
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int COLS_PER_WARP = G2_BN / 2;
-    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    constexpr int NCHUNK = COLS_PER_WARP / 64;
     const int etid = threadIdx.x - 128;
     float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);  // [2][256]
+    uint8_t* staging = smem + Cfg::STAGING_OFFSET + (warp - 4) * GEMM_STAGING_BYTES;
+    const uint32_t staging_addr = smem_base + Cfg::STAGING_OFFSET + (warp - 4) * GEMM_STAGING_BYTES;
     int local = 0;
     for (int tile = cluster_id; tile < total; tile += n_clusters, ++local) {
       const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
-      const int row = m_pair * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const int row0 = m_pair * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < M;
-      const size_t row_off = static_cast<size_t>(row) * static_cast<size_t>(N);
       const int col0 = half * COLS_PER_WARP;
       const int gcol0 = n_blk * G2_BN + col0;
+      const bf16* resid_row =
+          (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       for (int i = etid; i < G2_BN; i += G2_EPI_WARPS * 32)
         sbias[as * G2_BN + i] = __ldg(bias + n_blk * G2_BN + i);
-      uint4 rres[NCHUNK][4];
-      if (EPI == EPI_BIAS_RESID) {
-#pragma unroll
-        for (int c = 0; c < NCHUNK; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            rres[c][j] = row_ok ? *reinterpret_cast<const uint4*>(resid + row_off + gcol0 + c * 32 + j * 8)
-                                : make_uint4(0u, 0u, 0u, 0u);
-      }
       asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");
 
       mbar_wait(tfull_bar + 8u * as, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(as * G2_BN + col0);
-      uint32_t r[2][32];
-      tmem_ld32(t_base, r[0]);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t acc[2][32];
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 64), acc[0]);
+        tmem_ld32(t_base + static_cast<uint32_t>(c * 64 + 32), acc[1]);
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
         tmem_ld_wait();
-        if (c + 1 < NCHUNK) tmem_ld32(t_base + static_cast<uint32_t>((c + 1) * 32), r[(c + 1) & 1]);
-        const float* bptr = sbias + as * G2_BN + col0 + c * 32;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bptr + j * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bptr + j * 8 + 4);
-          float v[8];
-          v[0] = __uint_as_float(r[c & 1][j * 8 + 0]) + b0.x;
-          v[1] = __uint_as_float(r[c & 1][j * 8 + 1]) + b0.y;
-          v[2] = __uint_as_float(r[c & 1][j * 8 + 2]) + b0.z;
-          v[3] = __uint_as_float(r[c & 1][j * 8 + 3]) + b0.w;
-          v[4] = __uint_as_float(r[c & 1][j * 8 + 4]) + b1.x;
-          v[5] = __uint_as_float(r[c & 1][j * 8 + 5]) + b1.y;
-          v[6] = __uint_as_float(r[c & 1][j * 8 + 6]) + b1.z;
-          v[7] = __uint_as_float(r[c & 1][j * 8 + 7]) + b1.w;
-          if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-          }
-          if (EPI == EPI_BIAS_RESID) {
-            const float2 r0 = unpack_bf16x2(rres[c][j].x), r1 = unpack_bf16x2(rres[c][j].y),
-                         r2 = unpack_bf16x2(rres[c][j].z), r3 = unpack_bf16x2(rres[c][j].w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-          }
-          if (row_ok) {
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(out + row_off + gcol0 + c * 32 + j * 8) = o;
-          }
+        gemm_epilogue_chunk<EPI>(acc, sbias + as * G2_BN + col0 + c * 64, resid_row + c * 64, row_ok,
+                                 staging, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          tma_store_2d(&tm_out, staging_addr, gcol0 + c * 64, row0);
+          tma_store_commit();
         }
       }
       tc_fence_before();
@@ -247,9 +219,10 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,   // [M,K], box
         else mbar_arrive_cluster(mapa_shared(tempty_bar + 8u * as, 0));
       }
     }
+    if (lane == 0) tma_store_wait_all();
   }
-
 #undef G2_STAMP
+
   tc_fence_before();
   cluster_sync_all();  // neither CTA may free TMEM / exit while the pair still references it
   if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);

@@ -63,7 +63,8 @@ def ref_attention(qkv, mask, b, s, heads):
 
 @pytest.mark.parametrize('b,s,heads,ragged', [(2, 128, 2, False), (2, 512, 12, False), (3, 200, 12, True),
                                               (2, 512, 12, True), (4, 37, 4, True), (5, 1, 4, False),
-                                              (2, 129, 4, True), (1, 384, 12, True)])
+                                              (2, 129, 4, True), (1, 384, 12, True), (2, 640, 2, False),
+                                              (1, 1026, 4, True), (3, 257, 2, True)])
 def test_attention_matches_reference(dev, b, s, heads, ragged):
     g = torch.Generator(device=dev).manual_seed(b * 1000 + s)
     qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).bfloat16()
@@ -91,10 +92,32 @@ def test_attention_mask_with_holes_and_fully_masked_row(dev):
     torch.testing.assert_close(ctx.float(), ref, rtol=2e-2, atol=1e-2)
 
 
-def test_attention_rejects_long_sequences(dev):
-    with pytest.raises(nv.NativeError, match='S=513'):
-        nv.attention_d64(torch.zeros(513, 192, device=dev, dtype=torch.bfloat16),
-                         torch.ones(1, 513, dtype=torch.int64, device=dev), 1, 513, 1)
+def test_attention_many_items_per_cta(dev):
+    """More work items than SMs: the persistent CTAs recycle Q buffers, ring stages and TMEM slots."""
+    b, s, heads = 40, 300, 12
+    g = torch.Generator(device=dev).manual_seed(77)
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).bfloat16()
+    lens = torch.randint(1, s + 1, (b,), generator=torch.Generator().manual_seed(5))
+    mask = (torch.arange(s)[None] < lens[:, None]).long().to(dev)
+    ctx = nv.attention_d64(qkv, mask, b, s, heads)
+    ref = ref_attention(qkv, mask, b, s, heads)
+    valid = mask.bool().view(-1)
+    torch.testing.assert_close(ctx.float()[valid], ref[valid], rtol=2e-2, atol=1e-2)
+    assert torch.isfinite(ctx.float()).all()
+
+
+def test_attention_large_scores_trigger_rescale(dev):
+    """Scores that grow along the key axis force the lazy online-softmax rescale path."""
+    b, s, heads = 2, 512, 2
+    g = torch.Generator(device=dev).manual_seed(78)
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g)
+    # keys later in the sequence get larger norms -> row maxima jump by far more than 2^8
+    ramp = torch.linspace(0.2, 6.0, s, device=dev).repeat(b)[:, None]
+    qkv[:, heads * 64:2 * heads * 64] *= ramp
+    qkv = qkv.bfloat16()
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    ctx = nv.attention_d64(qkv, mask, b, s, heads)
+    torch.testing.assert_close(ctx.float(), ref_attention(qkv, mask, b, s, heads), rtol=3e-2, atol=2e-2)
 
 
 @pytest.mark.parametrize('h', [256, 768, 1024, 1280])
