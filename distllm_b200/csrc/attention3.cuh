@@ -35,8 +35,11 @@ constexpr int AT3_KVTILE = AT3_KC * AT3_D * 2;        // 8 KiB
 constexpr int AT3_SMEM_Q = 0;                         // [2 item buffers][2 slots]
 constexpr int AT3_SMEM_KV = AT3_SMEM_Q + 4 * AT3_QTILE;            // stage: K | V
 constexpr int AT3_SMEM_BIAS = AT3_SMEM_KV + AT3_NST * 2 * AT3_KVTILE;
-constexpr int AT3_SMEM_BAR = AT3_SMEM_BIAS + AT3_NST * AT3_KC * 4;
+constexpr int AT3_SMEM_OST = AT3_SMEM_BIAS + AT3_NST * AT3_KC * 4;   // [2 slots] output staging tiles
+constexpr int AT3_SMEM_BAR = AT3_SMEM_OST + 2 * AT3_QTILE;
 constexpr int AT3_SMEM_BYTES = AT3_SMEM_BAR + 512;
+static_assert(AT3_SMEM_OST % 1024 == 0, "swizzled staging tiles need 1024-byte alignment");
+static_assert(AT3_SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
 constexpr float AT3_MASKED = -3.0e38f;
 constexpr float AT3_RESCALE_THRESHOLD = 8.0f;
@@ -97,12 +100,32 @@ __device__ __forceinline__ float at3_exp_pack(const uint32_t (&s)[32], const flo
   return sum;
 }
 
+// One work item = (sequence b, head h, pair of query tiles pr); n = key chunks to visit.
+struct At3Item {
+  int b, h, pr, n;
+};
+__device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
+                                              const int* __restrict__ kv_chunks, int n_items) {
+  At3Item it{0, 0, 0, 0};
+  if (item < n_items) {
+    it.pr = item % npairs;
+    const int bh = item / npairs;
+    it.h = bh % heads;
+    it.b = bh / heads;
+    it.n = __ldg(kv_chunks + it.b);
+  }
+  return it;
+}
+
+// profiling aid (b2e_debug_set_clock_buffer): CTA 0 records (clock64, code) pairs per role
+__device__ long long* g_att3_clock = nullptr;
+
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
                       const __grid_constant__ CUtensorMap tm_kv,  // [T, 3H] bf16, box 64 x 64
                       const float* __restrict__ bias,             // [B, S_pad]
                       const int* __restrict__ kv_chunks,          // [B]
-                      bf16* __restrict__ ctx,                     // [T, H]
+                      const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] bf16, box 64 x 128 x 1
                       int B, int S, int S_pad, int heads, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -130,6 +153,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     if (elect_one()) {
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_kv);
+      tma_prefetch_desc(&tm_ctx);
       for (int i = 0; i < AT3_NST; ++i) {
         mbar_init(kv_full + 8u * i, 1);
         mbar_init(kv_empty + 8u * i, 1);
@@ -154,6 +178,17 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* const clk = (blockIdx.x == 0) ? g_att3_clock : nullptr;
+  int clk_n = 0;
+  // role 0/1: softmax slot A/B (thread 0 of the warpgroup), role 2: MMA issuer; 2 x 256 int64 each
+#define AT3_STAMP(role, code)                                          \
+  do {                                                                 \
+    if (clk != nullptr && clk_n < 256) {                               \
+      clk[(role) * 512 + clk_n] = clock64();                           \
+      clk[(role) * 512 + 256 + clk_n] = (code);                        \
+      ++clk_n;                                                         \
+    }                                                                  \
+  } while (0)
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -163,9 +198,11 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         uint32_t chunk_ctr = 0;          // ring position, runs across items
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-          const int pr = item % npairs, bh = item / npairs;
-          const int h = bh % heads, b = bh / heads;
+        int item = blockIdx.x;
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+        for (; item < n_items; item += gridDim.x, ++it) {
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+          const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = b * S;
           const int buf = it & 1;
           for (int slot = 0; slot < 2; ++slot) {
@@ -181,7 +218,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             q_par ^= bit;
             q_any |= bit;
           }
-          const int n = kv_chunks[b];
+          const int n = cur.n;
           for (int j = 0; j < n; ++j, ++chunk_ctr) {
             const int st = chunk_ctr % AT3_NST;
             const uint32_t use = chunk_ctr / AT3_NST;
@@ -193,7 +230,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             tma_load_2d(dst + AT3_KVTILE, &tm_kv, fb, 2 * H + h * AT3_D, row_base + j * AT3_KC);
             bulk_load_1d(sb + AT3_SMEM_BIAS + st * AT3_KC * 4,
                          bias + static_cast<size_t>(b) * S_pad + j * AT3_KC, AT3_KC * 4, fb);
+            AT3_STAMP(3, it * 100 + j);
           }
+          cur = nxt;
         }
       }
     } else if (warp == 8) {
@@ -206,12 +245,15 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         uint32_t p_par = 0;        // per (slot,sbuf) bit: parity of the p_ready phase to wait for
         uint32_t tile_cnt[2] = {0, 0};
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-          const int pr = item % npairs, bh = item / npairs;
-          const int b = bh / heads;
-          const int n = kv_chunks[b];
+        int item = blockIdx.x;
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+        for (; item < n_items; item += gridDim.x, ++it) {
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+          const int pr = cur.pr;
+          const int n = cur.n;
           const int buf = it & 1;
           const int n_active = (2 * pr + 1 < nq) ? 2 : 1;
+          AT3_STAMP(2, 9000 + n);
           int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
           bool q_ok[2] = {false, false};
           int released = 0;
@@ -245,6 +287,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
                     tc_mma_f16_ss(d, q_desc + 2u * k, k_desc + 2u * k, idesc_s,
                                   static_cast<uint32_t>(k != 0));
                   tc_commit(s_ready + 8u * (slot * 2 + (j & 1)));
+                  AT3_STAMP(2, slot * 1000 + j * 10 + 1);
                   if (j + 1 == n) tc_commit(q_empty + 8u * qidx);
                   ++qk_next[slot];
                 }
@@ -272,6 +315,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
                                   static_cast<uint32_t>((j | k) != 0));
                   }
                   tc_commit(pv_done + 8u * pidx);
+                  AT3_STAMP(2, slot * 1000 + j * 10 + 2);
                   ++pv_next[slot];
                   if (pv_next[slot] == n) {
                     tc_commit(o_ready + 8u * slot);
@@ -289,6 +333,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             }
           }
           chunk_base += static_cast<uint32_t>(n);
+          cur = nxt;
         }
       }
     }
@@ -303,10 +348,15 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     uint32_t chunk_base = 0;
     uint32_t s_par = 0;   // bit sbuf: parity of the s_ready[slot][sbuf] phase to wait for
     uint32_t o_cnt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int pr = item % npairs, bh = item / npairs;
-      const int h = bh % heads, b = bh / heads;
-      const int n = kv_chunks[b];
+    // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
+    // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
+    int item = blockIdx.x;
+    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+    uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
+    const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
+    for (; item < n_items; item += gridDim.x) {
+      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+      const int pr = cur.pr, h = cur.h, b = cur.b, n = cur.n;
       const int t = 2 * pr + slot;
       if (t < nq) {
         float m_used = 0.0f, l = 0.0f;
@@ -314,8 +364,10 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           const int sbuf = j & 1;
           const uint32_t c = chunk_base + j;
           const int st = c % AT3_NST;
+          if (r == 0) AT3_STAMP(slot, j * 10 + 0);
           mbar_wait(s_ready + 8u * (slot * 2 + sbuf), (s_par >> sbuf) & 1u);
           s_par ^= 1u << sbuf;
+          if (r == 0) AT3_STAMP(slot, j * 10 + 1);
           mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);  // already complete: acquires the bias bytes
           tc_fence_after();
           const float* bias_j = reinterpret_cast<const float*>(smem + AT3_SMEM_BIAS + st * AT3_KC * 4);
@@ -365,42 +417,56 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             }
             l += sum;
           }
+          if (r == 0) AT3_STAMP(slot, j * 10 + 2);
           tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(p_ready + 8u * (slot * 2 + sbuf));
+          if (r == 0) AT3_STAMP(slot, j * 10 + 3);
         }
-        // ---- epilogue: O / l -> ctx
+        // ---- epilogue: O / l -> bf16 -> swizzled staging tile -> one TMA store per tile
+        if (r == 0) AT3_STAMP(slot, 900);
+        if (r == 0) tma_store_wait_read<0>();   // the previous tile's store has read the staging
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
         mbar_wait(o_ready + 8u * slot, o_cnt & 1u);
+        if (r == 0) AT3_STAMP(slot, 901);
         ++o_cnt;
         tc_fence_after();
         const float inv_l = 1.0f / l;
-        const int q = t * 128 + r;
-        bf16* dst = ctx + (static_cast<size_t>(b) * S + q) * H + h * AT3_D;
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t o[32];
           tmem_ld32(t_o + static_cast<uint32_t>(cc * 32), o);
           tmem_ld_wait();
-          if (q < S) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-              w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-              w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-              w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + cc * 32 + i) = w;
-            }
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            const int unit = cc * 4 + (i >> 3);
+            *reinterpret_cast<uint4*>(ostage + r * 128 + ((unit ^ (r & 7)) << 4)) = w;
           }
         }
         tc_fence_before();
-        mbar_arrive(o_empty + 8u * slot);
+        mbar_arrive(o_empty + 8u * slot);   // O's TMEM columns may be overwritten by the next tile
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
+        if (r == 0) {
+          // rows >= S of the last tile are clipped by the 3-D [B,S,H] tensor map
+          tma_store_3d(&tm_ctx, ostage_addr, h * AT3_D, t * 128, b);
+          tma_store_commit();
+          AT3_STAMP(slot, 902);
+        }
       }
       chunk_base += static_cast<uint32_t>(n);
+      cur = nxt;
     }
+    if (r == 0) tma_store_wait_all();
   }
 
+#undef AT3_STAMP
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 512);

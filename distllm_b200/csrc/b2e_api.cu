@@ -81,6 +81,25 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
   return B2E_OK;
 }
 
+// 3-D bf16 [batch, rows, cols] tensor (contiguous), box = 64 columns x box_rows x 1: used for
+// per-sequence TMA stores that must clip at the end of EACH sequence, not only at the tensor end.
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows,
+                      uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled 3d(batch=%llu, rows=%llu, cols=%llu) -> %d",
+                (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols, (int)r);
+  return B2E_OK;
+}
+
 struct DeviceInfo {
   int sms = 0;
   int cc_major = 0;
@@ -321,9 +340,11 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
   const int grid = items < sms ? (int)items : sms;
+  CUtensorMap tctx;  // [B, S, H]: the output store clips rows >= S per sequence
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
   attention3_d64_kernel<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(
-      tq, tkv, sc.bias, sc.kv_chunks, static_cast<bf16*>(ctx), B, S, attn_s_pad(S), heads,
-      scale_log2e);
+      tq, tkv, sc.bias, sc.kv_chunks, tctx, B, S, attn_s_pad(S), heads, scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -543,6 +564,13 @@ int b2e_version(void) { return B2E_ABI_VERSION; }
 
 // Profiling aid (not part of include/b2e.h): device buffer of 4 x 256 int64 that CTAs 0 and 1 of
 // the CTA-pair GEMM fill with clock64() stamps ([cta*2 + role][n], role 0 = producer, 1 = MMA).
+// Same idea for the streaming attention kernel: 3 roles x (256 clocks + 256 event codes) int64.
+int b2e_debug_set_att3_clock(void* device_buffer) {
+  long long* p = static_cast<long long*>(device_buffer);
+  CUDA_TRY(cudaMemcpyToSymbol(g_att3_clock, &p, sizeof(p)));
+  return B2E_OK;
+}
+
 int b2e_debug_set_clock_buffer(void* device_buffer) {
   long long* p = static_cast<long long*>(device_buffer);
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_clock, &p, sizeof(p)));
