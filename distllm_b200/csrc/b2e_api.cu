@@ -155,6 +155,27 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
+  static int cluster_probe = -1;  // B2E_GEMM=v1cluster: same kernel, launched as clusters of 2 (experiment)
+  if (cluster_probe < 0) {
+    const char* e = getenv("B2E_GEMM");
+    cluster_probe = (e && strcmp(e, "v1cluster") == 0) ? 1 : 0;
+  }
+  if (cluster_probe) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid & ~1);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, bias, resid, M, N, K));
+    return B2E_OK;
+  }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
