@@ -490,6 +490,15 @@ struct B2EEncoder {
   const float* emb_g() const { return (const float*)w[3]; }
   const float* emb_b() const { return (const float*)w[4]; }
   const void* L(int l, int k) const { return w[5 + 12 * l + k]; }
+
+  // ESM-2: fp32 residual stream, token-dropout scales, rotary tables; weight slots (weights.py):
+  //   0 word emb, 1/2 final LayerNorm; per layer (3 + 12 l): ln1 g/b, Wqkv, bqkv, Wo, bo, ln2 g/b,
+  //   W1, b1, W2, b2
+  float* xres = nullptr;
+  float* tok_scale = nullptr;
+  size_t cap_scale = 0;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  const void* E(int l, int k) const { return w[3 + 12 * l + k]; }
 };
 
 namespace {
@@ -510,7 +519,18 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     CUDA_TRY(cudaMalloc(&e->ctx, tokens * H * 2));
     CUDA_TRY(cudaMalloc(&e->tmp, tokens * H * 2));
     CUDA_TRY(cudaMalloc(&e->ffn, tokens * I * 2));
+    if (e->desc.arch == B2E_ARCH_ESM2) {
+      cudaFree(e->xres);
+      e->xres = nullptr;
+      CUDA_TRY(cudaMalloc(&e->xres, tokens * H * 4));
+    }
     e->cap_tokens = tokens;
+  }
+  if (e->desc.arch == B2E_ARCH_ESM2 && (size_t)B > e->cap_scale) {
+    cudaFree(e->tok_scale);
+    e->tok_scale = nullptr;
+    CUDA_TRY(cudaMalloc(&e->tok_scale, sizeof(float) * B));
+    e->cap_scale = B;
   }
   return e->pool.ensure(B, S, (size_t)B * pool_nsplit(S) * e->desc.hidden);
 }
@@ -576,6 +596,64 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
   return B2E_OK;
 }
 
+// ESM-2 (pre-LayerNorm, rotary): transformers/models/esm/modeling_esm.py:189-234 (embeddings with
+// token dropout), :318-362 (attention, rotary on q/k), :386-404 / :446-483 (pre-LN blocks).  The
+// residual stream e->xres stays fp32; each add_layernorm call folds the previous GEMM output into it
+// and emits the next GEMM's bf16 input.  Leaves xres (before the last FFN output is added) and e->tmp
+// (that FFN-down output): the caller applies emb_layer_norm_after to xres + tmp.
+int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
+                  cudaStream_t st) {
+  const B2EModelDesc& d = e->desc;
+  const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
+  const int mask_token = d.reserved - 1;  // reserved = mask_token_id + 1, 0 = token dropout off
+  int rc;
+  esm_token_scale_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, mask, e->tok_scale, B, S, mask_token);
+  DISPATCH_NV(H, (esm_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     ids, mask, (const float*)e->w[0], e->tok_scale, e->xres, M, S, mask_token)));
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
+  CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
+  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
+
+  DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     e->xres, nullptr, (const float*)e->E(0, 0), (const float*)e->E(0, 1), e->hidden,
+                     M, d.eps)));
+  const long long rope_work = (long long)M * d.heads * 2;
+  for (int l = 0; l < L; ++l) {
+    if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->E(l, 3), nullptr, M,
+                          3 * H, H, B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+    rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
+                                                                    M, S, d.heads);
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, mask, e->ctx, B, S, d.heads, nullptr,
+                               e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->E(l, 5), nullptr, M, H, H,
+                          B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+    DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->E(l, 6), (const float*)e->E(l, 7), e->hidden,
+                       M, d.eps)));
+    if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->E(l, 9), nullptr, M, I, H,
+                          B2E_EPI_BIAS_GELU, e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->E(l, 11), nullptr, M, H, I,
+                          B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+    if (l + 1 < L) {
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->E(l + 1, 0), (const float*)e->E(l + 1, 1),
+                         e->hidden, M, d.eps)));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
 }  // namespace
 
 // ================================================================== C ABI
@@ -602,6 +680,7 @@ const char* b2e_last_error(void) { return g_err.c_str(); }
 int b2e_num_weights(const B2EModelDesc* desc) {
   if (!desc) return -1;
   if (desc->arch == B2E_ARCH_BERT) return 5 + 12 * desc->num_layers;
+  if (desc->arch == B2E_ARCH_ESM2) return 3 + 12 * desc->num_layers;
   return -1;
 }
 
@@ -609,8 +688,11 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
                        int device, B2EEncoder** out) {
   if (!desc || !weights || !out) return fail(B2E_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (desc->arch != B2E_ARCH_BERT)
-    return fail(B2E_ERR_UNSUPPORTED, "arch %d: only B2E_ARCH_BERT is built in this round", desc->arch);
+  if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
+    return fail(B2E_ERR_UNSUPPORTED, "arch %d: only B2E_ARCH_BERT and B2E_ARCH_ESM2 are built",
+                desc->arch);
+  if (desc->arch == B2E_ARCH_ESM2 && attention_mode() != 3)
+    return fail(B2E_ERR_UNSUPPORTED, "ESM-2 needs the streaming attention kernel (unset B2E_ATTENTION)");
   if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
     return fail(B2E_ERR_UNSUPPORTED, "need head_dim 64 and heads*64 == hidden (got %d x %d, H=%d)",
                 desc->heads, desc->head_dim, desc->hidden);
@@ -635,13 +717,31 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
   e->sms = info.sms;
   const int L = desc->num_layers, H = desc->hidden, I = desc->intermediate;
   e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
+  const bool esm = desc->arch == B2E_ARCH_ESM2;
   for (int l = 0; l < L; ++l) {
-    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], e->L(l, 0), 3 * H, H, gemm_bn_for(3 * H))) ||
-        (rc = make_tmap_bf16(&e->tm_wo[l], e->L(l, 2), H, H, gemm_bn_for(H))) ||
-        (rc = make_tmap_bf16(&e->tm_w1[l], e->L(l, 6), I, H, gemm_bn_for(I))) ||
-        (rc = make_tmap_bf16(&e->tm_w2[l], e->L(l, 8), H, I, gemm_bn_for(H)))) {
+    const void* wqkv = esm ? e->E(l, 2) : e->L(l, 0);
+    const void* wo = esm ? e->E(l, 4) : e->L(l, 2);
+    const void* w1 = esm ? e->E(l, 8) : e->L(l, 6);
+    const void* w2 = esm ? e->E(l, 10) : e->L(l, 8);
+    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], wqkv, 3 * H, H, gemm_bn_for(3 * H))) ||
+        (rc = make_tmap_bf16(&e->tm_wo[l], wo, H, H, gemm_bn_for(H))) ||
+        (rc = make_tmap_bf16(&e->tm_w1[l], w1, I, H, gemm_bn_for(I))) ||
+        (rc = make_tmap_bf16(&e->tm_w2[l], w2, H, I, gemm_bn_for(H)))) {
       delete e;
       return rc;
+    }
+  }
+  if (esm) {
+    const size_t n = (size_t)desc->max_pos * 32;
+    if (cudaMalloc(&e->rope_cos, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->rope_sin, n * sizeof(float)) != cudaSuccess) {
+      b2e_encoder_destroy(e);
+      return fail(B2E_ERR_CUDA, "cudaMalloc of the rotary tables failed");
+    }
+    rope_table_kernel<<<(unsigned)((n + 255) / 256), 256>>>(e->rope_cos, e->rope_sin, desc->max_pos);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      b2e_encoder_destroy(e);
+      return fail(B2E_ERR_CUDA, "rotary table kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   *out = e;
@@ -653,6 +753,7 @@ void b2e_encoder_destroy(B2EEncoder* e) {
   cudaSetDevice(e->device);
   cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
   cudaFree(e->stage_in); cudaFree(e->stage_out);
+  cudaFree(e->xres); cudaFree(e->tok_scale); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
   e->pool.release();
   e->attn.release();
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -663,6 +764,7 @@ int64_t b2e_workspace_bytes(const B2EEncoder* e, int B, int S) {
   if (!e || B <= 0 || S <= 0) return -1;
   const size_t tokens = (size_t)B * S;
   size_t bytes = tokens_bytes(e->desc, tokens);
+  if (e->desc.arch == B2E_ARCH_ESM2) bytes += tokens * e->desc.hidden * 4 + (size_t)B * sizeof(float);
   bytes += tokens * sizeof(float) + (size_t)S * sizeof(int) + (size_t)B * (2 * sizeof(int) + sizeof(float));
   bytes += (size_t)B * pool_nsplit(S) * e->desc.hidden * sizeof(float);
   return (int64_t)bytes;
@@ -677,9 +779,24 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
     return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or BF16");
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_workspace(e, B, S))) return rc;
-  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, l = d.num_layers - 1;
+  if (d.arch == B2E_ARCH_ESM2) {
+    if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+    // emb_layer_norm_after over (residual stream + last FFN output)
+    if (out_dtype == B2E_DTYPE_F32) {
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
+                         (float*)out_hidden, M, d.eps)));
+    } else {
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
+                         (bf16*)out_hidden, M, d.eps)));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return B2E_OK;
+  }
+  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
   if (out_dtype == B2E_DTYPE_F32) {
     DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
@@ -702,12 +819,36 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     return fail(B2E_ERR_INVALID, "unknown pool_kind %d", pool_kind);
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_workspace(e, B, S))) return rc;
-  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
   const B2EModelDesc& d = e->desc;
   const int H = d.hidden, l = d.num_layers - 1;
+  PoolScratch& ps = e->pool;
+  if (d.arch == B2E_ARCH_ESM2) {
+    if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+    const int M = B * S;
+    // final LayerNorm into the bf16 hidden buffer, then the standalone pooling kernels over it
+    DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], e->hidden, M,
+                       d.eps)));
+    if (pool_kind == B2E_POOL_LAST_TOKEN) {
+      seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
+      last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
+      gather_rows_kernel<bf16><<<B, 128, 0, st>>>(e->hidden, ps.idx, out, B, S, H);
+      if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
+      CUDA_TRY(cudaGetLastError());
+      return B2E_OK;
+    }
+    if ((rc = launch_pool_weights(ps, const_cast<int64_t*>(mask), B, S, pool_kind, 0, st))) return rc;
+    const int nsplit = pool_nsplit(S);
+    const int rows_per = (S + nsplit - 1) / nsplit;
+    dim3 grid(B, nsplit);
+    DISPATCH_NV(H, (pool_sum_kernel<NV, bf16><<<grid, ROW_THREADS, 0, st>>>(e->hidden, ps.w, ps.part, S,
+                                                                          rows_per)));
+    CUDA_TRY(cudaGetLastError());
+    return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
+  }
+  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
   const float* g = (const float*)e->L(l, 10);
   const float* bt = (const float*)e->L(l, 11);
-  PoolScratch& ps = e->pool;
   if (pool_kind == B2E_POOL_LAST_TOKEN) {
     seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
     last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);

@@ -432,3 +432,115 @@ __global__ void adjacent_cosine_kernel(const T* __restrict__ emb, const int* __r
 }
 
 }  // namespace b2e
+
+// ====================================================================== ESM-2 (pre-LayerNorm) pieces
+namespace b2e {
+
+// scale[b] = (1 - 0.12) / (1 - n_mask_tokens / n_attended): ESM's "token dropout" compensation
+// (transformers/models/esm/modeling_esm.py:217-224).  mask_token < 0 disables it (scale 1).
+__global__ void esm_token_scale_kernel(const int64_t* __restrict__ ids,
+                                       const int64_t* __restrict__ mask, float* __restrict__ scale,
+                                       int B, int S, int mask_token) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  float n_mask = 0.0f, n_att = 0.0f;
+  for (int s = lane; s < S; s += 32) {
+    const size_t i = static_cast<size_t>(b) * S + s;
+    n_att += static_cast<float>(mask[i]);
+    n_mask += (mask_token >= 0 && ids[i] == mask_token) ? 1.0f : 0.0f;
+  }
+  n_mask = warp_sum(n_mask);
+  n_att = warp_sum(n_att);
+  if (lane == 0) scale[b] = mask_token >= 0 ? (1.0f - 0.15f * 0.8f) / (1.0f - n_mask / n_att) : 1.0f;
+}
+
+// x[t,:] = word[ids[t]] (zero for <mask> tokens) * scale[b] * attention_mask[t]  -> fp32 residual stream
+// (modeling_esm.py:189-234 with rotary positions: no position table, no embedding LayerNorm)
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS)
+esm_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                 const float* __restrict__ word, const float* __restrict__ scale,
+                 float* __restrict__ xres, int rows, int S, int mask_token) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t id = ids[row];
+  float f = scale[row / S] * static_cast<float>(mask[row]);
+  if (mask_token >= 0 && id == mask_token) f = 0.0f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = v * 256 + lane * 8;
+    float w[8];
+    load8(word + static_cast<size_t>(id) * H + c, w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] *= f;
+    store8(xres + static_cast<size_t>(row) * H + c, w);
+  }
+}
+
+// Residual stream update fused with the next LayerNorm (pre-LN blocks):
+//   xres += add (bf16 GEMM output; nullptr on the very first call);  out = LayerNorm(xres)
+// The fp32 residual stream keeps 33 layers of accumulation out of bf16.
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(ROW_THREADS)
+add_layernorm_kernel(float* __restrict__ xres, const bf16* __restrict__ add,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     OutT* __restrict__ out, int rows, float eps) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = static_cast<size_t>(row) * H + v * 256 + lane * 8;
+    load8(xres + off, x[v]);
+    if (add != nullptr) {
+      float a[8];
+      load8(add + off, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[v][e] += a[e];
+      store8(xres + off, x[v]);
+    }
+  }
+  warp_layernorm<NV>(x, gamma, beta, lane, eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
+}
+
+// cos/sin tables for rotary embeddings, [max_pos, 32] each: angle(p, i) = p * 10000^(-2i/64)
+// (modeling_esm.py:81-123, head_dim 64)
+__global__ void rope_table_kernel(float* __restrict__ cos_t, float* __restrict__ sin_t, int max_pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_pos * 32) return;
+  const int p = i / 32, k = i % 32;
+  const float inv_freq = powf(10000.0f, -static_cast<float>(2 * k) / 64.0f);
+  float s, c;
+  sincosf(static_cast<float>(p) * inv_freq, &s, &c);
+  cos_t[i] = c;
+  sin_t[i] = s;
+}
+
+// In-place rotary embedding of the Q and K thirds of qkv [T, 3H] (head_dim 64, halves of 32):
+//   out[i] = x[i] cos - x[i+32] sin ;  out[i+32] = x[i+32] cos + x[i] sin     (position = t % S)
+// One warp per (token, head pair of Q|K); lane = frequency index i.
+__global__ void rope_qk_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_t,
+                               const float* __restrict__ sin_t, int T, int S, int heads) {
+  const int H = heads * 64;
+  const int lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_work = static_cast<long long>(T) * heads * 2;  // q heads then k heads
+  if (w >= n_work) return;
+  const int t = static_cast<int>(w / (heads * 2));
+  const int hk = static_cast<int>(w % (heads * 2));  // [0, heads): q head, [heads, 2*heads): k head
+  bf16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
+  const int pos = t % S;
+  const float c = cos_t[pos * 32 + lane], s = sin_t[pos * 32 + lane];
+  const float x1 = __bfloat162float(p[lane]), x2 = __bfloat162float(p[lane + 32]);
+  p[lane] = __float2bfloat16_rn(x1 * c - x2 * s);
+  p[lane + 32] = __float2bfloat16_rn(x2 * c + x1 * s);
+}
+
+}  // namespace b2e

@@ -1,4 +1,5 @@
-"""Encoder family.  ``auto`` is native; ``esm2``/``esmc`` keep their names but are not built yet."""
+"""Encoder family: ``auto`` (BERT-family checkpoints) and ``esm2``, both on the native kernels.
+``esmc`` (needs the ``esm`` package) is not provided."""
 
 from __future__ import annotations
 
@@ -9,12 +10,15 @@ from distllm_b200.embed._factory import build_from_strategies
 from distllm_b200.embed.encoders.auto import AutoEncoder
 from distllm_b200.embed.encoders.auto import AutoEncoderConfig
 from distllm_b200.embed.encoders.base import Encoder
+from distllm_b200.embed.encoders.esm2 import Esm2Encoder
+from distllm_b200.embed.encoders.esm2 import Esm2EncoderConfig
 from distllm_b200.registry import registry
 from distllm_b200.utils import BaseConfig
 
-EncoderConfigs = Union[AutoEncoderConfig]
+EncoderConfigs = Union[Esm2EncoderConfig, AutoEncoderConfig]
 
 STRATEGIES: dict[str, tuple[type[BaseConfig], type[Encoder]]] = {
+    'esm2': (Esm2EncoderConfig, Esm2Encoder),
     'auto': (AutoEncoderConfig, AutoEncoder),
 }
 

@@ -12,11 +12,15 @@ from distllm_b200.embed.encoders import weights as W
 
 
 class NativeBertEncoder:
-    """BERT-family forward pass on libb2e (tcgen05 GEMMs + fused attention + row kernels).
+    """Encoder forward pass on libb2e (tcgen05 GEMMs + fused attention + row kernels).
 
     Holds the device weight tensors (the C handle only borrows their pointers) and wraps
-    ``b2e_encode`` / ``b2e_encode_pooled`` / ``b2e_embed_host``.
+    ``b2e_encode`` / ``b2e_encode_pooled`` / ``b2e_embed_host``.  ``_DESC`` / ``_WEIGHTS`` pick the
+    architecture: BERT here, ESM-2 in the ``NativeEsm2Encoder`` subclass.
     """
+
+    _DESC = staticmethod(W.bert_desc)
+    _WEIGHTS = staticmethod(W.bert_weight_list)
 
     def __init__(self, hf_config, state_dict: Mapping[str, torch.Tensor],
                  device: torch.device | str | None = None) -> None:
@@ -28,10 +32,10 @@ class NativeBertEncoder:
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self.hf_config = hf_config
-        self.desc = W.bert_desc(hf_config)
+        self.desc = self._DESC(hf_config)
         self.hidden_size = hf_config.hidden_size
         self.max_positions = hf_config.max_position_embeddings
-        self._weights = W.bert_weight_list(state_dict, hf_config.num_hidden_layers, self.device)
+        self._weights = self._WEIGHTS(state_dict, hf_config.num_hidden_layers, self.device)
         n = len(self._weights)
         expected = lib.b2e_num_weights(C.byref(self.desc))
         if n != expected:
@@ -124,3 +128,10 @@ class NativeBertEncoder:
             self._handle, input_ids.data_ptr(), attention_mask.data_ptr(),
             _native._ptr(token_type_ids), n, s, batch, pool_kind, int(normalize), out.data_ptr()))
         return out
+
+
+class NativeEsm2Encoder(NativeBertEncoder):
+    """ESM-2 (pre-LayerNorm, rotary, token dropout) on the same kernels; ``token_type_ids`` unused."""
+
+    _DESC = staticmethod(W.esm_desc)
+    _WEIGHTS = staticmethod(W.esm_weight_list)

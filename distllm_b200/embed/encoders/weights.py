@@ -133,3 +133,121 @@ def random_bert_state_dict(hf_config, seed: int = 0, device: torch.device | str 
             sd[p + name + '.weight'] = torch.ones(h, device=device)
             sd[p + name + '.bias'] = torch.zeros(h, device=device)
     return sd
+
+
+# --------------------------------------------------------------------------- ESM-2
+# ``B2E_ARCH_ESM2``, 3 + 12*L device tensors (HF EsmModel / EsmForMaskedLM names, ``esm.`` prefix
+# stripped; transformers/models/esm/modeling_esm.py):
+#
+#     0 embeddings.word_embeddings [V,H] f32
+#     1 encoder.emb_layer_norm_after.weight   2 .bias                         (f32 [H])
+#     per layer l, base = 3 + 12*l (pre-LayerNorm blocks):
+#       +0 attention.LayerNorm.weight  +1 .bias                 (LN before self-attention)
+#       +2 Wqkv [3H,H] bf16 (query | key | value)               +3 bqkv [3H] f32
+#       +4 attention.output.dense.weight [H,H] bf16             +5 .bias
+#       +6 LayerNorm.weight            +7 .bias                 (LN before the feed-forward)
+#       +8 intermediate.dense.weight [I,H] bf16                 +9 .bias
+#       +10 output.dense.weight [H,I] bf16                      +11 .bias
+#
+# ``B2EModelDesc.reserved`` carries ``mask_token_id + 1`` when ``token_dropout`` is on (0 = off).
+
+
+def esm_desc(hf_config) -> _native.ModelDesc:
+    """Translate a HF ``EsmConfig`` (ESM-2 family) into the C ``B2EModelDesc``."""
+    if getattr(hf_config, 'position_embedding_type', 'absolute') != 'rotary':
+        raise NotImplementedError('only rotary ESM-2 checkpoints are supported')
+    if getattr(hf_config, 'emb_layer_norm_before', False):
+        raise NotImplementedError('emb_layer_norm_before=True (ESM-1b style) is not built')
+    heads = hf_config.num_attention_heads
+    token_dropout = bool(getattr(hf_config, 'token_dropout', False))
+    return _native.ModelDesc(
+        arch=_native.ARCH_ESM2,
+        num_layers=hf_config.num_hidden_layers,
+        hidden=hf_config.hidden_size,
+        heads=heads,
+        kv_heads=heads,
+        head_dim=hf_config.hidden_size // heads,
+        intermediate=hf_config.intermediate_size,
+        vocab=hf_config.vocab_size,
+        max_pos=hf_config.max_position_embeddings,
+        type_vocab=0,
+        eps=float(hf_config.layer_norm_eps),
+        rope_theta=10000.0,
+        sliding_window=0,
+        reserved=(int(hf_config.mask_token_id) + 1) if token_dropout else 0,
+    )
+
+
+def esm_weight_list(
+    state_dict: Mapping[str, torch.Tensor],
+    num_layers: int,
+    device: torch.device,
+) -> list[torch.Tensor]:
+    """HF EsmModel/EsmForMaskedLM state dict -> contiguous device tensors in ABI order."""
+    sd = {k[4:] if k.startswith('esm.') else k: v for k, v in state_dict.items()}
+
+    def f32(key: str) -> torch.Tensor:
+        return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
+
+    def b16(t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+    out = [
+        f32('embeddings.word_embeddings.weight'),
+        f32('encoder.emb_layer_norm_after.weight'),
+        f32('encoder.emb_layer_norm_after.bias'),
+    ]
+    for layer in range(num_layers):
+        p = f'encoder.layer.{layer}.'
+        qkv_w = torch.cat([sd[p + f'attention.self.{n}.weight'] for n in ('query', 'key', 'value')])
+        qkv_b = torch.cat([sd[p + f'attention.self.{n}.bias'] for n in ('query', 'key', 'value')])
+        out += [
+            f32(p + 'attention.LayerNorm.weight'),
+            f32(p + 'attention.LayerNorm.bias'),
+            b16(qkv_w),
+            qkv_b.detach().to(device=device, dtype=torch.float32).contiguous(),
+            b16(sd[p + 'attention.output.dense.weight']),
+            f32(p + 'attention.output.dense.bias'),
+            f32(p + 'LayerNorm.weight'),
+            f32(p + 'LayerNorm.bias'),
+            b16(sd[p + 'intermediate.dense.weight']),
+            f32(p + 'intermediate.dense.bias'),
+            b16(sd[p + 'output.dense.weight']),
+            f32(p + 'output.dense.bias'),
+        ]
+    return out
+
+
+def random_esm_state_dict(hf_config, seed: int = 0, device: torch.device | str = 'cpu',
+                          std: float | None = None) -> dict[str, torch.Tensor]:
+    """Seeded random ESM-2 weights with HF EsmModel names (no ``esm.`` prefix)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    std = getattr(hf_config, 'initializer_range', 0.02) if std is None else std
+    h, i = hf_config.hidden_size, hf_config.intermediate_size
+
+    def normal(*shape: int) -> torch.Tensor:
+        return torch.randn(*shape, generator=gen, device=device, dtype=torch.float32) * std
+
+    def ln(prefix: str, sd: dict) -> None:
+        # non-trivial LayerNorm parameters so that both gamma and beta paths are exercised
+        sd[prefix + '.weight'] = 1.0 + normal(h)
+        sd[prefix + '.bias'] = normal(h)
+
+    sd: dict[str, torch.Tensor] = {'embeddings.word_embeddings.weight': normal(hf_config.vocab_size, h)}
+    ln('encoder.emb_layer_norm_after', sd)
+    for layer in range(hf_config.num_hidden_layers):
+        p = f'encoder.layer.{layer}.'
+        for name, (o, k) in {
+            'attention.self.query': (h, h),
+            'attention.self.key': (h, h),
+            'attention.self.value': (h, h),
+            'attention.output.dense': (h, h),
+            'intermediate.dense': (i, h),
+            'output.dense': (h, i),
+        }.items():
+            sd[p + name + '.weight'] = normal(o, k)
+            sd[p + name + '.bias'] = normal(o)
+        ln(p + 'attention.LayerNorm', sd)
+        ln(p + 'LayerNorm', sd)
+    return sd

@@ -162,6 +162,76 @@ def make_bert_golden() -> None:
     np.savez_compressed(GOLDEN / 'bert_tiny_golden.npz', **out)
 
 
+TINY_ESM = dict(vocab_size=33, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                intermediate_size=512, max_position_embeddings=160, position_embedding_type='rotary',
+                token_dropout=True, mask_token_id=32, pad_token_id=1, layer_norm_eps=1e-5,
+                emb_layer_norm_before=False, hidden_dropout_prob=0.0,
+                attention_probs_dropout_prob=0.0, initializer_range=0.05)
+TINY_ESM_SEED = 4321
+ESM_VOCAB = ['<cls>', '<pad>', '<eos>', '<unk>', 'L', 'A', 'G', 'V', 'S', 'E', 'R', 'T', 'I', 'D', 'P',
+             'K', 'Q', 'N', 'F', 'Y', 'M', 'H', 'W', 'C', 'X', 'B', 'U', 'Z', 'O', '.', '-', '<null_1>',
+             '<mask>']
+
+
+def make_esm_golden() -> None:
+    """The reference's own Esm2Encoder (HF EsmForMaskedLM) + MeanPooler + compute_embeddings on a
+    tiny seeded ESM-2 checkpoint with rotary positions and token dropout."""
+    from torch.utils.data import DataLoader
+    from transformers import EsmConfig
+    from transformers import EsmForMaskedLM
+    from transformers import EsmTokenizer
+
+    from distllm.embed.datasets.utils import DataCollator
+    from distllm.embed.datasets.utils import InMemoryDataset
+    from distllm.embed.embedders.full_sequence import compute_embeddings
+    from distllm.embed.encoders.esm2 import Esm2Encoder
+    from distllm.embed.encoders.esm2 import Esm2EncoderConfig
+    from distllm.embed.poolers.mean import MeanPooler
+    from distllm.embed.poolers.mean import MeanPoolerConfig
+    from distllm_b200.embed.encoders.weights import random_esm_state_dict
+
+    cfg = EsmConfig(**TINY_ESM)
+    sd = random_esm_state_dict(cfg, seed=TINY_ESM_SEED, device='cpu')
+    model = EsmForMaskedLM(cfg)
+    missing, unexpected = model.load_state_dict({'esm.' + k: v for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    # missing = parts the hot path never touches (LM head, contact head) and the rotary inv_freq buffers
+    assert all(k.startswith(('lm_head.', 'esm.contact_head.', 'esm.embeddings.position'))
+               or k.endswith('rotary_embeddings.inv_freq') for k in missing), missing
+    model.eval()
+
+    rng = np.random.default_rng(9)
+    residues = list('LAGVSERTIDPKQNFYMHWC')
+    lengths = [12, 150, 33, 1, 64, 64, 200, 7, 90, 41]   # 200 residues -> truncated to 160 tokens
+    seqs = [''.join(rng.choice(residues, size=n)) for n in lengths]
+    seqs[2] = seqs[2][:10] + '<mask>' + seqs[2][10:20] + '<mask>' + seqs[2][20:]  # token-dropout rows
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp_path = Path(tmp)
+        (tmp_path / 'vocab.txt').write_text('\n'.join(ESM_VOCAB) + '\n')
+        tok = EsmTokenizer(str(tmp_path / 'vocab.txt'))
+        model.save_pretrained(tmp_path / 'ckpt')
+        tok.save_pretrained(tmp_path / 'ckpt')
+        encoder = Esm2Encoder(Esm2EncoderConfig(
+            pretrained_model_name_or_path=str(tmp_path / 'ckpt'), half_precision=False))
+        assert encoder.tokenizer.model_max_length == TINY_ESM['max_position_embeddings']
+
+        def loader() -> DataLoader:
+            return DataLoader(InMemoryDataset(seqs), batch_size=4, num_workers=0,
+                              collate_fn=DataCollator(encoder.tokenizer))
+
+        out = {'weights_sha256': np.array(weights_digest(sd)), 'n_texts': np.array(len(seqs))}
+        for i, batch in enumerate(loader()):
+            out[f'batch{i}/input_ids'] = batch['input_ids'].numpy()
+            out[f'batch{i}/attention_mask'] = batch['attention_mask'].numpy()
+            if i == 0:
+                with torch.no_grad():
+                    out['batch0/hidden'] = encoder.encode(batch).numpy()
+        out['n_batches'] = np.array(i + 1)
+        out['pooled/mean'] = compute_embeddings(loader(), encoder, MeanPooler(MeanPoolerConfig()))
+    np.savez_compressed(GOLDEN / 'esm_tiny_golden.npz', **out)
+
+
 def main() -> None:
     if not REFERENCE.exists():
         raise SystemExit('/root/reference is not available: golden vectors can only be (re)generated '
@@ -173,6 +243,7 @@ def main() -> None:
     make_pool_golden()
     make_semantic_golden()
     make_bert_golden()
+    make_esm_golden()
     for f in sorted(GOLDEN.glob('*.npz')):
         print(f.name, f.stat().st_size, 'bytes')
 

@@ -57,6 +57,25 @@ def tiny_bert():
     return cfg, random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
 
 
+@pytest.fixture(scope='session')
+def esm_golden():
+    return np.load(GOLDEN / 'esm_tiny_golden.npz')
+
+
+@pytest.fixture(scope='session')
+def tiny_esm():
+    """(HF config, seeded state dict) of the tiny ESM-2 checkpoint behind esm_tiny_golden.npz."""
+    from transformers import EsmConfig
+
+    from oracle.make_golden import TINY_ESM
+    from oracle.make_golden import TINY_ESM_SEED
+
+    from distllm_b200.embed.encoders.weights import random_esm_state_dict
+
+    cfg = EsmConfig(**TINY_ESM)
+    return cfg, random_esm_state_dict(cfg, seed=TINY_ESM_SEED, device='cpu')
+
+
 def cosine_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = a.astype(np.float64)
     b = b.astype(np.float64)

@@ -239,3 +239,70 @@ def test_semantic_chunk_embedder_end_to_end(tmp_path, tiny_bert, tiny_native):
         ref.append(opool.average_pool(hidden, enc_b['attention_mask'].clone()))
     cos = cosine_rows(result.embeddings, torch.cat(ref).numpy())
     assert cos.min() > 1 - COS_TOL, cos
+
+
+# ---------------------------------------------------------------------------------- ESM-2
+def test_esm2_matches_reference_vectors(tiny_esm, esm_golden):
+    """esm2 encoder through the plugin API vs the reference's Esm2Encoder outputs (rotary positions,
+    token dropout rows, a row truncated to max_position_embeddings, S up to 160 > 128)."""
+    from distllm_b200.embed.encoders.esm2 import Esm2Encoder
+    from distllm_b200.embed.encoders.native import NativeEsm2Encoder
+
+    cfg, sd = tiny_esm
+    native = NativeEsm2Encoder(cfg, sd)
+    try:
+        encoder = Esm2Encoder.from_native(native)
+        batches = [{k: torch.from_numpy(esm_golden[f'batch{i}/{k}']) for k in ('input_ids', 'attention_mask')}
+                   for i in range(int(esm_golden['n_batches']))]
+        hidden = encoder.encode(BatchEncoding(batches[0])).cpu().numpy()
+        ref = esm_golden['batch0/hidden']
+        valid = batches[0]['attention_mask'].bool().numpy()
+        cos = cosine_rows(hidden[valid], ref[valid])
+        assert cos.min() > 1 - COS_TOL, cos.min()
+        for fused in (True, False):
+            enc = encoder
+            if not fused:
+                class Unfused:
+                    dtype, device, embedding_size = encoder.dtype, encoder.device, encoder.embedding_size
+                    tokenizer = None
+                    encode = staticmethod(encoder.encode)
+                enc = Unfused()
+            result = get_embedder({'name': 'full_sequence'}).embed(loader_of(batches), enc, get_pooler({'name': 'mean'}))
+            cos = cosine_rows(result.embeddings, esm_golden['pooled/mean'])
+            assert cos.min() > 1 - COS_TOL, (fused, cos)
+    finally:
+        native.close()
+
+
+def test_esm2_650m_width_vs_oracle():
+    """ESM2-650M layer shape (H=1280, 20 heads, I=5120) with 3 layers, S=300 ragged, vs the CPU oracle."""
+    from transformers import EsmConfig
+
+    from distllm_b200.embed.encoders.native import NativeEsm2Encoder
+    from distllm_b200.embed.encoders.weights import random_esm_state_dict
+    from oracle import esm as oesm
+
+    cfg = EsmConfig(vocab_size=33, hidden_size=1280, num_hidden_layers=3, num_attention_heads=20,
+                    intermediate_size=5120, max_position_embeddings=1026, position_embedding_type='rotary',
+                    token_dropout=True, mask_token_id=32, pad_token_id=1, layer_norm_eps=1e-5,
+                    emb_layer_norm_before=False, initializer_range=0.02)
+    sd = random_esm_state_dict(cfg, seed=3, device='cpu')
+    g = torch.Generator().manual_seed(4)
+    b, s = 3, 300
+    ids = torch.randint(4, 24, (b, s), generator=g)
+    lens = torch.tensor([300, 41, 177])
+    mask = (torch.arange(s)[None] < lens[:, None]).long()
+    ids = ids.masked_fill(mask == 0, 1)
+    ids[:, 0] = 0
+    ref_hidden = oesm.esm_forward(sd, cfg, ids, mask)
+    ref = opool.average_pool(ref_hidden, mask.clone()).numpy()
+    native = NativeEsm2Encoder(cfg, sd)
+    try:
+        got = native.encode_pooled(ids, mask, None, nv.POOL_MEAN_REF, False).cpu().numpy()
+        cos = cosine_rows(got, ref)
+        assert cos.min() > 1 - COS_TOL, cos
+        hidden = native.encode(ids, mask).cpu().numpy()
+        valid = mask.bool().numpy()
+        assert cosine_rows(hidden[valid], ref_hidden.numpy()[valid]).min() > 1 - COS_TOL
+    finally:
+        native.close()

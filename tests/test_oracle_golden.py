@@ -115,3 +115,54 @@ def test_oracle_forward_matches_hf_bertmodel(tiny_bert):
     assert len(got) == len(ref)
     for a, b in zip(got, ref):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------- ESM-2
+def _esm_batches(golden):
+    for i in range(int(golden['n_batches'])):
+        yield {k: torch.from_numpy(golden[f'batch{i}/{k}']) for k in ('input_ids', 'attention_mask')}
+
+
+def test_esm_weights_are_reproducible(esm_golden, tiny_esm):
+    _, sd = tiny_esm
+    assert weights_digest(sd) == str(esm_golden['weights_sha256'])
+
+
+def test_esm_oracle_matches_reference_hidden_and_embeddings(esm_golden, tiny_esm):
+    """oracle ESM-2 forward (+ reference-semantics mean pool) == distllm's Esm2Encoder outputs,
+    including the rows that contain <mask> tokens (token dropout) and the truncated 160-token row."""
+    from oracle import esm as oesm
+
+    cfg, sd = tiny_esm
+    batches = list(_esm_batches(esm_golden))
+    hidden = oesm.esm_forward(sd, cfg, batches[0]['input_ids'], batches[0]['attention_mask'])
+    np.testing.assert_allclose(hidden.numpy(), esm_golden['batch0/hidden'], rtol=1e-4, atol=5e-5)
+    assert (batches[0]['input_ids'] == cfg.mask_token_id).any(), 'fixture must exercise token dropout'
+
+    got = opool.compute_embeddings(
+        batches, lambda b: oesm.esm_forward(sd, cfg, b['input_ids'], b['attention_mask']),
+        opool.average_pool)
+    np.testing.assert_allclose(got, esm_golden['pooled/mean'], rtol=1e-4, atol=5e-5)
+
+
+def test_esm_oracle_matches_hf_esm_model(tiny_esm):
+    from transformers import EsmModel
+
+    from oracle import esm as oesm
+
+    cfg, sd = tiny_esm
+    model = EsmModel(cfg, add_pooling_layer=False)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    g = torch.Generator().manual_seed(8)
+    ids = torch.randint(4, 24, (3, 70), generator=g)
+    ids[:, 0] = 0
+    ids[1, 5] = cfg.mask_token_id
+    lens = torch.tensor([70, 9, 33])
+    mask = (torch.arange(70)[None] < lens[:, None]).long()
+    ids = ids.masked_fill(mask == 0, cfg.pad_token_id)
+    with torch.no_grad():
+        ref = model(input_ids=ids, attention_mask=mask).last_hidden_state
+    got = oesm.esm_forward(sd, cfg, ids, mask)
+    valid = mask.bool()
+    np.testing.assert_allclose(got[valid].numpy(), ref[valid].numpy(), rtol=1e-4, atol=5e-5)
