@@ -59,9 +59,10 @@ def flops_per_chunk(cfg: dict, s: int) -> float:
 
 
 def launches_per_step(cfg: dict) -> int:
-    """Kernels of ours per step: embed+LN, per layer 4 GEMMs + attention + 2 LayerNorms (the last
-    LayerNorm is the fused LN+pool), 3 pool-weight kernels, pool finalize, adjacent-cosine."""
-    return 1 + cfg['num_hidden_layers'] * 7 + 3 + 1 + 1
+    """Kernels of ours per step: embed+LN, attention mask prep, per layer 4 GEMMs + attention +
+    2 LayerNorms (the last LayerNorm is the fused LN+pool), 3 pool-weight kernels, pool finalize,
+    adjacent-cosine (matches the ncu launch list in profiles/)."""
+    return 1 + 1 + cfg['num_hidden_layers'] * 7 + 3 + 1 + 1
 
 
 def load_peaks() -> tuple[dict, str]:
