@@ -247,7 +247,15 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   if ((rc = make_tmap_bf16(&tout, out, M, N, GEMM_OUT_BOX_ROWS))) return rc;
   if (N % 256 == 0 && gemm_use_pair()) {
     switch (epi) {
-      case B2E_EPI_BIAS: return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS: {
+        static int stages = -1;  // experiment knob: B2E_PAIR_STAGES=3
+        if (stages < 0) {
+          const char* e = getenv("B2E_PAIR_STAGES");
+          stages = e ? atoi(e) : 6;
+        }
+        if (stages == 3) return launch_gemm2_cfg<3, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
+        return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      }
       case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<6, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
       case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<6, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
     }
@@ -667,6 +675,12 @@ int b2e_version(void) { return B2E_ABI_VERSION; }
 int b2e_debug_set_att3_clock(void* device_buffer) {
   long long* p = static_cast<long long*>(device_buffer);
   CUDA_TRY(cudaMemcpyToSymbol(g_att3_clock, &p, sizeof(p)));
+  return B2E_OK;
+}
+
+// Experiment knob for the CTA-pair GEMM: bit 0 = skip the epilogue's math and stores.
+int b2e_debug_set_pair_flags(int flags) {
+  CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_flags, &flags, sizeof(flags)));
   return B2E_OK;
 }
 

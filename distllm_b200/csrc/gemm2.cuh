@@ -39,6 +39,7 @@ struct Gemm2Cfg {
 
 // profiling aid: when set (b2e_debug_set_clock_buffer) CTAs 0/1 record clock64() timelines here
 __device__ long long* g_gemm2_clock = nullptr;
+__device__ int g_gemm2_flags = 0;  // experiment knob, bit 0: skip epilogue math + stores
 
 template <int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
@@ -202,6 +203,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         tmem_ld_wait();
+        if (g_gemm2_flags & 1) continue;
         gemm_epilogue_chunk<EPI>(acc, sbias + as * G2_BN + col0 + c * 64, resid_row + c * 64, row_ok,
                                  staging, lane);
         fence_proxy_async_smem();
