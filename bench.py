@@ -17,9 +17,10 @@ Printed JSON (one line, rank 0):
   value      chunks/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        chunks/s through the C-ABI host-buffer call (b2e_embed_host): pinned host ids/mask in,
              H2D + compute + D2H of the pooled rows inside the timed region
-  roofline   tensor-core bound: step-level achieved TFLOP/s (algorithmic matmul FLOPs)
-             against the measured sustained bf16 peak, plus the dominant kernel (FFN-up GEMM) timed
-             alone with CUDA events against the measured burst peak
+  roofline   tensor-core bound: the dominant kernel (FFN-up GEMM) timed alone with CUDA events against
+             the measured burst bf16 peak, its DRAM traffic per launch from the committed ncu capture
+             (profiles/ncu_traffic.json), and under "whole_step" the step-level achieved TFLOP/s
+             (algorithmic matmul FLOPs) against the measured sustained bf16 peak
   cpu_baseline  the CPU oracle (port of the reference path) timed on this box's host cores on a
              bounded sample (rank 0, N=1 only)
 --impl reference times that same CPU port as its own arm.
@@ -234,9 +235,21 @@ def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-    return {'name': 'gemm_bf16_tcgen05<256,4,GELU> (FFN up)', 'flops_per_launch': 2.0 * m * n * k,
+    return {'name': DOMINANT_KERNEL, 'flops_per_launch': 2.0 * m * n * k,
             'ms_per_launch': ms, 'achieved': tf, 'peak': peaks['bf16_tflops'], 'frac': tf / peaks['bf16_tflops'],
             'unit': 'TFLOP/s', 'peak_kind': 'burst (kernel timed alone)'}
+
+
+DOMINANT_KERNEL = 'gemm_bf16_tcgen05<256,4,GELU> (FFN up, M=262144 N=3072 K=768)'
+
+
+def ncu_traffic_bytes() -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` summary (profiles/ncu_traffic.json, written by tools/ncu_traffic.py)."""
+    path = REPO / 'profiles' / 'ncu_traffic.json'
+    if not path.exists():
+        return None
+    return json.loads(path.read_text()).get('ffn_up_gemm_b512', {}).get('dram_bytes_per_launch')
 
 
 def run_native(args) -> None:
@@ -332,10 +345,17 @@ def run_native(args) -> None:
     if rank == 0:
         fpc = flops_per_chunk(BERT_BASE, SEQ)
         step_tf = (value / world) * fpc / 1e12
-        roof = {'bound': 'tensor', 'achieved': step_tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': step_tf / peaks['bf16_tflops_sustained'], 'traffic': None,
-                'peak_source': f'{peak_src} sustained bf16 (whole step, per GPU)',
-                'flops_per_chunk': fpc, 'dominant_kernel': time_dominant_kernel(device, peaks)}
+        dom = time_dominant_kernel(device, peaks)
+        # top level: the dominant kernel against the burst peak (timed alone); whole_step: all 91
+        # launches of one step against the sustained peak
+        roof = {'bound': 'tensor', 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s',
+                'frac': dom['frac'], 'traffic': ncu_traffic_bytes(), 'kernel': dom['name'],
+                'flops_per_launch': dom['flops_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
+                'peak_source': f'{peak_src} burst bf16 (kernel timed alone)',
+                'whole_step': {'achieved': step_tf, 'peak': peaks['bf16_tflops_sustained'],
+                               'frac': step_tf / peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                               'flops_per_chunk': fpc,
+                               'peak_source': f'{peak_src} sustained bf16 (whole step, per GPU)'}}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
             pick_cpu_threads()

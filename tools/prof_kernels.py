@@ -1,5 +1,6 @@
 """Short single-GPU driver for `ncu --set full`: a few launches of the dominant kernels at the
-bench shapes (B=128 sequences of 512 tokens keeps replays cheap)."""
+bench shapes.  usage: prof_kernels.py [B]  (default 128 sequences of 512 tokens keeps replays cheap;
+512 is the bench batch, used for the per-launch DRAM traffic in the roofline)."""
 
 from __future__ import annotations
 
@@ -12,7 +13,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from distllm_b200 import _native as nv  # noqa: E402
 
 dev = torch.device('cuda:0')
-b, s, heads, h, i = 128, 512, 12, 768, 3072
+b, s, heads, h, i = (int(sys.argv[1]) if len(sys.argv) > 1 else 128), 512, 12, 768, 3072
 m = b * s
 torch.manual_seed(0)
 x = torch.randn(m, h, device=dev).bfloat16()
