@@ -251,3 +251,124 @@ def random_esm_state_dict(hf_config, seed: int = 0, device: torch.device | str =
         ln(p + 'attention.LayerNorm', sd)
         ln(p + 'LayerNorm', sd)
     return sd
+
+
+# ------------------------------------------------------------------------------ Mistral family
+# Mistral (``B2E_ARCH_MISTRAL``), 2 + 6*L device tensors (no biases anywhere):
+#
+#     0 embed_tokens [V,H] f32          1 norm.weight [H] f32 (final RMSNorm)
+#     per layer l, base = 2 + 6*l:
+#       +0 input_layernorm.weight [H] f32
+#       +1 Wqkv [(heads + 2*kv_heads)*d, H] bf16 (rows: q_proj | k_proj | v_proj)
+#       +2 Wo   [H, heads*d] bf16
+#       +3 post_attention_layernorm.weight [H] f32
+#       +4 Wgu  [2I, H] bf16: gate_proj and up_proj interleaved in blocks of 64 rows
+#               (rows [128t, 128t+64) = gate rows [64t, 64t+64); rows [128t+64, 128t+128) = up rows
+#               [64t, 64t+64)), so that one GEMM tile holds gate and up of the same 64 outputs and
+#               the SwiGLU product is taken in the epilogue
+#       +5 Wd   [H, I] bf16 (down_proj)
+#
+# Names are HF ``MistralModel`` state-dict keys (transformers/models/mistral/modeling_mistral.py).
+
+GATE_UP_BLOCK = 64
+
+
+def rope_theta_of(hf_config) -> float:
+    params = getattr(hf_config, 'rope_parameters', None)
+    if params and 'rope_theta' in params:
+        return float(params['rope_theta'])
+    return float(getattr(hf_config, 'rope_theta', 10000.0))
+
+
+def mistral_desc(hf_config) -> _native.ModelDesc:
+    """Translate a HF ``MistralConfig`` into the C ``B2EModelDesc``."""
+    heads = hf_config.num_attention_heads
+    head_dim = getattr(hf_config, 'head_dim', None) or hf_config.hidden_size // heads
+    if getattr(hf_config, 'hidden_act', 'silu') != 'silu':
+        raise NotImplementedError(f'hidden_act={hf_config.hidden_act!r}: only SwiGLU (silu) is built')
+    window = getattr(hf_config, 'sliding_window', None)
+    return _native.ModelDesc(
+        arch=_native.ARCH_MISTRAL,
+        num_layers=hf_config.num_hidden_layers,
+        hidden=hf_config.hidden_size,
+        heads=heads,
+        kv_heads=hf_config.num_key_value_heads,
+        head_dim=head_dim,
+        intermediate=hf_config.intermediate_size,
+        vocab=hf_config.vocab_size,
+        max_pos=hf_config.max_position_embeddings,
+        type_vocab=0,
+        eps=float(hf_config.rms_norm_eps),
+        rope_theta=rope_theta_of(hf_config),
+        sliding_window=int(window) if window else 0,
+        reserved=0,
+    )
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """[I,H], [I,H] -> [2I,H] in the block-interleaved row order the SwiGLU epilogue expects."""
+    i, h = gate.shape
+    if i % GATE_UP_BLOCK:
+        raise ValueError(f'intermediate_size {i} must be a multiple of {GATE_UP_BLOCK}')
+    g = gate.reshape(i // GATE_UP_BLOCK, 1, GATE_UP_BLOCK, h)
+    u = up.reshape(i // GATE_UP_BLOCK, 1, GATE_UP_BLOCK, h)
+    return torch.cat([g, u], dim=1).reshape(2 * i, h)
+
+
+def mistral_weight_list(
+    state_dict: Mapping[str, torch.Tensor],
+    num_layers: int,
+    device: torch.device,
+) -> list[torch.Tensor]:
+    """HF MistralModel (or ...ForCausalLM) state dict -> contiguous device tensors in ABI order."""
+    sd = {k[6:] if k.startswith('model.') else k: v for k, v in state_dict.items()}
+
+    def f32(key: str) -> torch.Tensor:
+        return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
+
+    def b16(t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+    out = [f32('embed_tokens.weight'), f32('norm.weight')]
+    for layer in range(num_layers):
+        p = f'layers.{layer}.'
+        qkv = torch.cat([sd[p + f'self_attn.{n}_proj.weight'] for n in ('q', 'k', 'v')])
+        out += [
+            f32(p + 'input_layernorm.weight'),
+            b16(qkv),
+            b16(sd[p + 'self_attn.o_proj.weight']),
+            f32(p + 'post_attention_layernorm.weight'),
+            b16(interleave_gate_up(sd[p + 'mlp.gate_proj.weight'], sd[p + 'mlp.up_proj.weight'])),
+            b16(sd[p + 'mlp.down_proj.weight']),
+        ]
+    return out
+
+
+def random_mistral_state_dict(hf_config, seed: int = 0, device: torch.device | str = 'cpu',
+                              std: float | None = None,
+                              dtype: torch.dtype = torch.float32) -> dict[str, torch.Tensor]:
+    """Seeded random Mistral weights with HF MistralModel names (no ``model.`` prefix)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    std = getattr(hf_config, 'initializer_range', 0.02) if std is None else std
+    h, i = hf_config.hidden_size, hf_config.intermediate_size
+    heads, kv = hf_config.num_attention_heads, hf_config.num_key_value_heads
+    d = getattr(hf_config, 'head_dim', None) or h // heads
+
+    def normal(*shape: int) -> torch.Tensor:
+        return (torch.randn(*shape, generator=gen, device=device, dtype=torch.float32) * std).to(dtype)
+
+    sd: dict[str, torch.Tensor] = {'embed_tokens.weight': normal(hf_config.vocab_size, h)}
+    sd['norm.weight'] = (1.0 + normal(h).float()).to(dtype)
+    for layer in range(hf_config.num_hidden_layers):
+        p = f'layers.{layer}.'
+        sd[p + 'self_attn.q_proj.weight'] = normal(heads * d, h)
+        sd[p + 'self_attn.k_proj.weight'] = normal(kv * d, h)
+        sd[p + 'self_attn.v_proj.weight'] = normal(kv * d, h)
+        sd[p + 'self_attn.o_proj.weight'] = normal(h, heads * d)
+        sd[p + 'mlp.gate_proj.weight'] = normal(i, h)
+        sd[p + 'mlp.up_proj.weight'] = normal(i, h)
+        sd[p + 'mlp.down_proj.weight'] = normal(h, i)
+        sd[p + 'input_layernorm.weight'] = (1.0 + normal(h).float()).to(dtype)
+        sd[p + 'post_attention_layernorm.weight'] = (1.0 + normal(h).float()).to(dtype)
+    return sd

@@ -232,6 +232,91 @@ def make_esm_golden() -> None:
     np.savez_compressed(GOLDEN / 'esm_tiny_golden.npz', **out)
 
 
+TINY_MISTRAL = dict(vocab_size=320, hidden_size=512, num_hidden_layers=2, num_attention_heads=4,
+                    num_key_value_heads=2, head_dim=128, intermediate_size=768,
+                    max_position_embeddings=320, rms_norm_eps=1e-5, hidden_act='silu',
+                    sliding_window=None, attention_dropout=0.0, initializer_range=0.05,
+                    pad_token_id=0, bos_token_id=1, eos_token_id=2)
+TINY_MISTRAL_SEED = 2468
+TINY_MISTRAL_WINDOW = 80   # second variant: same weights, sliding-window attention
+
+
+def make_mistral_golden() -> None:
+    """The reference's AutoEncoder (HF MistralModel: grouped-query causal attention, rotary, RMSNorm,
+    SwiGLU) + LastTokenPooler / MeanPooler + compute_embeddings on a tiny seeded checkpoint, with
+    right- and left-padded batches, without and with a sliding window."""
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from tokenizers.processors import TemplateProcessing
+    from torch.utils.data import DataLoader
+    from transformers import MistralConfig
+    from transformers import MistralModel
+    from transformers import PreTrainedTokenizerFast
+
+    from distllm.embed.datasets.utils import DataCollator
+    from distllm.embed.datasets.utils import InMemoryDataset
+    from distllm.embed.embedders.full_sequence import compute_embeddings
+    from distllm.embed.encoders.auto import AutoEncoder
+    from distllm.embed.encoders.auto import AutoEncoderConfig
+    from distllm.embed.poolers.last_token import LastTokenPooler
+    from distllm.embed.poolers.last_token import LastTokenPoolerConfig
+    from distllm.embed.poolers.mean import MeanPooler
+    from distllm.embed.poolers.mean import MeanPoolerConfig
+    from distllm_b200.embed.encoders.weights import random_mistral_state_dict
+
+    words = [f'w{i:03d}' for i in range(TINY_MISTRAL['vocab_size'] - 4)]
+    vocab = {t: i for i, t in enumerate(['<pad>', '<s>', '</s>', '<unk>', *words])}
+    rng = np.random.default_rng(21)
+    lengths = [5, 150, 33, 1, 64, 63, 400, 7, 127, 128, 200, 90]   # 400 words -> truncated to 320 tokens
+    texts = [' '.join(rng.choice(words, size=n)) for n in lengths]
+    out = {'n_texts': np.array(len(texts))}
+
+    for variant, window in (('full', None), ('window', TINY_MISTRAL_WINDOW)):
+        cfg = MistralConfig(**{**TINY_MISTRAL, 'sliding_window': window})
+        sd = random_mistral_state_dict(cfg, seed=TINY_MISTRAL_SEED, device='cpu')
+        model = MistralModel(cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected and all('rotary_emb' in k for k in missing), (missing, unexpected)
+        model.eval()
+        out['weights_sha256'] = np.array(weights_digest(sd))
+        with tempfile.TemporaryDirectory() as tmp:
+            tmp_path = Path(tmp)
+            raw = Tokenizer(WordLevel(vocab, unk_token='<unk>'))
+            raw.pre_tokenizer = Whitespace()
+            raw.post_processor = TemplateProcessing(single='<s> $A', special_tokens=[('<s>', 1)])
+            tok = PreTrainedTokenizerFast(tokenizer_object=raw, pad_token='<pad>', bos_token='<s>',
+                                          eos_token='</s>', unk_token='<unk>')
+            model.save_pretrained(tmp_path / 'ckpt')
+            tok.save_pretrained(tmp_path / 'ckpt')
+            encoder = AutoEncoder(AutoEncoderConfig(
+                pretrained_model_name_or_path=str(tmp_path / 'ckpt'), quantization=False, eval_mode=True))
+            assert type(encoder.model).__name__ == 'MistralModel'
+            assert encoder.tokenizer.model_max_length == TINY_MISTRAL['max_position_embeddings']
+
+            def loader() -> DataLoader:
+                return DataLoader(InMemoryDataset(texts), batch_size=4, num_workers=0,
+                                  collate_fn=DataCollator(encoder.tokenizer))
+
+            for side in ('right', 'left'):
+                encoder.tokenizer.padding_side = side
+                key = f'{variant}/{side}'
+                for i, batch in enumerate(loader()):
+                    out[f'{key}/batch{i}/input_ids'] = batch['input_ids'].numpy()
+                    out[f'{key}/batch{i}/attention_mask'] = batch['attention_mask'].numpy()
+                    assert 'token_type_ids' not in batch
+                    if i == 1 and key != 'window/left':   # batch 1 holds the truncated 320-token row
+                        with torch.no_grad():
+                            out[f'{key}/batch{i}/hidden'] = encoder.encode(batch).numpy()
+                out['n_batches'] = np.array(i + 1)
+                out[f'{key}/pooled/last_token'] = compute_embeddings(
+                    loader(), encoder, LastTokenPooler(LastTokenPoolerConfig()))
+                if side == 'right':
+                    out[f'{key}/pooled/mean_normalized'] = compute_embeddings(
+                        loader(), encoder, MeanPooler(MeanPoolerConfig()), normalize=True)
+    np.savez_compressed(GOLDEN / 'mistral_tiny_golden.npz', **out)
+
+
 def main() -> None:
     if not REFERENCE.exists():
         raise SystemExit('/root/reference is not available: golden vectors can only be (re)generated '
@@ -244,6 +329,7 @@ def main() -> None:
     make_semantic_golden()
     make_bert_golden()
     make_esm_golden()
+    make_mistral_golden()
     for f in sorted(GOLDEN.glob('*.npz')):
         print(f.name, f.stat().st_size, 'bytes')
 
