@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / 'libb2e.so'
 ARCH_BERT, ARCH_ESM2, ARCH_MISTRAL = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 POOL_MEAN_REF, POOL_MEAN_PER_ROW, POOL_LAST_TOKEN = 0, 1, 2
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID = 0, 1, 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_SWIGLU = 0, 1, 2, 3
 
 _DTYPE_CODES = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
 
@@ -38,6 +38,7 @@ EXPORTS = (
     'b2e_adjacent_cosine_dist',
     'b2e_gemm_bf16',
     'b2e_attention_d64',
+    'b2e_attention_causal_d128',
     'b2e_layernorm',
 )
 
@@ -102,6 +103,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b2e_attention_d64.restype = i32
     lib.b2e_attention_d64.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.b2e_attention_causal_d128.restype = i32
+    lib.b2e_attention_causal_d128.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b2e_layernorm.restype = i32
     lib.b2e_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
 
@@ -159,18 +162,24 @@ def _cuda_contig(t: torch.Tensor, what: str) -> torch.Tensor:
 def gemm_bf16(
     a: torch.Tensor,
     w: torch.Tensor,
-    bias: torch.Tensor,
+    bias: torch.Tensor | None,
     resid: torch.Tensor | None = None,
     epilogue: int = EPI_BIAS,
 ) -> torch.Tensor:
-    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; bf16 in/out."""
+    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; bf16 in/out.
+
+    ``EPI_SWIGLU``: ``w`` holds gate/up rows interleaved in blocks of 64 (weights.interleave_gate_up)
+    and the result is ``silu(gate) * up`` of shape [M, N/2]."""
     lib = load()
-    _cuda_contig(a, 'a'), _cuda_contig(w, 'w'), _cuda_contig(bias, 'bias')
+    _cuda_contig(a, 'a'), _cuda_contig(w, 'w')
+    if bias is not None:
+        _cuda_contig(bias, 'bias')
     m, k = a.shape
     n = w.shape[0]
-    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    n_out = n // 2 if epilogue == EPI_SWIGLU else n
+    out = torch.empty((m, n_out), dtype=torch.bfloat16, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib.b2e_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(resid),
+        check(lib.b2e_gemm_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid),
                                 out.data_ptr(), m, n, k, epilogue, stream_ptr(a.device)))
     return out
 
@@ -190,6 +199,25 @@ def attention_d64(
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_d64(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch,
                                     seq, heads, _ptr(debug_scores), stream_ptr(qkv.device)))
+    return ctx
+
+
+def attention_causal_d128(
+    qkv: torch.Tensor,
+    attention_mask: torch.Tensor,
+    batch: int,
+    seq: int,
+    heads: int,
+    kv_heads: int,
+    window: int = 0,
+) -> torch.Tensor:
+    """qkv [B*S, (heads + 2*kv_heads)*128] bf16 (q | k | v, rotary applied) -> [B*S, heads*128] bf16."""
+    lib = load()
+    _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
+    ctx = torch.zeros((batch * seq, heads * 128), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.b2e_attention_causal_d128(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(),
+                                            batch, seq, heads, kv_heads, window, stream_ptr(qkv.device)))
     return ctx
 
 

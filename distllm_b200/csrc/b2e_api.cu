@@ -16,9 +16,11 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "mistral_ops.cuh"
 #include "rowops.cuh"
 
 using namespace b2e;
@@ -193,6 +195,11 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     case B2E_EPI_BIAS_RESID:
       return launch_gemm_cfg<BN, STAGES, EPI_BIAS_RESID>(ta, tb, tout, bias, resid, M, N, K, sms,
                                                          st);
+    case B2E_EPI_SWIGLU:
+      if constexpr (BN == 256)
+        return launch_gemm_cfg<256, STAGES, EPI_SWIGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+      else
+        return fail(B2E_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0");
   }
   return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -244,8 +251,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
   CUtensorMap tout;
   int rc;
-  if ((rc = make_tmap_bf16(&tout, out, M, N, GEMM_OUT_BOX_ROWS))) return rc;
-  if (N % 256 == 0 && gemm_use_pair()) {
+  const int n_out = (epi == B2E_EPI_SWIGLU) ? N / 2 : N;   // SwiGLU writes silu(gate)*up: [M, N/2]
+  if ((rc = make_tmap_bf16(&tout, out, M, n_out, GEMM_OUT_BOX_ROWS))) return rc;
+  if (N % 256 == 0 && gemm_use_pair() && epi != B2E_EPI_SWIGLU) {
     switch (epi) {
       case B2E_EPI_BIAS: {
         static int stages = -1;  // experiment knob: B2E_PAIR_STAGES=3
@@ -374,6 +382,32 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
   attention3_d64_kernel<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(
       tq, tkv, sc.bias, sc.kv_chunks, tctx, B, S, attn_s_pad(S), heads, scale_log2e);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+// Causal grouped-query attention, head_dim 128 (attention4.cuh).  qkv is [B*S, (heads + 2 kv_heads)*128]
+// with columns  q heads | k heads | v heads;  sc must have been prepared for (mask, B, S).
+int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, int B, int S, int heads,
+                                 int kv_heads, int window, int sms, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(attention4_d128_causal_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
+    attr_done = true;
+  }
+  const uint64_t ld = (uint64_t)(heads + 2 * kv_heads) * AT4_D;
+  CUtensorMap tq, tkv, tctx;
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, ld, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, ld, AT4_KC))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT4_D, 128))) return rc;
+  const int nq = (S + 127) / 128;
+  const long long items = (long long)B * heads * ((nq + 1) / 2);
+  const int grid = items < sms ? (int)items : sms;
+  const float scale_log2e = 0.08838834764831845f * 1.4426950408889634f;  // 128^-0.5 * log2(e)
+  attention4_d128_causal_kernel<<<grid, AT4_THREADS, AT4_SMEM_BYTES, st>>>(
+      tq, tkv, sc.bias, sc.kv_chunks, tctx, B, S, attn_s_pad(S), heads, kv_heads, window, scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -507,11 +541,26 @@ struct B2EEncoder {
   size_t cap_scale = 0;
   float *rope_cos = nullptr, *rope_sin = nullptr;
   const void* E(int l, int k) const { return w[3 + 12 * l + k]; }
+
+  // Mistral family: fp32 residual stream and rotary tables as above; weight slots (weights.py):
+  //   0 embed_tokens, 1 final norm; per layer (2 + 6 l): input norm, Wqkv, Wo, post-attention norm,
+  //   Wgu (gate/up interleaved), Wd
+  const void* Mi(int l, int k) const { return w[2 + 6 * l + k]; }
+  int qkv_cols() const {
+    return desc.arch == B2E_ARCH_MISTRAL ? (desc.heads + 2 * desc.kv_heads) * desc.head_dim
+                                         : 3 * desc.hidden;
+  }
+  int ctx_cols() const {
+    return desc.arch == B2E_ARCH_MISTRAL ? desc.heads * desc.head_dim : desc.hidden;
+  }
+  bool has_xres() const { return desc.arch != B2E_ARCH_BERT; }
 };
 
 namespace {
 
 size_t tokens_bytes(const B2EModelDesc& d, size_t tokens) {
+  if (d.arch == B2E_ARCH_MISTRAL)
+    return tokens * (size_t)(2 * d.hidden + (2 * d.heads + 2 * d.kv_heads) * d.head_dim + d.intermediate) * 2;
   return tokens * (size_t)(6 * d.hidden + d.intermediate) * 2;
 }
 
@@ -523,11 +572,11 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     e->cap_tokens = 0;
     const size_t H = e->desc.hidden, I = e->desc.intermediate;
     CUDA_TRY(cudaMalloc(&e->hidden, tokens * H * 2));
-    CUDA_TRY(cudaMalloc(&e->qkv, tokens * 3 * H * 2));
-    CUDA_TRY(cudaMalloc(&e->ctx, tokens * H * 2));
+    CUDA_TRY(cudaMalloc(&e->qkv, tokens * (size_t)e->qkv_cols() * 2));
+    CUDA_TRY(cudaMalloc(&e->ctx, tokens * (size_t)e->ctx_cols() * 2));
     CUDA_TRY(cudaMalloc(&e->tmp, tokens * H * 2));
     CUDA_TRY(cudaMalloc(&e->ffn, tokens * I * 2));
-    if (e->desc.arch == B2E_ARCH_ESM2) {
+    if (e->has_xres()) {
       cudaFree(e->xres);
       e->xres = nullptr;
       CUDA_TRY(cudaMalloc(&e->xres, tokens * H * 4));
@@ -662,6 +711,59 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
   return B2E_OK;
 }
 
+// Mistral family (pre-RMSNorm decoder blocks, rotary, grouped-query causal attention, SwiGLU):
+// transformers/models/mistral/modeling_mistral.py:328-400 (model), :202-242 (block), :122-180
+// (attention), :35-48 (MLP).  Like the ESM-2 trunk it leaves xres (before the last MLP output is
+// added) and e->tmp (that down_proj output); the caller applies the final norm to xres + tmp.
+int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
+                      cudaStream_t st) {
+  const B2EModelDesc& d = e->desc;
+  const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
+  const int QC = e->qkv_cols(), CC = e->ctx_cols();
+  int rc;
+  DISPATCH_NV(H, (mistral_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     ids, (const float*)e->w[0], e->xres, M)));
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
+  CUtensorMap tm_hidden, tm_ctx, tm_ffn;
+  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, CC, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+
+  DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     e->xres, nullptr, (const float*)e->Mi(0, 0), e->hidden, M, d.eps)));
+  const int n_rot = d.heads + d.kv_heads;   // q heads and k heads are adjacent columns of qkv
+  const long long rope_work = (long long)M * n_rot;
+  for (int l = 0; l < L; ++l) {
+    if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, QC, H, B2E_EPI_BIAS,
+                          e->sms, st)))
+      return rc;
+    rope_d128_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
+                                                                      M, S, n_rot, QC);
+    if ((rc = launch_attention_causal_d128(e->qkv, e->attn, e->ctx, B, S, d.heads, d.kv_heads,
+                                           d.sliding_window, e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, CC, B2E_EPI_BIAS,
+                          e->sms, st)))
+      return rc;
+    DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->Mi(l, 3), e->hidden, M, d.eps)));
+    // gate and up in one GEMM (interleaved rows), silu(gate) * up in its epilogue: [M, I]
+    if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, nullptr, nullptr, M, 2 * I, H,
+                          B2E_EPI_SWIGLU, e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, nullptr, nullptr, M, H, I, B2E_EPI_BIAS,
+                          e->sms, st)))
+      return rc;
+    if (l + 1 < L) {
+      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->Mi(l + 1, 0), e->hidden, M, d.eps)));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
 }  // namespace
 
 // ================================================================== C ABI
@@ -695,16 +797,76 @@ int b2e_num_weights(const B2EModelDesc* desc) {
   if (!desc) return -1;
   if (desc->arch == B2E_ARCH_BERT) return 5 + 12 * desc->num_layers;
   if (desc->arch == B2E_ARCH_ESM2) return 3 + 12 * desc->num_layers;
+  if (desc->arch == B2E_ARCH_MISTRAL) return 2 + 6 * desc->num_layers;
   return -1;
 }
+
+namespace {
+// Mistral family: head_dim 128, grouped-query heads, SwiGLU MLP, no biases.
+int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_weights, int device,
+                   B2EEncoder** out) {
+  if (attention_mode() != 3)
+    return fail(B2E_ERR_UNSUPPORTED, "Mistral needs the streaming attention kernels (unset B2E_ATTENTION)");
+  if (desc->head_dim != 128 || desc->kv_heads <= 0 || desc->heads % desc->kv_heads != 0)
+    return fail(B2E_ERR_UNSUPPORTED, "need head_dim 128 and heads %% kv_heads == 0 (got %d/%d x %d)",
+                desc->heads, desc->kv_heads, desc->head_dim);
+  if (desc->intermediate % 128 != 0)
+    return fail(B2E_ERR_UNSUPPORTED, "intermediate size %d must be a multiple of 128", desc->intermediate);
+  if (desc->sliding_window < 0) return fail(B2E_ERR_INVALID, "negative sliding_window");
+  const int L = desc->num_layers, H = desc->hidden, I = desc->intermediate;
+  const int QC = (desc->heads + 2 * desc->kv_heads) * 128, CC = desc->heads * 128;
+  int rc;
+  if ((rc = check_h(H))) return rc;
+  if ((rc = check_gemm_shape(128, QC, H))) return rc;
+  if ((rc = check_gemm_shape(128, H, CC))) return rc;
+  if ((rc = check_gemm_shape(128, 2 * I, H))) return rc;
+  if ((rc = check_gemm_shape(128, H, I))) return rc;
+  if (n_weights != b2e_num_weights(desc))
+    return fail(B2E_ERR_INVALID, "expected %d weight pointers, got %d", b2e_num_weights(desc), n_weights);
+  for (int i = 0; i < n_weights; ++i)
+    if (!weights[i]) return fail(B2E_ERR_INVALID, "weight pointer %d is null", i);
+  DeviceInfo info;
+  if ((rc = device_info(device, &info))) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  B2EEncoder* e = new B2EEncoder();
+  e->desc = *desc;
+  e->w.assign(weights, weights + n_weights);
+  e->device = device;
+  e->sms = info.sms;
+  e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
+  for (int l = 0; l < L; ++l) {
+    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], e->Mi(l, 1), QC, H, gemm_bn_for(QC))) ||
+        (rc = make_tmap_bf16(&e->tm_wo[l], e->Mi(l, 2), H, CC, gemm_bn_for(H))) ||
+        (rc = make_tmap_bf16(&e->tm_w1[l], e->Mi(l, 4), 2 * I, H, 256)) ||
+        (rc = make_tmap_bf16(&e->tm_w2[l], e->Mi(l, 5), H, I, gemm_bn_for(H)))) {
+      delete e;
+      return rc;
+    }
+  }
+  const size_t n = (size_t)desc->max_pos * 64;
+  if (cudaMalloc(&e->rope_cos, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&e->rope_sin, n * sizeof(float)) != cudaSuccess) {
+    b2e_encoder_destroy(e);
+    return fail(B2E_ERR_CUDA, "cudaMalloc of the rotary tables failed");
+  }
+  rope_table_theta_kernel<<<(unsigned)((n + 255) / 256), 256>>>(e->rope_cos, e->rope_sin, desc->max_pos,
+                                                                64, desc->rope_theta);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    b2e_encoder_destroy(e);
+    return fail(B2E_ERR_CUDA, "rotary table kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = e;
+  return B2E_OK;
+}
+}  // namespace
 
 int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int n_weights,
                        int device, B2EEncoder** out) {
   if (!desc || !weights || !out) return fail(B2E_ERR_INVALID, "null argument");
   *out = nullptr;
+  if (desc->arch == B2E_ARCH_MISTRAL) return create_mistral(desc, weights, n_weights, device, out);
   if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
-    return fail(B2E_ERR_UNSUPPORTED, "arch %d: only B2E_ARCH_BERT and B2E_ARCH_ESM2 are built",
-                desc->arch);
+    return fail(B2E_ERR_UNSUPPORTED, "arch %d: unknown architecture", desc->arch);
   if (desc->arch == B2E_ARCH_ESM2 && attention_mode() != 3)
     return fail(B2E_ERR_UNSUPPORTED, "ESM-2 needs the streaming attention kernel (unset B2E_ATTENTION)");
   if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
@@ -778,7 +940,7 @@ int64_t b2e_workspace_bytes(const B2EEncoder* e, int B, int S) {
   if (!e || B <= 0 || S <= 0) return -1;
   const size_t tokens = (size_t)B * S;
   size_t bytes = tokens_bytes(e->desc, tokens);
-  if (e->desc.arch == B2E_ARCH_ESM2) bytes += tokens * e->desc.hidden * 4 + (size_t)B * sizeof(float);
+  if (e->has_xres()) bytes += tokens * e->desc.hidden * 4 + (size_t)B * sizeof(float);
   bytes += tokens * sizeof(float) + (size_t)S * sizeof(int) + (size_t)B * (2 * sizeof(int) + sizeof(float));
   bytes += (size_t)B * pool_nsplit(S) * e->desc.hidden * sizeof(float);
   return (int64_t)bytes;
@@ -795,6 +957,19 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
   if ((rc = ensure_workspace(e, B, S))) return rc;
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, l = d.num_layers - 1;
+  if (d.arch == B2E_ARCH_MISTRAL) {
+    if ((rc = run_mistral_trunk(e, ids, mask, B, S, st))) return rc;
+    // final RMSNorm over (residual stream + last down_proj output)
+    if (out_dtype == B2E_DTYPE_F32) {
+      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (float*)out_hidden, M, d.eps)));
+    } else {
+      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (bf16*)out_hidden, M, d.eps)));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return B2E_OK;
+  }
   if (d.arch == B2E_ARCH_ESM2) {
     if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
     // emb_layer_norm_after over (residual stream + last FFN output)
@@ -836,6 +1011,30 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
   const B2EModelDesc& d = e->desc;
   const int H = d.hidden, l = d.num_layers - 1;
   PoolScratch& ps = e->pool;
+  if (d.arch == B2E_ARCH_MISTRAL) {
+    if ((rc = run_mistral_trunk(e, ids, mask, B, S, st))) return rc;
+    const int M = B * S;
+    if (pool_kind == B2E_POOL_LAST_TOKEN) {
+      // only the B selected rows go through the final norm (fp32 end to end)
+      seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
+      last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
+      DISPATCH_NV(H, (rmsnorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], ps.idx, out, B, S, d.eps)));
+      if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
+      CUDA_TRY(cudaGetLastError());
+      return B2E_OK;
+    }
+    DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->w[1], e->hidden, M, d.eps)));
+    if ((rc = launch_pool_weights(ps, const_cast<int64_t*>(mask), B, S, pool_kind, 0, st))) return rc;
+    const int nsplit = pool_nsplit(S);
+    const int rows_per = (S + nsplit - 1) / nsplit;
+    dim3 grid(B, nsplit);
+    DISPATCH_NV(H, (pool_sum_kernel<NV, bf16><<<grid, ROW_THREADS, 0, st>>>(e->hidden, ps.w, ps.part, S,
+                                                                          rows_per)));
+    CUDA_TRY(cudaGetLastError());
+    return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
+  }
   if (d.arch == B2E_ARCH_ESM2) {
     if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
     const int M = B * S;
@@ -1047,10 +1246,12 @@ int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
 
 int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epi, void* stream) {
-  if (!A || !W || !bias || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (!A || !W || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");  // bias may be null
   if (epi == B2E_EPI_BIAS_RESID && !resid) return fail(B2E_ERR_INVALID, "resid epilogue needs resid");
   int rc;
   if ((rc = check_gemm_shape(M, N, K))) return rc;
+  if (epi == B2E_EPI_SWIGLU && N % 256 != 0)
+    return fail(B2E_ERR_INVALID, "gemm: SwiGLU epilogue needs N %% 256 == 0 (got %d)", N);
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;
   CUtensorMap ta, tb;
@@ -1074,6 +1275,23 @@ int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, in
   if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, AT3_KC))) return rc;
   if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
   return launch_attention(tq, tkv, g_attn_scratch, mask, ctx, B, S, heads, dbg, info.sms, st);
+}
+
+int b2e_attention_causal_d128(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int heads,
+                              int kv_heads, int window, void* stream) {
+  if (!qkv || !mask || !ctx) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || S <= 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads != 0 || window < 0)
+    return fail(B2E_ERR_INVALID, "bad causal attention problem B=%d S=%d heads=%d/%d window=%d", B, S,
+                heads, kv_heads, window);
+  if (attention_mode() != 3)
+    return fail(B2E_ERR_UNSUPPORTED, "causal attention needs the streaming kernels (unset B2E_ATTENTION)");
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
+  return launch_attention_causal_d128(qkv, g_attn_scratch, ctx, B, S, heads, kv_heads, window,
+                                      info.sms, st);
 }
 
 int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* out, int rows, int H,

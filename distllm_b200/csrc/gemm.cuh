@@ -21,7 +21,10 @@
 
 namespace b2e {
 
-enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+// EPI_SWIGLU: W holds gate and up rows interleaved in blocks of 64 (weights.py: interleave_gate_up),
+// so columns [128t, 128t+64) of the product are gate and [128t+64, 128t+128) up of outputs
+// [64t, 64t+64); the epilogue writes silu(gate) * up into out [M, N/2].
+enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_SWIGLU = 3 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
@@ -125,6 +128,33 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32]
     // 128B-swizzle: unit index XOR (row & 7) -- conflict-free for "one row per lane" writes and
     // exactly the layout the SWIZZLE_128B tensor map expects
     *reinterpret_cast<uint4*>(staging + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
+  }
+}
+
+// SwiGLU epilogue of one 32-row x 64-output chunk: g, u = the gate / up accumulators (two 32-column
+// TMEM reads each); silu(g) * u -> bf16 -> the warp's swizzled staging tile.
+// silu(g) = g / (1 + 2^(-g log2 e)): one ex2 + one rcp per element (hidden under the K loop's MMAs).
+__device__ __forceinline__ void gemm_swiglu_chunk(const uint32_t (&g)[2][32],
+                                                  const uint32_t (&u)[2][32], uint8_t* staging,
+                                                  int lane) {
+#pragma unroll
+  for (int un = 0; un < 8; ++un) {
+    const uint32_t* gg = &g[un >> 2][(un & 3) * 8];
+    const uint32_t* uu = &u[un >> 2][(un & 3) * 8];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = __uint_as_float(gg[e]);
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(-1.4426950408889634f * x)));
+      v[e] = x * r * __uint_as_float(uu[e]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(staging + lane * 128 + ((un ^ (lane & 7)) << 4)) = o;
   }
 }
 
@@ -249,16 +279,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] b
           (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       // the tile's bias slice goes to smem before the accumulator wait (double-buffered by `as`)
-      for (int i = etid; i < BN; i += GEMM_EPI_WARPS * 32)
-        sbias[as * BN + i] = __ldg(bias + n_blk * BN + i);
-      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+      if (EPI != EPI_SWIGLU) {
+        for (int i = etid; i < BN; i += GEMM_EPI_WARPS * 32)
+          sbias[as * BN + i] = (bias != nullptr) ? __ldg(bias + n_blk * BN + i) : 0.0f;
+        asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+      }
 
       mbar_wait(tfull_bar + 8u * as, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(as * BN + col0);
+      if constexpr (EPI == EPI_SWIGLU) {
+        static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU epilogue: 128 columns per warp");
+        uint32_t g[2][32], u[2][32];
+        tmem_ld32(t_base, g[0]);
+        tmem_ld32(t_base + 32u, g[1]);
+        tmem_ld32(t_base + 64u, u[0]);
+        tmem_ld32(t_base + 96u, u[1]);
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        tmem_ld_wait();
+        gemm_swiglu_chunk(g, u, staging, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out, staging_addr, n_blk * (BN / 2) + half * 64, row0);
+          tma_store_commit();
+        }
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = 0; c < (EPI == EPI_SWIGLU ? 0 : NCHUNK); ++c) {
         uint32_t acc[2][32];
         tmem_ld32(t_base + static_cast<uint32_t>(c * 64), acc[0]);
         tmem_ld32(t_base + static_cast<uint32_t>(c * 64 + 32), acc[1]);

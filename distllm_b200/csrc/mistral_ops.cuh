@@ -1,0 +1,143 @@
+// Row kernels of the Mistral-family forward pass (pre-norm decoder blocks used as an encoder):
+// embedding gather, RMSNorm fused with the fp32 residual update, rotary tables and the in-place
+// rotation of the q and k heads.  Semantics: transformers/models/mistral/modeling_mistral.py
+// :181-200 (RMSNorm), :51-80 and :262-326 (rotary, halves convention), :202-242 (pre-norm blocks),
+// :328-400 (embed_tokens, final norm), reached from distllm/embed/encoders/auto.py:135.
+#pragma once
+
+#include "rowops.cuh"
+
+namespace b2e {
+
+// xres[row] = embed_tokens[ids[row]]   (fp32 residual stream; padding rows are embedded like any other
+// token, exactly as HF does -- they are only ever masked as KEYS)
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS)
+mistral_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
+                     float* __restrict__ xres, int rows) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t id = ids[row];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = v * 256 + lane * 8;
+    float w[8];
+    load8(table + static_cast<size_t>(id) * H + c, w);
+    store8(xres + static_cast<size_t>(row) * H + c, w);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void warp_rmsnorm(float (&x)[NV][8], const float* __restrict__ gamma,
+                                             int lane, float eps) {
+  constexpr int H = NV * 256;
+  float ss = 0.0f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(x[v][e], x[v][e], ss);
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss * (1.0f / H) + eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float g[8];
+    load8(gamma + v * 256 + lane * 8, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[v][e] = g[e] * (x[v][e] * r);
+  }
+}
+
+// Residual stream update fused with the next RMSNorm:
+//   xres += add (bf16 GEMM output; nullptr on the very first call);  out = RMSNorm(xres) * gamma
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(ROW_THREADS)
+add_rmsnorm_kernel(float* __restrict__ xres, const bf16* __restrict__ add,
+                   const float* __restrict__ gamma, OutT* __restrict__ out, int rows, float eps) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = static_cast<size_t>(row) * H + v * 256 + lane * 8;
+    load8(xres + off, x[v]);
+    if (add != nullptr) {
+      float a[8];
+      load8(add + off, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[v][e] += a[e];
+      store8(xres + off, x[v]);
+    }
+  }
+  warp_rmsnorm<NV>(x, gamma, lane, eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
+}
+
+// Final norm for the last-token pooler: only the B selected rows are normalised.
+//   out[b] = RMSNorm(xres[b*S + idx[b]] + add[b*S + idx[b]]) * gamma        (fp32 [B,H])
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+                      const float* __restrict__ gamma, const int* __restrict__ idx,
+                      float* __restrict__ out, int B, int S, float eps) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const size_t row = static_cast<size_t>(b) * S + idx[b];
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = row * H + v * 256 + lane * 8;
+    float a[8];
+    load8(xres + off, x[v]);
+    load8(add + off, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[v][e] += a[e];
+  }
+  warp_rmsnorm<NV>(x, gamma, lane, eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(b) * H + v * 256 + lane * 8, x[v]);
+}
+
+// cos/sin tables [max_pos, half]: angle(p, i) = p * theta^(-2i / (2*half))
+__global__ void rope_table_theta_kernel(float* __restrict__ cos_t, float* __restrict__ sin_t,
+                                        int max_pos, int half, float theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_pos * half) return;
+  const int p = i / half, k = i % half;
+  const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * k) / static_cast<float>(2 * half));
+  float s, c;
+  sincosf(static_cast<float>(p) * inv_freq, &s, &c);
+  cos_t[i] = c;
+  sin_t[i] = s;
+}
+
+// In-place rotary embedding of the first `n_rot` heads of every row of qkv [T, ld] (head_dim 128,
+// halves of 64; q heads are followed directly by the k heads, so one pass rotates both):
+//   out[i] = x[i] cos_i - x[i+64] sin_i ;  out[i+64] = x[i+64] cos_i + x[i] sin_i   (position = t % S)
+// One warp per (token, head); a lane owns frequencies lane and lane + 32.
+__global__ void rope_d128_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_t,
+                                 const float* __restrict__ sin_t, int T, int S, int n_rot, int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= static_cast<long long>(T) * n_rot) return;
+  const int t = static_cast<int>(w / n_rot);
+  const int hd = static_cast<int>(w % n_rot);
+  bf16* p = qkv + static_cast<size_t>(t) * ld + hd * 128;
+  const int pos = t % S;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = lane + 32 * k;
+    const float c = cos_t[pos * 64 + i], s = sin_t[pos * 64 + i];
+    const float x1 = __bfloat162float(p[i]), x2 = __bfloat162float(p[i + 64]);
+    p[i] = __float2bfloat16_rn(x1 * c - x2 * s);
+    p[i + 64] = __float2bfloat16_rn(x2 * c + x1 * s);
+  }
+}
+
+}  // namespace b2e

@@ -18,9 +18,13 @@ from transformers import BatchEncoding
 from transformers import PreTrainedTokenizer
 
 from distllm_b200.embed.encoders.native import NativeBertEncoder
+from distllm_b200.embed.encoders.native import NativeMistralEncoder
 from distllm_b200.utils import BaseConfig
 
-_SUPPORTED_MODEL_TYPES = ('bert',)
+# HF model_type -> native forward pass (BERT: post-LN encoder; Mistral: pre-RMSNorm decoder blocks
+# with rotary, grouped-query causal attention and SwiGLU, used as an encoder by the embedding models)
+_NATIVE_BY_MODEL_TYPE = {'bert': NativeBertEncoder, 'mistral': NativeMistralEncoder}
+_SUPPORTED_MODEL_TYPES = tuple(_NATIVE_BY_MODEL_TYPE)
 
 
 class AutoEncoderConfig(BaseConfig):
@@ -42,7 +46,7 @@ class AutoEncoderConfig(BaseConfig):
 
 
 class AutoEncoder:
-    """Encoder for HF checkpoints of the BERT family on the native kernels."""
+    """Encoder for HF checkpoints of the BERT and Mistral families on the native kernels."""
 
     def __init__(self, config: AutoEncoderConfig):
         from transformers import AutoConfig
@@ -69,7 +73,7 @@ class AutoEncoder:
         tokenizer.model_max_length = hf_config.max_position_embeddings
 
         self.config = config
-        self._native = NativeBertEncoder(hf_config, model.state_dict())
+        self._native = _NATIVE_BY_MODEL_TYPE[hf_config.model_type](hf_config, model.state_dict())
         del model
         self._tokenizer = tokenizer
         self._dtype = torch.float16 if config.half_precision else torch.float32

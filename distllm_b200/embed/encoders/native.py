@@ -135,3 +135,12 @@ class NativeEsm2Encoder(NativeBertEncoder):
 
     _DESC = staticmethod(W.esm_desc)
     _WEIGHTS = staticmethod(W.esm_weight_list)
+
+
+class NativeMistralEncoder(NativeBertEncoder):
+    """Mistral family (pre-RMSNorm blocks, rotary, grouped-query causal attention with optional sliding
+    window, SwiGLU) on the tcgen05 GEMM + the head_dim-128 causal attention kernel; ``token_type_ids``
+    unused."""
+
+    _DESC = staticmethod(W.mistral_desc)
+    _WEIGHTS = staticmethod(W.mistral_weight_list)

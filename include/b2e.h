@@ -48,7 +48,12 @@ enum {
   B2E_POOL_MEAN_PER_ROW = 1, /* drop only each row's own first/last token */
   B2E_POOL_LAST_TOKEN = 2
 };
-enum { B2E_EPI_BIAS = 0, B2E_EPI_BIAS_GELU = 1, B2E_EPI_BIAS_RESID = 2 };
+enum {
+  B2E_EPI_BIAS = 0,
+  B2E_EPI_BIAS_GELU = 1,
+  B2E_EPI_BIAS_RESID = 2,
+  B2E_EPI_SWIGLU = 3 /* W rows = gate/up interleaved in blocks of 64; out is [M, N/2]; no bias */
+};
 
 typedef struct B2EModelDesc {
   int32_t arch;          /* B2E_ARCH_* */
@@ -122,6 +127,12 @@ int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* r
 /* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; dbg_scores nullable ([128,512] fp32 of CTA 0). */
 int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
                       int heads, float* dbg_scores, void* stream);
+/* Causal grouped-query attention, head_dim 128 (Mistral family):
+ * qkv [B*S, (heads + 2*kv_heads)*128] with columns q heads | k heads | v heads (rotary already
+ * applied) -> ctx [B*S, heads*128].  Key j is visible to query i iff j <= i, attention_mask[b,j] != 0
+ * and (window == 0 or i - j < window). */
+int b2e_attention_causal_d128(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
+                              int heads, int kv_heads, int window, void* stream);
 int b2e_layernorm(const void* in_bf16, const float* gamma, const float* beta, void* out, int rows,
                   int H, float eps, int out_dtype, void* stream);
 

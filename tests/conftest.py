@@ -76,6 +76,27 @@ def tiny_esm():
     return cfg, random_esm_state_dict(cfg, seed=TINY_ESM_SEED, device='cpu')
 
 
+@pytest.fixture(scope='session')
+def mistral_golden():
+    return np.load(GOLDEN / 'mistral_tiny_golden.npz')
+
+
+def tiny_mistral_variant(variant: str):
+    """(HF config, seeded state dict) of the tiny Mistral checkpoint behind mistral_tiny_golden.npz;
+    variant 'full' = no sliding window, 'window' = the same weights with a sliding window."""
+    from transformers import MistralConfig
+
+    from oracle.make_golden import TINY_MISTRAL
+    from oracle.make_golden import TINY_MISTRAL_SEED
+    from oracle.make_golden import TINY_MISTRAL_WINDOW
+
+    from distllm_b200.embed.encoders.weights import random_mistral_state_dict
+
+    window = None if variant == 'full' else TINY_MISTRAL_WINDOW
+    cfg = MistralConfig(**{**TINY_MISTRAL, 'sliding_window': window})
+    return cfg, random_mistral_state_dict(cfg, seed=TINY_MISTRAL_SEED, device='cpu')
+
+
 def cosine_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = a.astype(np.float64)
     b = b.astype(np.float64)

@@ -44,7 +44,11 @@ def test_num_weights_bert():
     lib = _native.load()
     desc = _native.ModelDesc(arch=_native.ARCH_BERT, num_layers=12)
     assert lib.b2e_num_weights(C.byref(desc)) == 5 + 12 * 12
+    desc.arch = _native.ARCH_ESM2
+    assert lib.b2e_num_weights(C.byref(desc)) == 3 + 12 * 12
     desc.arch = _native.ARCH_MISTRAL
+    assert lib.b2e_num_weights(C.byref(desc)) == 2 + 6 * 12
+    desc.arch = 7
     assert lib.b2e_num_weights(C.byref(desc)) == -1
 
 

@@ -215,3 +215,95 @@ def test_l2_normalize(dev):
     x[5] = 0
     ref = torch.nn.functional.normalize(x, p=2, dim=-1)
     torch.testing.assert_close(nv.l2_normalize_(x.clone()), ref, rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------- Mistral-family kernels
+@pytest.mark.parametrize('m,i,k', [(128, 128, 64), (300, 768, 512), (1000, 1792, 1024), (5, 256, 4096)])
+def test_gemm_swiglu_epilogue(dev, m, i, k):
+    """gate/up rows interleaved in blocks of 64 -> silu(gate) * up, no bias, [M, I] out."""
+    from distllm_b200.embed.encoders.weights import interleave_gate_up
+
+    g = torch.Generator(device=dev).manual_seed(m + i + k)
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).bfloat16()
+    gate = (torch.randn(i, k, device=dev, generator=g) * 0.08).bfloat16()
+    up = (torch.randn(i, k, device=dev, generator=g) * 0.08).bfloat16()
+    out = nv.gemm_bf16(a, interleave_gate_up(gate, up).contiguous(), None, None, nv.EPI_SWIGLU)
+    ref = torch.nn.functional.silu(a.float() @ gate.float().T) * (a.float() @ up.float().T)
+    assert out.dtype == torch.bfloat16 and out.shape == (m, i)
+    torch.testing.assert_close(out.float(), ref, rtol=1.5e-2, atol=1e-2)
+
+
+def test_gemm_without_bias(dev):
+    g = torch.Generator(device=dev).manual_seed(4)
+    a = torch.randn(200, 256, device=dev, generator=g).bfloat16()
+    w = (torch.randn(512, 256, device=dev, generator=g) * 0.05).bfloat16()
+    out = nv.gemm_bf16(a, w, None)
+    torch.testing.assert_close(out.float(), a.float() @ w.float().T, rtol=1e-2, atol=1e-2)
+
+
+def ref_attention_causal(qkv, mask, b, s, heads, kv_heads, window):
+    d = 128
+    q = qkv[:, :heads * d].float().view(b, s, heads, d).permute(0, 2, 1, 3)
+    k = qkv[:, heads * d:(heads + kv_heads) * d].float().view(b, s, kv_heads, d).permute(0, 2, 1, 3)
+    v = qkv[:, (heads + kv_heads) * d:].float().view(b, s, kv_heads, d).permute(0, 2, 1, 3)
+    k = k.repeat_interleave(heads // kv_heads, dim=1)
+    v = v.repeat_interleave(heads // kv_heads, dim=1)
+    i = torch.arange(s, device=qkv.device)[:, None]
+    j = torch.arange(s, device=qkv.device)[None, :]
+    vis = j <= i
+    if window:
+        vis = vis & (i - j < window)
+    vis = vis[None, None] & (mask != 0)[:, None, None, :]
+    scores = (q @ k.transpose(-1, -2)) * d ** -0.5
+    p = torch.softmax(scores.masked_fill(~vis, float('-inf')), dim=-1)
+    alive = vis.any(-1)                      # [B,1,S]: query rows with at least one visible key
+    p = torch.nan_to_num(p, nan=0.0)
+    out = (p @ v).permute(0, 2, 1, 3).reshape(b * s, heads * d)
+    return out, alive.expand(b, heads, s)[:, 0].reshape(b * s)
+
+
+CAUSAL_CASES = [
+    # b, s, heads, kv_heads, window, padding
+    (2, 128, 2, 1, 0, 'none'), (2, 256, 4, 2, 0, 'none'), (3, 200, 4, 1, 0, 'right'),
+    (2, 513, 2, 2, 0, 'right'), (2, 320, 4, 2, 80, 'right'), (2, 320, 4, 2, 80, 'left'),
+    (1, 1100, 2, 1, 0, 'none'), (1, 1100, 2, 1, 300, 'left'), (4, 37, 2, 1, 16, 'right'),
+    (5, 1, 2, 2, 0, 'none'), (2, 640, 8, 2, 128, 'none'), (2, 300, 4, 4, 1, 'none'),
+    (2, 400, 2, 1, 64, 'right'), (2, 400, 2, 1, 65, 'left'),
+]
+
+
+@pytest.mark.parametrize('b,s,heads,kv_heads,window,padding', CAUSAL_CASES)
+def test_attention_causal_d128_matches_reference(dev, b, s, heads, kv_heads, window, padding):
+    g = torch.Generator(device=dev).manual_seed(b * 1000 + s + window)
+    qkv = torch.randn(b * s, (heads + 2 * kv_heads) * 128, device=dev, generator=g).bfloat16()
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    for r in range(b):
+        n_pad = min(s - 1, 23 * r + (5 if padding != 'none' else 0)) if padding != 'none' else 0
+        if padding == 'right' and n_pad:
+            mask[r, s - n_pad:] = 0
+        if padding == 'left' and n_pad:
+            mask[r, :n_pad] = 0
+    ctx = nv.attention_causal_d128(qkv, mask, b, s, heads, kv_heads, window)
+    ref, alive = ref_attention_causal(qkv, mask, b, s, heads, kv_heads, window)
+    assert torch.isfinite(ctx.float()).all()
+    # rows that see no key at all (queries inside left padding) are unspecified; everything else,
+    # including padded query positions that still see attended keys, must match
+    torch.testing.assert_close(ctx.float()[alive], ref[alive], rtol=2e-2, atol=1e-2)
+
+
+def test_attention_causal_d128_many_items_and_rescale(dev):
+    """More items than SMs with mixed lengths, and key norms that grow along the sequence so the lazy
+    rescale path runs on top of the causal/window edge masking."""
+    b, s, heads, kv_heads, window = 24, 700, 8, 2, 333
+    g = torch.Generator(device=dev).manual_seed(91)
+    qkv = torch.randn(b * s, (heads + 2 * kv_heads) * 128, device=dev, generator=g)
+    ramp = torch.linspace(0.2, 4.0, s, device=dev).repeat(b)[:, None]
+    qkv[:, heads * 128:(heads + kv_heads) * 128] *= ramp
+    qkv = qkv.bfloat16()
+    lens = torch.randint(1, s + 1, (b,), generator=torch.Generator().manual_seed(6))
+    mask = (torch.arange(s)[None] < lens[:, None]).long().to(dev)
+    ctx = nv.attention_causal_d128(qkv, mask, b, s, heads, kv_heads, window)
+    ref, alive = ref_attention_causal(qkv, mask, b, s, heads, kv_heads, window)
+    sel = alive & mask.bool().view(-1)
+    assert torch.isfinite(ctx.float()).all()
+    torch.testing.assert_close(ctx.float()[sel], ref[sel], rtol=3e-2, atol=2e-2)

@@ -306,3 +306,120 @@ def test_esm2_650m_width_vs_oracle():
         assert cosine_rows(hidden[valid], ref_hidden.numpy()[valid]).min() > 1 - COS_TOL
     finally:
         native.close()
+
+
+# ---------------------------------------------------------------------------------- Mistral family
+@pytest.mark.parametrize('variant', ['full', 'window'])
+@pytest.mark.parametrize('side', ['right', 'left'])
+def test_mistral_matches_reference_vectors(mistral_golden, variant, side):
+    """`auto` encoder on a Mistral checkpoint through the plugin API vs the reference's AutoEncoder
+    (HF MistralModel) outputs: grouped-query causal attention (head_dim 128), rotary, RMSNorm, SwiGLU;
+    right- and left-padded batches, without / with a sliding window, a row truncated at 320 tokens."""
+    from conftest import tiny_mistral_variant
+
+    from distllm_b200.embed.encoders.native import NativeMistralEncoder
+
+    cfg, sd = tiny_mistral_variant(variant)
+    key = f'{variant}/{side}'
+    native = NativeMistralEncoder(cfg, sd)
+    try:
+        encoder = AutoEncoder.from_native(native)
+        batches = [{k: torch.from_numpy(mistral_golden[f'{key}/batch{i}/{k}'])
+                    for k in ('input_ids', 'attention_mask')} for i in range(int(mistral_golden['n_batches']))]
+        if f'{key}/batch1/hidden' in mistral_golden.files:
+            hidden = encoder.encode(BatchEncoding(batches[1])).cpu().numpy()
+            ref = mistral_golden[f'{key}/batch1/hidden']
+            valid = batches[1]['attention_mask'].bool().numpy()
+            assert np.isfinite(hidden).all()
+            cos = cosine_rows(hidden[valid], ref[valid])
+            assert cos.min() > 1 - COS_TOL, cos.min()
+        for fused in (True, False):
+            enc = encoder
+            if not fused:
+                class Unfused:
+                    dtype, device, embedding_size = encoder.dtype, encoder.device, encoder.embedding_size
+                    tokenizer = None
+                    encode = staticmethod(encoder.encode)
+                enc = Unfused()
+            result = get_embedder({'name': 'full_sequence'}).embed(
+                loader_of(batches), enc, get_pooler({'name': 'last_token'}))
+            cos = cosine_rows(result.embeddings, mistral_golden[f'{key}/pooled/last_token'])
+            assert cos.min() > 1 - COS_TOL, (fused, cos)
+            if side == 'right':
+                result = get_embedder({'name': 'full_sequence', 'normalize_embeddings': True}).embed(
+                    loader_of(batches), enc, get_pooler({'name': 'mean'}))
+                ref = mistral_golden[f'{key}/pooled/mean_normalized']
+                # the 2-token row loses both tokens to the mean pooler (mean.py:35-36): exact zeros
+                empty = np.linalg.norm(ref, axis=-1) == 0
+                assert empty.sum() == 1 and not result.embeddings[empty].any()
+                cos = cosine_rows(result.embeddings[~empty], ref[~empty])
+                assert cos.min() > 1 - COS_TOL, (fused, cos)
+    finally:
+        native.close()
+
+
+def test_mistral_7b_width_vs_oracle():
+    """Mistral-7B layer shape (H=4096, 32 query / 8 kv heads x 128, I=14336) with 2 layers, S=400
+    right-padded, vs the CPU oracle; last-token pooling as in BASELINE config C3."""
+    from transformers import MistralConfig
+
+    from distllm_b200.embed.encoders.native import NativeMistralEncoder
+    from distllm_b200.embed.encoders.weights import random_mistral_state_dict
+    from oracle import mistral as omis
+
+    cfg = MistralConfig(vocab_size=2000, hidden_size=4096, num_hidden_layers=2, num_attention_heads=32,
+                        num_key_value_heads=8, head_dim=128, intermediate_size=14336,
+                        max_position_embeddings=4096, rms_norm_eps=1e-5, sliding_window=4096,
+                        initializer_range=0.02)
+    sd = random_mistral_state_dict(cfg, seed=5, device='cpu')
+    g = torch.Generator().manual_seed(6)
+    b, s = 3, 400
+    ids = torch.randint(3, 2000, (b, s), generator=g)
+    lens = torch.tensor([400, 57, 263])
+    mask = (torch.arange(s)[None] < lens[:, None]).long()
+    ref_hidden = omis.mistral_forward(sd, cfg, ids, mask)
+    ref = opool.last_token_pool(ref_hidden, mask).numpy()
+    native = NativeMistralEncoder(cfg, sd)
+    try:
+        got = native.encode_pooled(ids, mask, None, nv.POOL_LAST_TOKEN, False).cpu().numpy()
+        cos = cosine_rows(got, ref)
+        assert cos.min() > 1 - COS_TOL, cos
+        hidden = native.encode(ids, mask).cpu().numpy()
+        valid = mask.bool().numpy()
+        assert cosine_rows(hidden[valid], ref_hidden.numpy()[valid]).min() > 1 - COS_TOL
+    finally:
+        native.close()
+
+
+def test_mistral_long_sequence_properties():
+    """S = 4096 (BASELINE C3 length), 1 layer at 7B width: determinism, and the last-token embedding of a
+    right-padded row equals the embedding of the same row without its padding (causal attention never
+    looks right), bit for bit."""
+    from transformers import MistralConfig
+
+    from distllm_b200.embed.encoders.native import NativeMistralEncoder
+    from distllm_b200.embed.encoders.weights import random_mistral_state_dict
+
+    cfg = MistralConfig(vocab_size=1000, hidden_size=4096, num_hidden_layers=1, num_attention_heads=32,
+                        num_key_value_heads=8, head_dim=128, intermediate_size=14336,
+                        max_position_embeddings=4096, rms_norm_eps=1e-5, sliding_window=4096,
+                        initializer_range=0.02)
+    dev = torch.device('cuda:0')
+    sd = random_mistral_state_dict(cfg, seed=7, device=dev, dtype=torch.bfloat16)
+    native = NativeMistralEncoder(cfg, sd)
+    try:
+        g = torch.Generator().manual_seed(8)
+        ids = torch.randint(3, 1000, (2, 4096), generator=g)
+        mask = torch.ones(2, 4096, dtype=torch.int64)
+        mask[1, 3000:] = 0
+        a = native.encode_pooled(ids, mask, None, nv.POOL_LAST_TOKEN, True)
+        b = native.encode_pooled(ids, mask, None, nv.POOL_LAST_TOKEN, True)
+        assert torch.equal(a, b)
+        assert torch.isfinite(a).all()
+        np.testing.assert_allclose(a.norm(dim=-1).cpu().numpy(), 1.0, rtol=1e-5)
+        short = native.encode_pooled(ids[1:, :3000].contiguous(), mask[1:, :3000].contiguous(), None,
+                                     nv.POOL_LAST_TOKEN, True)
+        cos = cosine_rows(short.cpu().numpy(), a[1:].cpu().numpy())
+        assert cos.min() > 1 - 1e-5, cos
+    finally:
+        native.close()

@@ -166,3 +166,80 @@ def test_esm_oracle_matches_hf_esm_model(tiny_esm):
     got = oesm.esm_forward(sd, cfg, ids, mask)
     valid = mask.bool()
     np.testing.assert_allclose(got[valid].numpy(), ref[valid].numpy(), rtol=1e-4, atol=5e-5)
+
+
+# ---------------------------------------------------------------------------------- Mistral
+MISTRAL_CASES = [('full', 'right'), ('full', 'left'), ('window', 'right'), ('window', 'left')]
+
+
+def _mistral_batches(golden, key):
+    for i in range(int(golden['n_batches'])):
+        yield {k: torch.from_numpy(golden[f'{key}/batch{i}/{k}']) for k in ('input_ids', 'attention_mask')}
+
+
+def test_mistral_weights_are_reproducible(mistral_golden):
+    from conftest import tiny_mistral_variant
+
+    _, sd = tiny_mistral_variant('full')
+    assert weights_digest(sd) == str(mistral_golden['weights_sha256'])
+
+
+@pytest.mark.parametrize(('variant', 'side'), MISTRAL_CASES)
+def test_mistral_oracle_matches_reference(mistral_golden, variant, side):
+    """oracle Mistral forward + last-token / mean pool == distllm's AutoEncoder (HF MistralModel)
+    outputs: grouped-query causal attention, rotary, RMSNorm, SwiGLU; right and left padding; without
+    and with a sliding window; a row truncated at max_position_embeddings."""
+    from conftest import tiny_mistral_variant
+
+    from oracle import mistral as omis
+
+    cfg, sd = tiny_mistral_variant(variant)
+    key = f'{variant}/{side}'
+    batches = list(_mistral_batches(mistral_golden, key))
+    assert batches[1]['attention_mask'].sum(1).max() == cfg.max_position_embeddings  # truncated row
+    if f'{key}/batch1/hidden' in mistral_golden.files:
+        hidden = omis.mistral_forward(sd, cfg, batches[1]['input_ids'], batches[1]['attention_mask'])
+        # every position: the reference's SDPA gives zeros on rows that see no key (left padding)
+        np.testing.assert_allclose(hidden.numpy(), mistral_golden[f'{key}/batch1/hidden'],
+                                   rtol=1e-4, atol=5e-5)
+
+    def encode(b):
+        return omis.mistral_forward(sd, cfg, b['input_ids'], b['attention_mask'])
+
+    got = opool.compute_embeddings(batches, encode, opool.last_token_pool)
+    np.testing.assert_allclose(got, mistral_golden[f'{key}/pooled/last_token'], rtol=1e-4, atol=5e-5)
+    if side == 'right':
+        got = opool.compute_embeddings(batches, encode, opool.average_pool, do_normalize=True)
+        np.testing.assert_allclose(got, mistral_golden[f'{key}/pooled/mean_normalized'],
+                                   rtol=1e-4, atol=5e-5)
+
+
+def test_mistral_sliding_window_changes_the_result(mistral_golden):
+    a = mistral_golden['full/right/pooled/last_token']
+    b = mistral_golden['window/right/pooled/last_token']
+    long_rows = [1, 6, 8, 9, 10, 11]   # > 80 tokens: the window drops keys
+    short_rows = [0, 2, 3, 7]          # shorter than the window: identical
+    assert np.abs(a[long_rows] - b[long_rows]).max() > 1e-3
+    np.testing.assert_allclose(a[short_rows], b[short_rows], rtol=0, atol=1e-6)
+
+
+def test_mistral_oracle_matches_hf_model():
+    """Independent of the fixtures: the restatement against transformers' MistralModel."""
+    from conftest import tiny_mistral_variant
+    from transformers import MistralModel
+
+    from oracle import mistral as omis
+
+    cfg, sd = tiny_mistral_variant('window')
+    model = MistralModel(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    g = torch.Generator().manual_seed(12)
+    ids = torch.randint(4, cfg.vocab_size, (3, 150), generator=g)
+    lens = torch.tensor([150, 9, 97])
+    mask = (torch.arange(150)[None] < lens[:, None]).long()
+    with torch.no_grad():
+        ref = model(input_ids=ids, attention_mask=mask).last_hidden_state
+    got = omis.mistral_forward(sd, cfg, ids, mask)
+    valid = mask.bool()
+    np.testing.assert_allclose(got[valid].numpy(), ref[valid].numpy(), rtol=1e-4, atol=5e-5)
