@@ -240,7 +240,7 @@ def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
             'unit': 'TFLOP/s', 'peak_kind': 'burst (kernel timed alone)'}
 
 
-DOMINANT_KERNEL = 'gemm_bf16_tcgen05<256,4,GELU> (FFN up, M=262144 N=3072 K=768)'
+DOMINANT_KERNEL = 'gemm2_bf16_pair<5,GELU> (FFN up, M=262144 N=3072 K=768; CTA-pair tcgen05 kernel)'
 
 
 def ncu_traffic_bytes() -> float | None:

@@ -204,13 +204,13 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
-// B2E_GEMM=pair selects the experimental CTA-pair kernel (gemm2.cuh) when N is a multiple of 256;
-// the default is the single-CTA kernel with TMA-store epilogue.
+// The CTA-pair kernel (gemm2.cuh, 256 x 256 tiles over two SMs) is the default whenever N is a multiple
+// of 256; B2E_GEMM=single forces the single-CTA kernel (gemm.cuh), which also serves N % 256 == 128.
 inline bool gemm_use_pair() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B2E_GEMM");
-    v = (e && strcmp(e, "pair") == 0) ? 1 : 0;
+    v = (e && strcmp(e, "single") == 0) ? 0 : 1;
   }
   return v == 1;
 }
@@ -253,19 +253,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   int rc;
   const int n_out = (epi == B2E_EPI_SWIGLU) ? N / 2 : N;   // SwiGLU writes silu(gate)*up: [M, N/2]
   if ((rc = make_tmap_bf16(&tout, out, M, n_out, GEMM_OUT_BOX_ROWS))) return rc;
-  if (N % 256 == 0 && gemm_use_pair() && epi != B2E_EPI_SWIGLU) {
+  if (N % 256 == 0 && gemm_use_pair()) {
+    constexpr int PS = 5;   // 5 x 32 KiB stages + two staging tiles per epilogue warp
     switch (epi) {
-      case B2E_EPI_BIAS: {
-        static int stages = -1;  // experiment knob: B2E_PAIR_STAGES=3
-        if (stages < 0) {
-          const char* e = getenv("B2E_PAIR_STAGES");
-          stages = e ? atoi(e) : 6;
-        }
-        if (stages == 3) return launch_gemm2_cfg<3, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
-        return launch_gemm2_cfg<6, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      }
-      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<6, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<6, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS: return launch_gemm2_cfg<PS, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<PS, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<PS, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_SWIGLU: return launch_gemm2_cfg<PS, EPI_SWIGLU>(ta, tb, tout, bias, r, M, N, K, sms, st);
     }
     return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
   }
@@ -837,7 +831,7 @@ int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_w
   for (int l = 0; l < L; ++l) {
     if ((rc = make_tmap_bf16(&e->tm_wqkv[l], e->Mi(l, 1), QC, H, gemm_bn_for(QC))) ||
         (rc = make_tmap_bf16(&e->tm_wo[l], e->Mi(l, 2), H, CC, gemm_bn_for(H))) ||
-        (rc = make_tmap_bf16(&e->tm_w1[l], e->Mi(l, 4), 2 * I, H, 256)) ||
+        (rc = make_tmap_bf16(&e->tm_w1[l], e->Mi(l, 4), 2 * I, H, gemm_bn_for(2 * I))) ||
         (rc = make_tmap_bf16(&e->tm_w2[l], e->Mi(l, 5), H, I, gemm_bn_for(H)))) {
       delete e;
       return rc;

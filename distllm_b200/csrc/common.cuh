@@ -244,6 +244,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// Remote arrive WITHOUT release semantics.  The releasing form makes the issuing thread wait for its
+// (and, measured, the SM's in-flight async) memory traffic: 500 clk idle, 1000-1500 clk under TMA load
+// (profiles/r01_notes.md).  Use it only where no generic-proxy write has to be published, e.g. to hand
+// TMEM columns back after tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
 // wait on a LOCAL barrier whose arrivals come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;

@@ -131,6 +131,52 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32]
   }
 }
 
+// Same chunk epilogue with the bias slice read straight from global memory (all lanes read the same
+// 16 float4: L1 broadcast hits), no shared-memory bias tile and no barrier among the epilogue warps.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_chunk_gbias(const uint32_t (&acc)[2][32],
+                                                          const float* __restrict__ bias,
+                                                          const bf16* __restrict__ resid_row,
+                                                          bool row_ok, uint8_t* staging, int lane) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (bias != nullptr) {
+      b0 = __ldg(reinterpret_cast<const float4*>(bias + u * 8));
+      b1 = __ldg(reinterpret_cast<const float4*>(bias + u * 8 + 4));
+    }
+    const uint32_t* a = &acc[u >> 2][(u & 3) * 8];
+    float v[8];
+    v[0] = __uint_as_float(a[0]) + b0.x;
+    v[1] = __uint_as_float(a[1]) + b0.y;
+    v[2] = __uint_as_float(a[2]) + b0.z;
+    v[3] = __uint_as_float(a[3]) + b0.w;
+    v[4] = __uint_as_float(a[4]) + b1.x;
+    v[5] = __uint_as_float(a[5]) + b1.y;
+    v[6] = __uint_as_float(a[6]) + b1.z;
+    v[7] = __uint_as_float(a[7]) + b1.w;
+    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
+    }
+    if (EPI == EPI_BIAS_RESID) {
+      if (row_ok) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(resid_row + u * 8);
+        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                     r3 = unpack_bf16x2(rr.w);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+        v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(staging + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
+  }
+}
+
 // SwiGLU epilogue of one 32-row x 64-output chunk: g, u = the gate / up accumulators (two 32-column
 // TMEM reads each); silu(g) * u -> bf16 -> the warp's swizzled staging tile.
 // silu(g) = g / (1 + 2^(-g log2 e)): one ex2 + one rcp per element (hidden under the K loop's MMAs).
