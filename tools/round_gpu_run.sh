@@ -9,6 +9,6 @@ timeout -s KILL 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.
 timeout -s KILL 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
 timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:gemm_bf16|attention3|attn_prep|layernorm_kernel" --launch-skip 7 -c 7 -f \
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:gemm|attention3|attn_prep|layernorm" --launch-skip 7 -c 7 -f \
   -o gpurun_out/layer_b512 python tools/prof_kernels.py 512 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | tail -n 12
