@@ -25,9 +25,9 @@ mask = torch.ones(b, s, dtype=torch.int64, device=dev)
 for _ in range(2):
     qkv = nv.gemm_bf16(x, wqkv, torch.zeros(3 * h, device=dev), None, nv.EPI_BIAS)
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
-    t = nv.gemm_bf16(ctx, wo, torch.zeros(h, device=dev), x, nv.EPI_BIAS_RESID)
+    t = nv.gemm_bf16(ctx, wo, torch.zeros(h, device=dev), None, nv.EPI_BIAS)   # residual add lives in the LayerNorm
     y = nv.layernorm(t, torch.ones(h, device=dev), torch.zeros(h, device=dev), 1e-12)
     f = nv.gemm_bf16(y, w1, torch.zeros(i, device=dev), None, nv.EPI_BIAS_GELU)
-    t2 = nv.gemm_bf16(f, w2, torch.zeros(h, device=dev), y, nv.EPI_BIAS_RESID)
+    t2 = nv.gemm_bf16(f, w2, torch.zeros(h, device=dev), None, nv.EPI_BIAS)
 torch.cuda.synchronize()
 print('done')
