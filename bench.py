@@ -212,7 +212,7 @@ def run_reference(args) -> None:
         'e2e': {'value': value, 'unit': 'chunks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
@@ -376,7 +376,7 @@ def run_native(args) -> None:
             'gpu_launches': launches_per_step(BERT_BASE) * steps,
             'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_base,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     enc.close()
     if world > 1:
         dist.barrier()
@@ -391,10 +391,25 @@ def main() -> None:
     ap.add_argument('--impl', choices=['native', 'reference'], default='native')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle timing leg')
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries write to fd 1 while the benchmark
+    # runs (NCCL's version banner, progress bars) is sent to stderr; emit() writes to the saved fd
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
         run_native(args)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    payload = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, payload)
 
 
 if __name__ == '__main__':
