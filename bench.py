@@ -359,7 +359,7 @@ def run_native(args) -> None:
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
             pick_cpu_threads()
-            n_chunks = 16
+            n_chunks = 64   # ~10-15 s of CPU work on 16 threads
             sec, n = cpu_oracle_run(n_chunks, 8)
             cpu_base = {'value': n / sec, 'unit': 'chunks/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                         'sample': f'{n} chunks of {SEQ} tokens, batch 8, fp32 torch CPU oracle ({sec:.1f} s)'}
