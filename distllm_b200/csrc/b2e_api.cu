@@ -289,7 +289,9 @@ struct AttnScratch {
   float* bias = nullptr;   // [B, S_pad]
   int* kv_chunks = nullptr;  // [B]
   size_t cap_bias = 0, cap_b = 0;
+  uint64_t gen = 0;   // bumped on every reallocation
   int ensure(int B, int S_pad) {
+    if ((size_t)B * S_pad > cap_bias || (size_t)B > cap_b) ++gen;
     if ((size_t)B * S_pad > cap_bias) {
       if (bias) cudaFree(bias);
       bias = nullptr;
@@ -435,8 +437,10 @@ struct PoolScratch {
   float* part = nullptr;   // [B,nsplit,H]
   size_t cap_b = 0, cap_s = 0, cap_bs = 0, cap_part = 0;
   int device = -1;
+  uint64_t gen = 0;   // bumped on every reallocation (captured CUDA graphs hold these pointers)
 
   int ensure(int B, int S, size_t part_elems) {
+    if ((size_t)B > cap_b || (size_t)S > cap_s || (size_t)B * S > cap_bs || part_elems > cap_part) ++gen;
     if ((size_t)B > cap_b) {
       if (seq_len) cudaFree(seq_len);
       if (idx) cudaFree(idx);
@@ -540,6 +544,21 @@ struct B2EEncoder {
   //   0 embed_tokens, 1 final norm; per layer (2 + 6 l): input norm, Wqkv, Wo, post-attention norm,
   //   Wgu (gate/up interleaved), Wd
   const void* Mi(int l, int k) const { return w[2 + 6 * l + k]; }
+  // b2e_embed_host replays one CUDA graph per (batch shape, pooling, staging slot) instead of ~90
+  // launches per batch; every graph is dropped when a buffer it points into is reallocated
+  struct StepGraph {
+    int B, S, pool_kind, l2, has_types, slot;
+    cudaGraphExec_t exec;
+  };
+  std::vector<StepGraph> graphs;
+  uint64_t ws_gen = 0;        // bumped when the workspace or a staging buffer is reallocated
+  uint64_t graphs_stamp = 0;  // buffer_stamp() at the time the cached graphs were captured
+  uint64_t buffer_stamp() const { return ws_gen + pool.gen + attn.gen; }
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+
   int qkv_cols() const {
     return desc.arch == B2E_ARCH_MISTRAL ? (desc.heads + 2 * desc.kv_heads) * desc.head_dim
                                          : 3 * desc.hidden;
@@ -561,6 +580,7 @@ size_t tokens_bytes(const B2EModelDesc& d, size_t tokens) {
 int ensure_workspace(B2EEncoder* e, int B, int S) {
   const size_t tokens = (size_t)B * S;
   if (tokens > e->cap_tokens) {
+    ++e->ws_gen;
     cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
     e->hidden = e->qkv = e->ctx = e->tmp = e->ffn = nullptr;
     e->cap_tokens = 0;
@@ -578,6 +598,7 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     e->cap_tokens = tokens;
   }
   if (e->desc.arch == B2E_ARCH_ESM2 && (size_t)B > e->cap_scale) {
+    ++e->ws_gen;
     cudaFree(e->tok_scale);
     e->tok_scale = nullptr;
     CUDA_TRY(cudaMalloc(&e->tok_scale, sizeof(float) * B));
@@ -924,6 +945,7 @@ void b2e_encoder_destroy(B2EEncoder* e) {
   cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
   cudaFree(e->stage_in); cudaFree(e->stage_out);
   cudaFree(e->xres); cudaFree(e->tok_scale); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
+  e->drop_graphs();
   e->pool.release();
   e->attn.release();
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1092,6 +1114,7 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
   // two input slots (ids | mask | types) so batch i+1 uploads while batch i computes
   const size_t slot = (size_t)batch * S * 3;
   if (2 * slot > e->stage_cap) {
+    ++e->ws_gen;
     cudaFree(e->stage_in);
     e->stage_in = nullptr;
     CUDA_TRY(cudaMalloc(&e->stage_in, 2 * slot * sizeof(int64_t)));
@@ -1099,11 +1122,16 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
   }
   const size_t out_elems = (size_t)batch * H * 2;
   if (out_elems > e->stage_out_cap) {
+    ++e->ws_gen;
     cudaFree(e->stage_out);
     e->stage_out = nullptr;
     CUDA_TRY(cudaMalloc(&e->stage_out, out_elems * sizeof(float)));
     e->stage_out_cap = out_elems;
   }
+  static const bool use_graphs = [] {
+    const char* v = getenv("B2E_GRAPHS");   // B2E_GRAPHS=0: every batch launches its kernels one by one
+    return !(v && v[0] == '0');
+  }();
   int which = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += batch, which ^= 1) {
     const int B = (int)((n_rows - r0 < batch) ? (n_rows - r0) : batch);
@@ -1115,9 +1143,45 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     CUDA_TRY(cudaMemcpyAsync(d_ids, ids + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_mask, mask + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
     if (types) CUDA_TRY(cudaMemcpyAsync(d_types, types + r0 * S, n * 8, cudaMemcpyHostToDevice, st));
-    if ((rc = b2e_encode_pooled(e, d_ids, d_mask, types ? d_types : nullptr, B, S, pool_kind, l2,
-                                d_out, st)))
-      return rc;
+    // The first batch runs eagerly (it sizes every buffer and sets the kernels' attributes); later
+    // FULL batches replay a graph captured once per (shape, pooling, staging slot): one launch
+    // instead of ~90, which is what a small `batch_size` (the reference's default is 8) is bound by.
+    const bool eager = !use_graphs || r0 == 0 || B != batch;
+    if (eager) {
+      if ((rc = b2e_encode_pooled(e, d_ids, d_mask, types ? d_types : nullptr, B, S, pool_kind, l2,
+                                  d_out, st)))
+        return rc;
+    } else {
+      if (e->graphs_stamp != e->buffer_stamp()) {
+        e->drop_graphs();
+        e->graphs_stamp = e->buffer_stamp();
+      }
+      cudaGraphExec_t exec = nullptr;
+      for (const auto& g : e->graphs)
+        if (g.B == B && g.S == S && g.pool_kind == pool_kind && g.l2 == l2 &&
+            g.has_types == (types != nullptr) && g.slot == which)
+          exec = g.exec;
+      if (!exec) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = b2e_encode_pooled(e, d_ids, d_mask, types ? d_types : nullptr, B, S, pool_kind, l2, d_out, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess) return fail(B2E_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        if (e->graphs_stamp != e->buffer_stamp()) {   // a buffer moved during capture: do not keep it
+          cudaGraphDestroy(graph);
+          return fail(B2E_ERR_CUDA, "workspace reallocated while capturing a step graph");
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(B2E_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        e->graphs.push_back({B, S, pool_kind, l2, types != nullptr, which, exec});
+      }
+      CUDA_TRY(cudaGraphLaunch(exec, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(out_host + r0 * H, d_out, (size_t)B * H * sizeof(float),
                              cudaMemcpyDeviceToHost, st));
   }

@@ -122,6 +122,29 @@ def test_embed_host_equals_device_path_bitwise(tiny_native, bert_golden):
     assert s >= 1
 
 
+def test_embed_host_graph_replay_equals_eager(tiny_native, tiny_bert):
+    """From the second full batch on b2e_embed_host replays a captured CUDA graph (two staging slots):
+    every batch must equal the eager per-batch call bit for bit, including a ragged last batch, a
+    second call with another shape (new graphs) and a return to the first shape (cached graphs)."""
+    cfg, _ = tiny_bert
+    g = torch.Generator().manual_seed(31)
+
+    def make(n, s):
+        ids = torch.randint(5, cfg.vocab_size, (n, s), generator=g)
+        lens = torch.randint(1, s + 1, (n,), generator=g)
+        mask = (torch.arange(s)[None] < lens[:, None]).long()
+        return ids.pin_memory(), mask.pin_memory(), torch.zeros_like(ids).pin_memory()
+
+    for n, s, batch, pool in [(27, 40, 4, nv.POOL_MEAN_REF), (16, 64, 8, nv.POOL_LAST_TOKEN),
+                              (27, 40, 4, nv.POOL_MEAN_REF)]:
+        ids, mask, types = make(n, s)
+        host = tiny_native.embed_host(ids, mask, types, batch=batch, pool_kind=pool, normalize=True)
+        for r0 in range(0, n, batch):
+            sl = slice(r0, min(n, r0 + batch))
+            ref = tiny_native.encode_pooled(ids[sl], mask[sl], types[sl], pool, True)
+            assert torch.equal(host[sl], ref.cpu()), (n, s, batch, r0)
+
+
 @pytest.fixture(scope='module')
 def base_model():
     """BERT-base shape (S-PubMedBert-MS-MARCO: L=12, H=768, 12 heads, I=3072), seeded random weights."""
