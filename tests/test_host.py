@@ -251,3 +251,90 @@ def test_cli_embed_flags_match_reference():
         'jsonl', 1, 'mean', 'full_sequence', 'huggingface', False)
     merge_opts = {o for p in group.commands['merge'].params for o in p.opts}
     assert {'--writer_name', '--num_proc', '--dataset_dir', '--output_dir'} <= merge_opts
+
+
+# ------------------------------------------------------------------------------ host feed (collator)
+def _bert_tokenizer(tmp_path, max_len=32):
+    from transformers import BertTokenizerFast
+
+    words = [f'w{i:03d}' for i in range(300)]
+    (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
+    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok.model_max_length = max_len
+    return tok, words
+
+
+def _llama_like_tokenizer(max_len=24):
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from tokenizers.processors import TemplateProcessing
+    from transformers import PreTrainedTokenizerFast
+
+    words = [f'w{i:03d}' for i in range(300)]
+    vocab = {t: i for i, t in enumerate(['<pad>', '<s>', '</s>', '<unk>', *words])}
+    raw = Tokenizer(WordLevel(vocab, unk_token='<unk>'))
+    raw.pre_tokenizer = Whitespace()
+    raw.post_processor = TemplateProcessing(single='<s> $A', special_tokens=[('<s>', 1)])
+    tok = PreTrainedTokenizerFast(tokenizer_object=raw, pad_token='<pad>', bos_token='<s>', eos_token='</s>',
+                                  unk_token='<unk>', model_input_names=['input_ids', 'attention_mask'])
+    tok.model_max_length = max_len
+    return tok, words
+
+
+def _assert_same_batch(collator_fast, collator_ref, texts):
+    import torch
+
+    a, b = collator_fast(texts), collator_ref(texts)
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].dtype == b[k].dtype == torch.int64
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_fast_collator_equals_the_reference_call_bert(tmp_path):
+    """The numpy-padded batch built from the Rust backend's encodings is, tensor for tensor, what
+    `tokenizer(batch, padding=True, truncation=True, return_tensors='pt')` returns
+    (distllm/embed/datasets/utils.py:43-50): ragged rows, a truncated row, an empty string, unknown
+    words, one-row batches."""
+    from distllm_b200.embed.datasets.utils import DataCollator
+
+    tok, words = _bert_tokenizer(tmp_path)
+    rng = np.random.default_rng(3)
+    texts = [' '.join(rng.choice(words, size=n)) for n in (1, 7, 30, 31, 80, 2, 15)] + ['', 'zzz unknown w001']
+    fast, ref = DataCollator(tok), DataCollator(tok, fast=False)
+    assert fast._fast and not ref._fast
+    _assert_same_batch(fast, ref, texts)
+    _assert_same_batch(fast, ref, texts[:1])
+    _assert_same_batch(fast, ref, [texts[4]])          # only a truncated row
+    assert fast(texts)['input_ids'].shape[1] == 32     # truncated to model_max_length
+    # the reference call still works after the fast path has reconfigured the backend, and vice versa
+    _assert_same_batch(fast, ref, texts[::-1])
+
+
+@pytest.mark.parametrize('side', ['right', 'left'])
+def test_fast_collator_equals_the_reference_call_without_token_types(side):
+    from distllm_b200.embed.datasets.utils import DataCollator
+
+    tok, words = _llama_like_tokenizer()
+    tok.padding_side = side
+    rng = np.random.default_rng(4)
+    texts = [' '.join(rng.choice(words, size=n)) for n in (3, 40, 1, 23, 22, 9)]
+    fast, ref = DataCollator(tok), DataCollator(tok, fast=False)
+    _assert_same_batch(fast, ref, texts)
+    assert 'token_type_ids' not in fast(texts)
+    mask = fast(texts)['attention_mask']
+    assert (mask[:, 0] == 1).all() if side == 'right' else (mask[:, -1] == 1).all()
+
+
+def test_slow_tokenizers_take_the_reference_call(tmp_path):
+    from transformers import EsmTokenizer
+
+    from distllm_b200.embed.datasets.utils import DataCollator
+
+    (tmp_path / 'vocab.txt').write_text('\n'.join(['<cls>', '<pad>', '<eos>', '<unk>', 'L', 'A', 'G', 'V', '<mask>']) + '\n')
+    tok = EsmTokenizer(str(tmp_path / 'vocab.txt'))
+    coll = DataCollator(tok)
+    assert not coll._fast
+    out = coll(['LAGV', 'LA'])
+    assert out['input_ids'].shape == (2, 6) and out['attention_mask'].sum().item() == 10
