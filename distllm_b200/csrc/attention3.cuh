@@ -6,11 +6,11 @@
 //
 //   warp 9      loader      Q tiles (double-buffered across items) and {K_j, V_j, mask-bias_j}
 //                           ring stages: cp.async.bulk.tensor + one 256 B cp.async.bulk
-//   warp 8      MMA issuer  S_j = Q K_j^T (SS, 128x64x16) and O += P_j V_j (TS: P read from TMEM,
-//                           V_j as MN-major smem operand); per-slot state machines polled without
-//                           blocking; S is DOUBLE-buffered per slot, so Q K_{j+1}^T is issued
-//                           before softmax_j finishes and the MMA round trip leaves the softmax
-//                           critical path
+//   warps 8,10  MMA issuers (one elected thread each, one per query tile / TMEM slot):
+//                           S_j = Q K_j^T (SS, 128x64x16) and O += P_j V_j (TS: P read from TMEM,
+//                           V_j as MN-major smem operand); S is DOUBLE-buffered per slot, so
+//                           Q K_{j+1}^T is issued before softmax_j finishes and the MMA round trip
+//                           leaves the softmax critical path
 //   warps 0-3   softmax for query tile A (slot 0)    one row per thread; scores of a chunk live in
 //   warps 4-7   softmax for query tile B (slot 1)    registers; online softmax with lazy rescale;
 //                                                    bf16 P written over S's own TMEM columns
@@ -119,6 +119,7 @@ __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
 
 // profiling aid (b2e_debug_set_clock_buffer): CTA 0 records (clock64, code) pairs per role
 __device__ long long* g_att3_clock = nullptr;
+__device__ int g_att3_flags = 0;   // experiment knob, bit 0: ping-pong between the softmax warpgroups
 
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
@@ -156,7 +157,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
       tma_prefetch_desc(&tm_ctx);
       for (int i = 0; i < AT3_NST; ++i) {
         mbar_init(kv_full + 8u * i, 1);
-        mbar_init(kv_empty + 8u * i, 1);
+        mbar_init(kv_empty + 8u * i, 2);   // one arrival from each slot's MMA issuer
       }
       for (int i = 0; i < 4; ++i) {
         mbar_init(q_full + 8u * i, 1);
@@ -235,101 +236,86 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           cur = nxt;
         }
       }
-    } else if (warp == 8) {
+    } else if (warp == 8 || warp == 10) {
       if (elect_one()) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ MMA issuer of ONE slot
+        // (warp 8: query tile A, warp 10: query tile B).  One thread driving both slots needed ~450 clk
+        // per QK or PV event (polls + 4 MMAs + commits), four events per pair of chunks: 1800 clk,
+        // more than the softmax itself.  Two threads run their slots side by side with blocking waits.
+        const int slot = (warp == 8) ? 0 : 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(128, AT3_KC, 0, 0);
         constexpr uint32_t idesc_o = make_idesc_bf16(128, AT3_D, 0, 1);  // B (= V) is MN-major
+        const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
         uint32_t chunk_base = 0;   // ring position of this item's chunk 0
-        uint32_t q_par = 0;        // per (buf,slot) bit: parity of the q_full phase to wait for
-        uint32_t p_par = 0;        // per (slot,sbuf) bit: parity of the p_ready phase to wait for
-        uint32_t tile_cnt[2] = {0, 0};
+        uint32_t q_cnt[2] = {0, 0};   // Q tiles consumed per item buffer (parity of q_full)
+        uint32_t p_par = 0;           // bit sbuf: parity of the p_ready phase to wait for
+        uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
         At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
         for (; item < n_items; item += gridDim.x, ++it) {
           const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
-          const int pr = cur.pr;
           const int n = cur.n;
           const int buf = it & 1;
-          const int n_active = (2 * pr + 1 < nq) ? 2 : 1;
-          AT3_STAMP(2, 9000 + n);
-          int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
-          bool q_ok[2] = {false, false};
-          int released = 0;
-          int remaining = n_active;
-          while (remaining > 0) {
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              if (slot >= n_active || pv_next[slot] >= n) continue;
-              const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
-              const int qidx = buf * 2 + slot;
-              // ---- S_j = Q K_j^T into S buffer j&1 (at most one chunk ahead of P_j V_j)
-              if (qk_next[slot] < n && qk_next[slot] < pv_next[slot] + 2) {
-                const int j = qk_next[slot];
-                const uint32_t c = chunk_base + j;
-                const int st = c % AT3_NST;
-                bool ready = q_ok[slot] || mbar_test(q_full + 8u * qidx, (q_par >> qidx) & 1u);
-                ready = ready && mbar_test(kv_full + 8u * st, (c / AT3_NST) & 1u);
-                if (ready) {
-                  if (!q_ok[slot]) {
-                    q_ok[slot] = true;
-                    q_par ^= 1u << qidx;
-                  }
-                  tc_fence_after();
-                  const uint64_t q_desc =
-                      make_smem_desc_sw128(sb + AT3_SMEM_Q + qidx * AT3_QTILE, 16, 1024);
-                  const uint64_t k_desc =
-                      make_smem_desc_sw128(sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE, 16, 1024);
-                  const uint32_t d = t_slot + static_cast<uint32_t>((j & 1) * 64);
-#pragma unroll
-                  for (int k = 0; k < AT3_D / 16; ++k)
-                    tc_mma_f16_ss(d, q_desc + 2u * k, k_desc + 2u * k, idesc_s,
-                                  static_cast<uint32_t>(k != 0));
-                  tc_commit(s_ready + 8u * (slot * 2 + (j & 1)));
-                  AT3_STAMP(2, slot * 1000 + j * 10 + 1);
-                  if (j + 1 == n) tc_commit(q_empty + 8u * qidx);
-                  ++qk_next[slot];
-                }
-              }
-              // ---- O += P_j V_j once the softmax warpgroup has published P_j
-              if (pv_next[slot] < qk_next[slot]) {
-                const int j = pv_next[slot];
-                const int sbuf = j & 1;
-                const int pidx = slot * 2 + sbuf;
-                if (mbar_test(p_ready + 8u * pidx, (p_par >> pidx) & 1u)) {
-                  p_par ^= 1u << pidx;
-                  // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
-                  if (j == 0 && tile_cnt[slot] > 0)
-                    mbar_wait(o_empty + 8u * slot, (tile_cnt[slot] - 1) & 1u);
-                  tc_fence_after();
-                  const uint32_t c = chunk_base + j;
-                  const int st = c % AT3_NST;
-                  const uint32_t p = t_slot + static_cast<uint32_t>(sbuf * 64);
-                  const uint32_t o = t_slot + 128u;
-                  const uint32_t v_base = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE + AT3_KVTILE;
-#pragma unroll
-                  for (int k = 0; k < AT3_KC / 16; ++k) {
-                    const uint64_t v_desc = make_smem_desc_sw128(v_base + k * 16 * 128, 1024, 1024);
-                    tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
-                                  static_cast<uint32_t>((j | k) != 0));
-                  }
-                  tc_commit(pv_done + 8u * pidx);
-                  AT3_STAMP(2, slot * 1000 + j * 10 + 2);
-                  ++pv_next[slot];
-                  if (pv_next[slot] == n) {
-                    tc_commit(o_ready + 8u * slot);
-                    ++tile_cnt[slot];
-                    --remaining;
-                  }
-                }
-              }
+          const bool active = 2 * cur.pr + slot < nq;
+          if (slot == 0) AT3_STAMP(2, 9000 + n);
+          if (!active) {
+            // this slot has no query tile in the item: it still owes the ring one arrival per chunk,
+            // and may give it only once the stage has been filled for THIS use
+            for (int j = 0; j < n; ++j) {
+              const uint32_t c = chunk_base + j;
+              mbar_wait(kv_full + 8u * (c % AT3_NST), (c / AT3_NST) & 1u);
+              mbar_arrive(kv_empty + 8u * (c % AT3_NST));
             }
-            // ring stages whose chunk has been consumed by every active slot go back to the loader
-            const int done = (n_active == 2) ? min(pv_next[0], pv_next[1]) : pv_next[0];
-            while (released < done) {
-              tc_commit(kv_empty + 8u * ((chunk_base + released) % AT3_NST));
-              ++released;
+          } else {
+            const int qidx = buf * 2 + slot;
+            const uint64_t q_desc = make_smem_desc_sw128(sb + AT3_SMEM_Q + qidx * AT3_QTILE, 16, 1024);
+            auto issue_qk = [&](int j) {
+              const uint32_t c = chunk_base + j;
+              const int st = c % AT3_NST;
+              mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);
+              tc_fence_after();
+              const uint64_t k_desc =
+                  make_smem_desc_sw128(sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE, 16, 1024);
+              const uint32_t d = t_slot + static_cast<uint32_t>((j & 1) * 64);
+#pragma unroll
+              for (int k = 0; k < AT3_D / 16; ++k)
+                tc_mma_f16_ss(d, q_desc + 2u * k, k_desc + 2u * k, idesc_s, static_cast<uint32_t>(k != 0));
+              tc_commit(s_ready + 8u * (slot * 2 + (j & 1)));
+              if (slot == 0) AT3_STAMP(2, j * 10 + 1);
+              if (j + 1 == n) tc_commit(q_empty + 8u * qidx);
+            };
+            mbar_wait(q_full + 8u * qidx, q_cnt[buf] & 1u);
+            ++q_cnt[buf];
+            issue_qk(0);
+            for (int j = 0; j < n; ++j) {
+              // S_{j+1} = Q K_{j+1}^T goes out before P_j is awaited: its buffer held P_{j-1}, whose
+              // P V was issued one iteration ago (tcgen05 ops of one thread execute in order)
+              if (j + 1 < n) issue_qk(j + 1);
+              const int sbuf = j & 1;
+              mbar_wait(p_ready + 8u * (slot * 2 + sbuf), (p_par >> sbuf) & 1u);
+              p_par ^= 1u << sbuf;
+              // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
+              if (j == 0 && tile_cnt > 0) mbar_wait(o_empty + 8u * slot, (tile_cnt - 1) & 1u);
+              tc_fence_after();
+              const uint32_t c = chunk_base + j;
+              const int st = c % AT3_NST;
+              const uint32_t p = t_slot + static_cast<uint32_t>(sbuf * 64);
+              const uint32_t o = t_slot + 128u;
+              const uint32_t v_base = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE + AT3_KVTILE;
+#pragma unroll
+              for (int k = 0; k < AT3_KC / 16; ++k) {
+                const uint64_t v_desc = make_smem_desc_sw128(v_base + k * 16 * 128, 1024, 1024);
+                tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
+                              static_cast<uint32_t>((j | k) != 0));
+              }
+              tc_commit(pv_done + 8u * (slot * 2 + sbuf));
+              tc_commit(kv_empty + 8u * st);   // this slot is done with the stage (K by Q K^T, V by P V)
+              if (slot == 0) AT3_STAMP(2, j * 10 + 2);
+              if (j + 1 == n) {
+                tc_commit(o_ready + 8u * slot);
+                ++tile_cnt;
+              }
             }
           }
           chunk_base += static_cast<uint32_t>(n);
@@ -352,12 +338,22 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
     At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+    // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
+    const bool pingpong = (g_att3_flags & 1) != 0;   // off by default: measured 3 % slower, see below
+    if (pingpong && slot == 1) asm volatile("bar.arrive %0, 256;" ::"r"(4) : "memory");  // A goes first
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
       const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
       const int pr = cur.pr, h = cur.h, b = cur.b, n = cur.n;
       const int t = 2 * pr + slot;
+      if (t >= nq && pingpong) {
+        // no query tile for this slot in the item: keep the other warpgroup's turns coming
+        for (int j = 0; j < n; ++j) {
+          asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
+          asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
+        }
+      }
       if (t < nq) {
         float m_used = 0.0f, l = 0.0f;
         for (int j = 0; j < n; ++j) {
@@ -376,6 +372,11 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           tmem_ld32(t_s, s0);
           tmem_ld32(t_s + 32u, s1);
           tmem_ld_wait();
+          // Optional ping-pong (experiment, b2e_debug_set_att3_flags bit 0): the exp-heavy part of a chunk
+          // runs in ONE warpgroup at a time.  Measured: a warpgroup alone still needs ~950 clk for the 64
+          // exponentials per thread (issue/latency bound, MUFU alone would be 512), so strict alternation
+          // gives 2 x 950 per pair of chunks, no better than the ~1950 of the free-running version.
+          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           uint32_t pk[32];
           if (j == 0) {
             // first chunk of the row: exact maximum first (always finite: key 0 exists)
@@ -417,6 +418,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             }
             l += sum;
           }
+          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
           if (r == 0) AT3_STAMP(slot, j * 10 + 2);
           tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
           tmem_st_wait();

@@ -795,6 +795,11 @@ int b2e_debug_set_att3_clock(void* device_buffer) {
   return B2E_OK;
 }
 
+int b2e_debug_set_att3_flags(int flags) {
+  CUDA_TRY(cudaMemcpyToSymbol(g_att3_flags, &flags, sizeof(flags)));
+  return B2E_OK;
+}
+
 // Experiment knob for the CTA-pair GEMM: bit 0 = skip the epilogue's math and stores.
 int b2e_debug_set_pair_flags(int flags) {
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_flags, &flags, sizeof(flags)));
