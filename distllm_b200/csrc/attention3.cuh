@@ -119,7 +119,7 @@ __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
 
 // profiling aid (b2e_debug_set_clock_buffer): CTA 0 records (clock64, code) pairs per role
 __device__ long long* g_att3_clock = nullptr;
-__device__ int g_att3_flags = 0;   // experiment knob, bit 0: ping-pong between the softmax warpgroups
+__device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the exp phase, 2 (default) de-phase once per item
 
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
@@ -339,7 +339,10 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     int item = blockIdx.x;
     At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
-    const bool pingpong = (g_att3_flags & 1) != 0;   // off by default: measured 3 % slower, see below
+    // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
+    // is ordered (A before B), which merely de-phases the two warpgroups
+    const int pp_mode = g_att3_flags & 3;
+    const bool pingpong = pp_mode != 0;
     if (pingpong && slot == 1) asm volatile("bar.arrive %0, 256;" ::"r"(4) : "memory");  // A goes first
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
@@ -349,7 +352,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
       const int t = 2 * pr + slot;
       if (t >= nq && pingpong) {
         // no query tile for this slot in the item: keep the other warpgroup's turns coming
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < ((pp_mode & 1) ? n : 1); ++j) {
           asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
         }
@@ -376,7 +379,8 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           // runs in ONE warpgroup at a time.  Measured: a warpgroup alone still needs ~950 clk for the 64
           // exponentials per thread (issue/latency bound, MUFU alone would be 512), so strict alternation
           // gives 2 x 950 per pair of chunks, no better than the ~1950 of the free-running version.
-          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
+          const bool turn = (pp_mode & 1) || (pp_mode == 2 && j == 0);
+          if (turn) asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           uint32_t pk[32];
           if (j == 0) {
             // first chunk of the row: exact maximum first (always finite: key 0 exists)
@@ -418,7 +422,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
             }
             l += sum;
           }
-          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
+          if (turn) asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
           if (r == 0) AT3_STAMP(slot, j * 10 + 2);
           tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
           tmem_st_wait();
