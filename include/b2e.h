@@ -9,8 +9,9 @@
  * Reference interfaces replaced (paths relative to the distllm tree):
  *   b2e_encoder_create      distllm/embed/encoders/auto.py:37-97   (AutoEncoder.__init__)
  *   b2e_encode              distllm/embed/encoders/auto.py:119-138 (AutoEncoder.encode ->
- *                           HF BertModel.forward, transformers/models/bert/modeling_bert.py:628-690) and
- *                           distllm/embed/encoders/esm2.py:109-134 (Esm2Encoder.encode -> HF
+ *                           HF BertModel.forward, transformers/models/bert/modeling_bert.py:628-690, or
+ *                           HF MistralModel.forward, transformers/models/mistral/modeling_mistral.py:328-400)
+ *                           and distllm/embed/encoders/esm2.py:109-134 (Esm2Encoder.encode -> HF
  *                           EsmForMaskedLM, transformers/models/esm/modeling_esm.py:189-516)
  *   b2e_encode_pooled       distllm/embed/embedders/full_sequence.py:59-69 (encode + pool + normalize)
  *   b2e_embed_host          distllm/embed/embedders/full_sequence.py:57-78 (the whole batch loop,
@@ -19,8 +20,8 @@
  *   b2e_pool_last_token     distllm/embed/poolers/last_token.py:12-39
  *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
  *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
- *   b2e_gemm_bf16 / b2e_attention_d64 / b2e_layernorm: the building blocks, exported so the parity
- *                           tests can pin each kernel separately.
+ *   b2e_gemm_bf16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
+ *                           blocks, exported so the parity tests can pin each kernel separately.
  */
 #ifndef B2E_H_
 #define B2E_H_
@@ -78,10 +79,13 @@ int b2e_version(void);
 const char* b2e_last_error(void);
 
 /* Number of device weight pointers b2e_encoder_create expects for `desc` (BERT: 5 + 12*L, ESM-2:
- * 3 + 12*L; order documented in distllm_b200/embed/encoders/weights.py).  Matrices are bf16 [out,in]
- * row-major, vectors and embedding tables fp32.  The pointers stay owned by the caller and must
- * outlive the handle.  For B2E_ARCH_ESM2, desc.reserved = mask_token_id + 1 enables ESM's token
- * dropout rescaling (0 = off) and token_type_ids are ignored. */
+ * 3 + 12*L, Mistral: 2 + 6*L; order documented in distllm_b200/embed/encoders/weights.py).  Matrices
+ * are bf16 [out,in] row-major, vectors and embedding tables fp32.  The pointers stay owned by the
+ * caller and must outlive the handle.  For B2E_ARCH_ESM2, desc.reserved = mask_token_id + 1 enables
+ * ESM's token dropout rescaling (0 = off) and token_type_ids are ignored.  For B2E_ARCH_MISTRAL
+ * (head_dim 128, heads % kv_heads == 0, intermediate % 128 == 0) the gate/up projection is ONE matrix
+ * with rows interleaved in blocks of 64 (see B2E_EPI_SWIGLU), desc.sliding_window = 0 means none, and
+ * token_type_ids are ignored. */
 int b2e_num_weights(const B2EModelDesc* desc);
 int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int n_weights,
                        int device, B2EEncoder** out);
