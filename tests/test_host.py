@@ -338,3 +338,64 @@ def test_slow_tokenizers_take_the_reference_call(tmp_path):
     assert not coll._fast
     out = coll(['LAGV', 'LA'])
     assert out['input_ids'].shape == (2, 6) and out['attention_mask'].sum().item() == 10
+
+
+# ------------------------------------------------------------------------------ columnar writer
+def _reference_rows(result):
+    """What distllm/embed/writers/huggingface.py:19-34 + :70 build: one dict per row -> from_list."""
+    rows = []
+    for idx, (text, emb) in enumerate(zip(result.text, result.embeddings)):
+        item = {'text': text, 'embeddings': emb}
+        if result.metadata is not None:
+            item.update(result.metadata[idx])
+        rows.append(item)
+    return rows
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float16])
+@pytest.mark.parametrize('with_metadata', [True, False])
+def test_columnar_huggingface_writer_equals_the_reference_table(tmp_path, dtype, with_metadata):
+    """Same features, same column order, same content as the reference's row-wise `Dataset.from_list`,
+    including a metadata key that is missing from later rows and one that only later rows carry
+    (dropped by from_list, which takes its columns from the first row)."""
+    from datasets import Dataset
+
+    rng = np.random.default_rng(1)
+    n, h = 37, 24
+    emb = rng.standard_normal((n, h)).astype(dtype)
+    text = [f'chunk {i}' for i in range(n)]
+    meta = None
+    if with_metadata:
+        meta = [{'path': f'doc{i // 5}', 'idx': i, 'score': i / 7} for i in range(n)]
+        del meta[3]['score']          # absent later -> None
+        meta[5]['extra'] = 'ignored'  # not in the first row -> no column
+    result = EmbedderResult(emb, text, meta)
+    w = get_writer({'name': 'huggingface'})
+    w.write(tmp_path / 'col', result)
+    got = Dataset.load_from_disk(tmp_path / 'col')
+    want = Dataset.from_list(_reference_rows(result))
+    assert got.features == want.features
+    assert got.column_names == want.column_names
+    assert got.to_dict() == want.to_dict()
+    # and the merged dataset of two such directories reads back in order
+    w.write(tmp_path / 'col2', result)
+    w.merge([tmp_path / 'col', tmp_path / 'col2'], tmp_path / 'merged')
+    merged = Dataset.load_from_disk(tmp_path / 'merged')
+    assert len(merged) == 2 * n and merged[n]['text'] == 'chunk 0'
+
+
+def test_columnar_writer_falls_back_on_untypeable_metadata(tmp_path):
+    from datasets import Dataset
+
+    result = EmbedderResult(np.zeros((2, 4), np.float32), ['a', 'b'], [{'k': 1}, {'k': 'one'}])
+    w = get_writer({'name': 'huggingface'})
+    try:
+        want = Dataset.from_list(_reference_rows(result))
+    except Exception:  # noqa: BLE001  the reference cannot type this column either
+        want = None
+    if want is None:
+        with pytest.raises(Exception):  # noqa: B017, PT011
+            w.write(tmp_path / 'x', result)
+    else:
+        w.write(tmp_path / 'x', result)
+        assert Dataset.load_from_disk(tmp_path / 'x').to_dict() == want.to_dict()
