@@ -39,6 +39,7 @@ EXPORTS = (
     'b2e_gemm_bf16',
     'b2e_attention_d64',
     'b2e_attention_causal_d128',
+    'b2e_topk_ip',
     'b2e_layernorm',
 )
 
@@ -105,6 +106,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_attention_d64.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.b2e_attention_causal_d128.restype = i32
     lib.b2e_attention_causal_d128.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.b2e_topk_ip.restype = i32
+    lib.b2e_topk_ip.argtypes = [vp, i32, vp, i32, i64, i32, i32, vp, vp, vp]
     lib.b2e_layernorm.restype = i32
     lib.b2e_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
 
@@ -219,6 +222,23 @@ def attention_causal_d128(
         check(lib.b2e_attention_causal_d128(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(),
                                             batch, seq, heads, kv_heads, window, stream_ptr(qkv.device)))
     return ctx
+
+
+def topk_ip(queries: torch.Tensor, corpus: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Exact inner-product top-k: queries [Q,H] f32, corpus [N,H] f32|bf16 (CUDA) -> (scores [Q,k] f32,
+    indices [Q,k] i64), sorted by descending score."""
+    lib = load()
+    _cuda_contig(queries, 'queries'), _cuda_contig(corpus, 'corpus')
+    if queries.dtype != torch.float32:
+        raise NativeError('queries must be float32')
+    q, h = queries.shape
+    n = corpus.shape[0]
+    scores = torch.empty((q, k), dtype=torch.float32, device=queries.device)
+    indices = torch.empty((q, k), dtype=torch.int64, device=queries.device)
+    with torch.cuda.device(queries.device):
+        check(lib.b2e_topk_ip(queries.data_ptr(), q, corpus.data_ptr(), dtype_code(corpus.dtype), n, h, k,
+                              scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
+    return scores, indices
 
 
 def layernorm(

@@ -22,6 +22,7 @@
 #include "gemm2.cuh"
 #include "mistral_ops.cuh"
 #include "rowops.cuh"
+#include "topk.cuh"
 
 using namespace b2e;
 
@@ -1355,6 +1356,76 @@ int b2e_attention_causal_d128(const void* qkv, const int64_t* mask, void* ctx, i
   if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
   return launch_attention_causal_d128(qkv, g_attn_scratch, ctx, B, S, heads, kv_heads, window,
                                       info.sms, st);
+}
+
+// ---- exact inner-product top-k (retrieval query path)
+extern "C++" {
+namespace {
+struct TopkScratch {
+  float* score = nullptr;
+  int64_t* index = nullptr;
+  size_t cap = 0;
+  int ensure(size_t elems) {
+    if (elems > cap) {
+      cudaFree(score); cudaFree(index);
+      score = nullptr; index = nullptr; cap = 0;
+      CUDA_TRY(cudaMalloc(&score, elems * sizeof(float)));
+      CUDA_TRY(cudaMalloc(&index, elems * sizeof(int64_t)));
+      cap = elems;
+    }
+    return B2E_OK;
+  }
+};
+thread_local TopkScratch g_topk_scratch;
+
+template <typename T>
+int launch_topk(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
+                int64_t* out_index, int sms, cudaStream_t st) {
+  // queries per pass: bounded by TOPK_QT and by ~160 KiB of shared memory for the query tile
+  int qt = TOPK_QT;
+  while (qt > 1 && (size_t)qt * H * 4 > 160 * 1024) qt >>= 1;
+  const long long rows_per_cta = (TOPK_THREADS / 32) * TOPK_ROWS;
+  long long want = (N + rows_per_cta - 1) / rows_per_cta;
+  const int grid = (int)(want < (long long)2 * sms ? (want > 0 ? want : 1) : (long long)2 * sms);
+  int rc;
+  if ((rc = g_topk_scratch.ensure((size_t)grid * qt * k))) return rc;
+  auto kern = topk_scan_kernel<T>;
+  const size_t smem_max = (size_t)qt * H * 4 + (size_t)qt * k * 12 + 8 + (size_t)qt * 12;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  for (int q0 = 0; q0 < Q; q0 += qt) {
+    const int nq = (Q - q0 < qt) ? (Q - q0) : qt;
+    const size_t smem = (size_t)nq * H * 4 + (size_t)nq * k * 12 + 8 + (size_t)nq * 12;
+    kern<<<grid, TOPK_THREADS, smem, st>>>(queries + (size_t)q0 * H, corpus, nq, (long long)N, H, k,
+                                           g_topk_scratch.score, g_topk_scratch.index);
+    topk_merge_kernel<<<nq, TOPK_THREADS, 0, st>>>(g_topk_scratch.score, g_topk_scratch.index, grid, nq,
+                                                   k, out_score + (size_t)q0 * k,
+                                                   out_index + (size_t)q0 * k, k);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtype, int64_t N, int H,
+                int k, float* out_scores, int64_t* out_indices, void* stream) {
+  if (!queries || !corpus || !out_scores || !out_indices) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (Q <= 0 || N <= 0) return fail(B2E_ERR_INVALID, "topk: empty problem Q=%d N=%lld", Q, (long long)N);
+  if (k <= 0 || k > TOPK_MAX_K) return fail(B2E_ERR_INVALID, "topk: k=%d must be in [1, %d]", k, TOPK_MAX_K);
+  const int hq = (corpus_dtype == B2E_DTYPE_BF16) ? 256 : 128;   // one 16-byte vector per lane
+  if (H % hq != 0 || H > 8192)
+    return fail(B2E_ERR_INVALID, "topk: H=%d must be a multiple of %d (<= 8192)", H, hq);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (corpus_dtype) {
+    case B2E_DTYPE_F32:
+      return launch_topk<float>(queries, Q, (const float*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
+    case B2E_DTYPE_BF16:
+      return launch_topk<bf16>(queries, Q, (const bf16*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
+  }
+  return fail(B2E_ERR_INVALID, "topk: corpus dtype %d (F32 or BF16)", corpus_dtype);
 }
 
 int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* out, int rows, int H,

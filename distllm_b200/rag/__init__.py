@@ -1,0 +1,7 @@
+"""Retrieval query path on the native kernels."""
+
+from distllm_b200.rag.search import ExactIndex
+from distllm_b200.rag.search import ExactIndexConfig
+from distllm_b200.rag.search import Retriever
+
+__all__ = ['ExactIndex', 'ExactIndexConfig', 'Retriever']

@@ -20,6 +20,7 @@
  *   b2e_pool_last_token     distllm/embed/poolers/last_token.py:12-39
  *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
  *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
+ *   b2e_topk_ip             distllm/rag/search.py:280-336 (exact float32 search of the query path)
  *   b2e_gemm_bf16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
  *                           blocks, exported so the parity tests can pin each kernel separately.
  */
@@ -137,6 +138,13 @@ int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx,
  * and (window == 0 or i - j < window). */
 int b2e_attention_causal_d128(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
                               int heads, int kv_heads, int window, void* stream);
+/* Exact inner-product top-k over a device-resident embedding matrix (the retrieval query path,
+ * distllm/rag/search.py:280-336: faiss IndexFlatIP through semantic_search_faiss, float32/exact).
+ * queries [Q,H] f32, corpus [N,H] F32 or BF16 (both row-major on the device), 1 <= k <= 256,
+ * H % 128 == 0.  out_scores / out_indices are [Q,k], sorted by descending score (ties: ascending
+ * index); when N < k the tail is filled with -inf / -1. */
+int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtype, int64_t N, int H,
+                int k, float* out_scores, int64_t* out_indices, void* stream);
 int b2e_layernorm(const void* in_bf16, const float* gamma, const float* beta, void* out, int rows,
                   int H, float eps, int out_dtype, void* stream);
 

@@ -307,3 +307,49 @@ def test_attention_causal_d128_many_items_and_rescale(dev):
     sel = alive & mask.bool().view(-1)
     assert torch.isfinite(ctx.float()).all()
     torch.testing.assert_close(ctx.float()[sel], ref[sel], rtol=3e-2, atol=2e-2)
+
+
+# ---------------------------------------------------------------------------- exact inner-product top-k
+@pytest.mark.parametrize('q,n,h,k', [(1, 1000, 768, 10), (7, 5000, 768, 100), (16, 20000, 768, 5),
+                                     (33, 3000, 256, 64), (3, 17, 128, 8), (2, 5, 768, 10),
+                                     (5, 40000, 1280, 256), (4, 2000, 4096, 20), (1, 1, 768, 1)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_topk_inner_product_matches_oracle(dev, q, n, h, k, dtype):
+    from oracle import search as osearch
+
+    g = torch.Generator(device=dev).manual_seed(q * 31 + n + k)
+    if dtype == torch.bfloat16 and h % 256:
+        with pytest.raises(nv.NativeError, match='multiple of 256'):
+            nv.topk_ip(torch.zeros(q, h, device=dev), torch.zeros(n, h, device=dev, dtype=dtype), k)
+        return
+    corpus = torch.randn(n, h, device=dev, generator=g)
+    corpus = corpus / corpus.norm(dim=1, keepdim=True)
+    queries = torch.randn(q, h, device=dev, generator=g)
+    queries = queries / queries.norm(dim=1, keepdim=True)
+    corpus = corpus.to(dtype).contiguous()
+    scores, idx = nv.topk_ip(queries, corpus, k)
+    ref_s, ref_i = osearch.topk_inner_product(queries.cpu().numpy(), corpus.float().cpu().numpy(), k)
+    kk = ref_s.shape[1]
+    got_s, got_i = scores.cpu().numpy(), idx.cpu().numpy()
+    # scores: fp32 dot products in a different summation order
+    np.testing.assert_allclose(got_s[:, :kk], ref_s, rtol=0, atol=2e-5)
+    assert (np.diff(got_s[:, :kk], axis=1) <= 0).all()
+    if kk < k:   # fewer rows than k: the tail is marked empty
+        assert (got_i[:, kk:] == -1).all() and np.isinf(got_s[:, kk:]).all()
+    # indices: identical wherever the oracle's neighbouring scores are not within rounding of each other
+    full = queries.cpu().numpy().astype(np.float64) @ corpus.float().cpu().numpy().astype(np.float64).T
+    for r in range(q):
+        assert len(set(got_i[r, :kk].tolist())) == kk
+        np.testing.assert_allclose(full[r, got_i[r, :kk]], ref_s[r], rtol=0, atol=2e-5)
+        clear = np.abs(np.diff(ref_s[r])) > 1e-4
+        stable = np.concatenate([[True], clear]) & np.concatenate([clear, [True]])
+        assert (got_i[r, :kk][stable] == ref_i[r][stable]).all()
+
+
+def test_topk_rejects_bad_arguments(dev):
+    c = torch.zeros(10, 768, device=dev)
+    qq = torch.zeros(2, 768, device=dev)
+    with pytest.raises(nv.NativeError, match='k=300'):
+        nv.topk_ip(qq, c, 300)
+    with pytest.raises(nv.NativeError, match='H=100'):
+        nv.topk_ip(torch.zeros(2, 100, device=dev), torch.zeros(10, 100, device=dev), 3)

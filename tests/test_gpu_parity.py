@@ -446,3 +446,52 @@ def test_mistral_long_sequence_properties():
         assert cos.min() > 1 - 1e-5, cos
     finally:
         native.close()
+
+
+# ---------------------------------------------------------------------------------- retrieval query path
+def test_retriever_query_path_end_to_end(tmp_path, tiny_bert, tiny_native):
+    """Retriever.search through the plugin surface (tokenise -> native encode -> mean pool -> normalise ->
+    exact top-k on the device) vs the oracle forward + numpy search on the same corpus."""
+    from transformers import BertTokenizerFast
+
+    from distllm_b200.rag import ExactIndex
+    from distllm_b200.rag import Retriever
+    from oracle import search as osearch
+    from oracle.make_golden import TINY
+
+    cfg, sd = tiny_bert
+    words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
+    (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
+    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok.model_max_length = cfg.max_position_embeddings
+    encoder = AutoEncoder.from_native(tiny_native, tokenizer=tok)
+    pooler = get_pooler({'name': 'mean'})
+    rng = np.random.default_rng(5)
+    corpus = rng.standard_normal((3000, cfg.hidden_size)).astype(np.float32)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    retriever = Retriever(encoder, pooler, ExactIndex(corpus), batch_size=4)
+    queries = [' '.join(rng.choice(words, size=n)) for n in (5, 30, 12, 3, 50, 8, 20)]
+    results, q_emb = retriever.search(queries, top_k=7)
+    assert q_emb.shape == (7, cfg.hidden_size) and q_emb.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(q_emb, axis=1), 1.0, rtol=1e-5)
+    # the query embeddings against the oracle forward, same batching (sorted by length, batches of 4)
+    order = sorted(range(len(queries)), key=lambda i: len(queries[i]))
+    ref_rows = {}
+    for b0 in range(0, len(order), 4):
+        ids = [order[i] for i in range(b0, min(b0 + 4, len(order)))]
+        enc = tok([queries[i] for i in ids], padding=True, truncation=True, return_tensors='pt')
+        hidden = obert.bert_forward(sd, cfg, enc['input_ids'], enc['attention_mask'], enc['token_type_ids'])
+        pooled = opool.average_pool(hidden, enc['attention_mask'].clone()).numpy()
+        for i, row in zip(ids, osearch.normalize_l2(pooled)):
+            ref_rows[i] = row
+    ref_q = np.stack([ref_rows[i] for i in range(len(queries))])
+    assert cosine_rows(q_emb, ref_q).min() > 1 - COS_TOL
+    # the search itself: exact on the embeddings the retriever produced
+    ref_s, ref_i = osearch.topk_inner_product(q_emb, corpus, 7)
+    np.testing.assert_allclose(np.array(results.total_scores), ref_s, rtol=0, atol=2e-5)
+    assert np.array(results.total_indices).tolist() == ref_i.tolist()
+    # a precomputed embedding and a score threshold
+    res2, _ = retriever.search(query_embedding=q_emb[:2], top_k=7, score_threshold=float(ref_s[0, 3]))
+    assert res2.total_indices[0] == ref_i[0, :4].tolist()
+    with pytest.raises(ValueError, match='at least one of'):
+        retriever.search()

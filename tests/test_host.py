@@ -399,3 +399,46 @@ def test_columnar_writer_falls_back_on_untypeable_metadata(tmp_path):
     else:
         w.write(tmp_path / 'x', result)
         assert Dataset.load_from_disk(tmp_path / 'x').to_dict() == want.to_dict()
+
+
+# ------------------------------------------------------------------------------ retrieval (host side)
+def test_search_oracle_and_score_filter():
+    from datasets.search import BatchedSearchResults
+
+    from distllm_b200.rag.search import ExactIndex
+    from distllm_b200.rag.search import filter_search_by_score
+    from oracle import search as osearch
+
+    rng = np.random.default_rng(2)
+    q = rng.standard_normal((4, 16)).astype(np.float32)
+    c = rng.standard_normal((50, 16)).astype(np.float32)
+    c[7] = c[3]                                  # a tie: the lower index comes first
+    s, i = osearch.topk_inner_product(q, c, 10)
+    full = q @ c.T
+    for r in range(4):
+        assert np.allclose(s[r], np.sort(full[r])[::-1][:10], rtol=1e-6)
+        assert set(i[r]) == set(np.argsort(-full[r], kind='stable')[:10])
+        pos = {int(v): p for p, v in enumerate(i[r])}
+        if 3 in pos and 7 in pos:
+            assert pos[3] < pos[7]
+    s2, i2 = osearch.topk_inner_product(q, c[:3], 10)
+    assert s2.shape == (4, 3) and i2.shape == (4, 3)
+    # normalisation: faiss.normalize_L2 semantics, zero rows stay zero, in place
+    x = np.array([[3.0, 4.0], [0.0, 0.0]], dtype=np.float32)
+    assert ExactIndex.transform(x) is x and np.allclose(x, [[0.6, 0.8], [0.0, 0.0]])
+    assert np.allclose(osearch.normalize_l2(np.array([[3.0, 4.0]])), [[0.6, 0.8]])
+    res = BatchedSearchResults(total_scores=[[0.9, 0.5, 0.1], [0.2]], total_indices=[[4, 2, 9], [1]])
+    assert filter_search_by_score(res, 0.0) is res
+    kept = filter_search_by_score(res, 0.5)
+    assert kept.total_indices == [[4, 2], []] and kept.total_scores == [[0.9, 0.5], []]
+
+
+@pytest.mark.skipif(__import__('torch').cuda.is_available(), reason='CPU-only behaviour')
+def test_exact_index_has_no_cpu_fallback():
+    from distllm_b200 import _native
+    from distllm_b200.rag.search import ExactIndex
+
+    with pytest.raises(_native.NativeError, match='no CPU fallback'):
+        ExactIndex(np.zeros((4, 128), np.float32))
+    with pytest.raises(ValueError, match='embedding matrix or a dataset_dir'):
+        ExactIndex()
