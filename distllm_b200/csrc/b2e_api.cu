@@ -1378,18 +1378,18 @@ struct TopkScratch {
 };
 thread_local TopkScratch g_topk_scratch;
 
-template <typename T>
-int launch_topk(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
-                int64_t* out_index, int sms, cudaStream_t st) {
-  // queries per pass: bounded by TOPK_QT and by ~160 KiB of shared memory for the query tile
-  int qt = TOPK_QT;
+template <typename T, int QT, int ROWS, int VMAX>
+int launch_topk_cfg(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
+                    int64_t* out_index, int sms, cudaStream_t st) {
+  // queries per pass: bounded by QT and by ~160 KiB of shared memory for the query tile
+  int qt = QT;
   while (qt > 1 && (size_t)qt * H * 4 > 160 * 1024) qt >>= 1;
-  const long long rows_per_cta = (TOPK_THREADS / 32) * TOPK_ROWS;
-  long long want = (N + rows_per_cta - 1) / rows_per_cta;
+  const long long rows_per_cta = (TOPK_THREADS / 32) * ROWS;
+  const long long want = (N + rows_per_cta - 1) / rows_per_cta;
   const int grid = (int)(want < (long long)2 * sms ? (want > 0 ? want : 1) : (long long)2 * sms);
   int rc;
   if ((rc = g_topk_scratch.ensure((size_t)grid * qt * k))) return rc;
-  auto kern = topk_scan_kernel<T>;
+  auto kern = topk_scan_kernel<T, QT, ROWS, VMAX>;
   const size_t smem_max = (size_t)qt * H * 4 + (size_t)qt * k * 12 + 8 + (size_t)qt * 12;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   for (int q0 = 0; q0 < Q; q0 += qt) {
@@ -1403,6 +1403,15 @@ int launch_topk(const float* queries, int Q, const T* corpus, int64_t N, int H, 
   }
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
+}
+
+// one to four queries: the narrow, deeper scan; more: 16 queries per pass
+template <typename T, int VWIDE, int VNARROW>
+int launch_topk(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
+                int64_t* out_index, int sms, cudaStream_t st) {
+  if (Q <= 4)
+    return launch_topk_cfg<T, 4, 8, VNARROW>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st);
+  return launch_topk_cfg<T, TOPK_QT, 4, VWIDE>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st);
 }
 }  // namespace
 }  // extern "C++"
@@ -1421,9 +1430,9 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
   cudaStream_t st = (cudaStream_t)stream;
   switch (corpus_dtype) {
     case B2E_DTYPE_F32:
-      return launch_topk<float>(queries, Q, (const float*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
+      return launch_topk<float, 6, 3>(queries, Q, (const float*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
     case B2E_DTYPE_BF16:
-      return launch_topk<bf16>(queries, Q, (const bf16*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
+      return launch_topk<bf16, 3, 2>(queries, Q, (const bf16*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
   }
   return fail(B2E_ERR_INVALID, "topk: corpus dtype %d (F32 or BF16)", corpus_dtype);
 }

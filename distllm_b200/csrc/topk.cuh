@@ -14,8 +14,10 @@
 
 namespace b2e {
 
-constexpr int TOPK_QT = 16;        // queries per pass over the corpus
-constexpr int TOPK_ROWS = 4;       // corpus rows a warp holds at once
+constexpr int TOPK_QT = 16;        // queries per pass over the corpus (wide variant)
+// Two shapes of the scan: <QT=16, ROWS=4> shares one pass among up to 16 queries; <QT=4, ROWS=8> serves
+// the usual one-to-four-query search with twice the rows (bytes) in flight per warp and a 32-value
+// reduction instead of a 64-value one.  QT * ROWS is 32 or 64: the transposing butterfly needs it.
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_MAX_K = 256;
 
@@ -78,7 +80,6 @@ __device__ __noinline__ void topk_insert(const TopkSet& s, int k, float score, i
 template <typename T> struct TopkVec;
 template <> struct TopkVec<float> {
   static constexpr int E = 4;
-  static constexpr int VMAX = 6;   // vectors per lane and row held in registers at a time (24 elements)
   float4 raw;
   __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ void zero() { raw = make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -89,7 +90,6 @@ template <> struct TopkVec<float> {
 };
 template <> struct TopkVec<bf16> {
   static constexpr int E = 8;
-  static constexpr int VMAX = 3;
   uint4 raw;
   __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
@@ -103,7 +103,7 @@ template <> struct TopkVec<bf16> {
 };
 
 // shared memory: queries [nq][H] f32 | sets: score [nq][k] f32, index [nq][k] i64, kth/kth_pos/lock [nq]
-template <typename T>
+template <typename T, int QT, int ROWS, int VMAX>
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's query tile)
                  const T* __restrict__ corpus,        // [N, H]
@@ -133,14 +133,18 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
   __syncthreads();
 
   constexpr int E = TopkVec<T>::E;
-  constexpr int TOPK_VMAX = TopkVec<T>::VMAX;
+  constexpr int TOPK_VMAX = VMAX;     // 16-byte vectors per lane and row held in registers at a time
+  constexpr int TOPK_ROWS = ROWS;
+  constexpr int VALS = QT * ROWS;
+  constexpr int PER = VALS / 32;      // totals a lane ends up with
+  static_assert(VALS == 32 || VALS == 64, "the butterfly reduces 32 or 64 values per lane");
   const int nv = H / (32 * E);                 // 16-byte vectors per lane and row
   const long long warps_total = static_cast<long long>(gridDim.x) * (TOPK_THREADS / 32);
   const long long gwarp = static_cast<long long>(blockIdx.x) * (TOPK_THREADS / 32) + warp;
   for (long long row0 = gwarp * TOPK_ROWS; row0 < N; row0 += warps_total * TOPK_ROWS) {
-    float acc[TOPK_QT][TOPK_ROWS];
+    float acc[QT][TOPK_ROWS];
 #pragma unroll
-    for (int q = 0; q < TOPK_QT; ++q)
+    for (int q = 0; q < QT; ++q)
 #pragma unroll
       for (int r = 0; r < TOPK_ROWS; ++r) acc[q][r] = 0.0f;
     for (int v0 = 0; v0 < nv; v0 += TOPK_VMAX) {
@@ -156,7 +160,7 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
         }
       }
 #pragma unroll
-      for (int q = 0; q < TOPK_QT; ++q) {
+      for (int q = 0; q < QT; ++q) {
         if (q < nq) {
 #pragma unroll
           for (int v = 0; v < TOPK_VMAX; ++v) {
@@ -169,15 +173,15 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
         }
       }
     }
-    // 64 partial sums per lane -> totals by a transposing butterfly (62 shuffles instead of 320): lane l
-    // ends up with the totals of value indices 2l and 2l+1, i.e. query l/2, rows 2(l%2) and 2(l%2)+1
-    float v[TOPK_QT * TOPK_ROWS];
+    // VALS partial sums per lane -> totals by a transposing butterfly (VALS - PER shuffles instead of
+    // 5 * VALS): lane l ends up with the totals of value indices l * PER + j, index = query * ROWS + row
+    float v[VALS];
 #pragma unroll
-    for (int q = 0; q < TOPK_QT; ++q)
+    for (int q = 0; q < QT; ++q)
 #pragma unroll
       for (int r = 0; r < TOPK_ROWS; ++r) v[q * TOPK_ROWS + r] = acc[q][r];
 #pragma unroll
-    for (int half = TOPK_QT * TOPK_ROWS / 2, bit = 16; half >= 2; half >>= 1, bit >>= 1) {
+    for (int half = VALS / 2, bit = 16; half >= PER; half >>= 1, bit >>= 1) {
       const bool upper = (lane & bit) != 0;
 #pragma unroll
       for (int i = 0; i < half; ++i) {
@@ -188,19 +192,19 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
     }
     // the few candidates that beat their query's current k-th score are inserted one by one; the loop
     // body exists once (64 inlined copies of it used to push the kernel out of the instruction cache)
-    const int my_q = lane >> 1;
-    const float th = (my_q < nq) ? *reinterpret_cast<volatile float*>(kth + my_q) : INFINITY;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int my_r = 2 * (lane & 1) + j;
+    for (int j = 0; j < PER; ++j) {
+      const int my_i = lane * PER + j;
+      const int my_q = my_i / TOPK_ROWS, my_r = my_i % TOPK_ROWS;
+      const float th = (my_q < nq) ? *reinterpret_cast<volatile float*>(kth + my_q) : INFINITY;
       const bool cand = (my_q < nq) && (row0 + my_r < N) && (v[j] > th);
       unsigned todo = __ballot_sync(0xffffffffu, cand);
       while (todo != 0) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
         const float sc = __shfl_sync(0xffffffffu, v[j], src);
-        const int q = src >> 1;
-        const int r = 2 * (src & 1) + j;
+        const int i = src * PER + j;
+        const int q = i / TOPK_ROWS, r = i % TOPK_ROWS;
         const TopkSet set{set_score + q * k, set_index + q * k, kth + q, kth_pos + q, lock + q};
         topk_insert(set, k, sc, row0 + r, lane);
       }
