@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "attention.cuh"
@@ -143,6 +144,22 @@ int current_device_info(DeviceInfo* info) {
   return rc;
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory, once per (kernel, device): the attribute belongs
+// to the device's context, and a process may drive more than one device over its lifetime.
+template <typename Kern>
+int ensure_smem_attr(Kern kern, int bytes) {
+  // keyed by the kernel's ADDRESS (kernels with equal signatures share one C++ type) and the device
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const void* key = reinterpret_cast<const void*>(kern);
+  for (const auto& d : done)
+    if (d.first == key && d.second == dev) return B2E_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(key, dev);
+  return B2E_OK;
+}
+
 // ---------------------------------------------------------------- launches
 template <int BN, int STAGES, int EPI>
 int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
@@ -150,11 +167,9 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
                     cudaStream_t st) {
   using Cfg = GemmCfg<BN, STAGES>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
-    attr_done = true;
+  {
+    const int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES);
+    if (arc) return arc;
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
   const int grid = tiles < sms ? tiles : sms;
@@ -231,11 +246,9 @@ int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                      cudaStream_t st) {
   using Cfg = Gemm2Cfg<STAGES>;
   auto kern = gemm2_bf16_pair_kernel<STAGES, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
-    attr_done = true;
+  {
+    const int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES);
+    if (arc) return arc;
   }
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
   int grid = 2 * tiles;
@@ -270,11 +283,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
 
 int launch_attention_v1(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
                         int heads, float* dbg, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(attention_d64_tcgen05_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    attr_done = true;
+  {
+    const int arc = ensure_smem_attr(attention_d64_tcgen05_kernel, ATT_SMEM_BYTES);
+    if (arc) return arc;
   }
   dim3 grid((S + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
@@ -291,7 +302,15 @@ struct AttnScratch {
   int* kv_chunks = nullptr;  // [B]
   size_t cap_bias = 0, cap_b = 0;
   uint64_t gen = 0;   // bumped on every reallocation
+  int device = -1;    // the buffers live on this device; a call from another one starts over
   int ensure(int B, int S_pad) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != device) {
+      release();
+      device = dev;
+      ++gen;
+    }
     if ((size_t)B * S_pad > cap_bias || (size_t)B > cap_b) ++gen;
     if ((size_t)B * S_pad > cap_bias) {
       if (bias) cudaFree(bias);
@@ -352,11 +371,9 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   }
   if (mode == 2 || mode == 4) {
     if (S > AT2_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "attention v2: S=%d > %d", S, AT2_MAX_S);
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(cudaFuncSetAttribute(attention2_d64_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
-      attr_done = true;
+    {
+      const int arc = ensure_smem_attr(attention2_d64_kernel, AT2_SMEM_BYTES);
+      if (arc) return arc;
     }
     dim3 grid(heads, B);
     attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
@@ -365,11 +382,9 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
   }
-  static bool attr3_done = false;
-  if (!attr3_done) {
-    CUDA_TRY(cudaFuncSetAttribute(attention3_d64_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM_BYTES));
-    attr3_done = true;
+  {
+    const int arc = ensure_smem_attr(attention3_d64_kernel, AT3_SMEM_BYTES);
+    if (arc) return arc;
   }
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
@@ -387,11 +402,9 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
 // with columns  q heads | k heads | v heads;  sc must have been prepared for (mask, B, S).
 int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, int B, int S, int heads,
                                  int kv_heads, int window, int sms, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(attention4_d128_causal_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM_BYTES));
-    attr_done = true;
+  {
+    const int arc = ensure_smem_attr(attention4_d128_causal_kernel, AT4_SMEM_BYTES);
+    if (arc) return arc;
   }
   const uint64_t ld = (uint64_t)(heads + 2 * kv_heads) * AT4_D;
   CUtensorMap tq, tkv, tctx;
@@ -441,6 +454,13 @@ struct PoolScratch {
   uint64_t gen = 0;   // bumped on every reallocation (captured CUDA graphs hold these pointers)
 
   int ensure(int B, int S, size_t part_elems) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != device) {   // buffers of another device: start over on this one
+      release();
+      device = dev;
+      ++gen;
+    }
     if ((size_t)B > cap_b || (size_t)S > cap_s || (size_t)B * S > cap_bs || part_elems > cap_part) ++gen;
     if ((size_t)B > cap_b) {
       if (seq_len) cudaFree(seq_len);
@@ -611,6 +631,9 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
 int validate_batch(const B2EEncoder* e, int B, int S) {
   if (!e) return fail(B2E_ERR_INVALID, "null encoder handle");
   if (B <= 0 || S <= 0) return fail(B2E_ERR_INVALID, "empty batch B=%d S=%d", B, S);
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != e->device)
+    return fail(B2E_ERR_INVALID, "encoder lives on device %d but device %d is current", e->device, cur);
   if (S > e->desc.max_pos)
     return fail(B2E_ERR_INVALID, "S=%d exceeds max_position_embeddings=%d", S, e->desc.max_pos);
   if (!attention_supports(S))
@@ -1112,8 +1135,8 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
   if (n_rows == 0) return B2E_OK;
   if (!ids || !mask || !out_host) return fail(B2E_ERR_INVALID, "null host pointer");
   int rc;
+  CUDA_TRY(cudaSetDevice(e->device));   // host entry point: it owns its device context and stream
   if ((rc = validate_batch(e, batch, S))) return rc;
-  CUDA_TRY(cudaSetDevice(e->device));
   if (!e->own_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = e->own_stream;
   const int H = e->desc.hidden;
@@ -1365,7 +1388,15 @@ struct TopkScratch {
   float* score = nullptr;
   int64_t* index = nullptr;
   size_t cap = 0;
+  int device = -1;
   int ensure(size_t elems) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != device) {
+      cudaFree(score); cudaFree(index);
+      score = nullptr; index = nullptr; cap = 0;
+      device = dev;
+    }
     if (elems > cap) {
       cudaFree(score); cudaFree(index);
       score = nullptr; index = nullptr; cap = 0;
@@ -1391,6 +1422,7 @@ int launch_topk_cfg(const float* queries, int Q, const T* corpus, int64_t N, int
   if ((rc = g_topk_scratch.ensure((size_t)grid * qt * k))) return rc;
   auto kern = topk_scan_kernel<T, QT, ROWS, VMAX>;
   const size_t smem_max = (size_t)qt * H * 4 + (size_t)qt * k * 12 + 8 + (size_t)qt * 12;
+  // (k varies between calls: always set the attribute to this call's worst case)
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   for (int q0 = 0; q0 < Q; q0 += qt) {
     const int nq = (Q - q0 < qt) ? (Q - q0) : qt;
