@@ -193,7 +193,6 @@ def attention_d64(
     batch: int,
     seq: int,
     heads: int,
-    debug_scores: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """qkv [B*S, 3*heads*64] bf16 -> context [B*S, heads*64] bf16."""
     lib = load()
@@ -201,7 +200,7 @@ def attention_d64(
     ctx = torch.zeros((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_d64(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch,
-                                    seq, heads, _ptr(debug_scores), stream_ptr(qkv.device)))
+                                    seq, heads, None, stream_ptr(qkv.device)))
     return ctx
 
 

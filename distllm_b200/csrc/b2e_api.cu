@@ -14,8 +14,6 @@
 #include <utility>
 #include <vector>
 
-#include "attention.cuh"
-#include "attention2.cuh"
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "common.cuh"
@@ -281,20 +279,6 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   return launch_gemm_bn<128, 6>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
 }
 
-int launch_attention_v1(const CUtensorMap& tqkv, const int64_t* mask, void* ctx, int B, int S,
-                        int heads, float* dbg, cudaStream_t st) {
-  {
-    const int arc = ensure_smem_attr(attention_d64_tcgen05_kernel, ATT_SMEM_BYTES);
-    if (arc) return arc;
-  }
-  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, heads, B);
-  const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  attention_d64_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(
-      tqkv, mask, static_cast<bf16*>(ctx), S, heads * ATT_D, scale_log2e, dbg);
-  CUDA_TRY(cudaGetLastError());
-  return B2E_OK;
-}
-
 // Per-forward attention inputs derived from the mask (attention3.cuh): additive key bias rows and
 // the number of 64-key chunks that hold an attended key.
 struct AttnScratch {
@@ -334,23 +318,7 @@ struct AttnScratch {
 
 inline int attn_s_pad(int S) { return (S + AT3_KC - 1) / AT3_KC * AT3_KC; }
 
-// B2E_ATTENTION selects the kernel generation: default v3 (streaming, any S); v2 / v2clock
-// (K/V resident, S <= 512), v1 (first serialized kernel, S <= 512; also used for score dumps).
-inline int attention_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("B2E_ATTENTION");
-    mode = 3;
-    if (e && strcmp(e, "v1") == 0) mode = 1;
-    if (e && strcmp(e, "v2") == 0) mode = 2;
-    if (e && strcmp(e, "v2clock") == 0) mode = 4;
-  }
-  return mode;
-}
-inline bool attention_supports(int S) { return attention_mode() == 3 || S <= ATT_MAX_S; }
-
 int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaStream_t st) {
-  if (attention_mode() != 3) return B2E_OK;
   int rc;
   const int S_pad = attn_s_pad(S);
   if ((rc = sc.ensure(B, S_pad))) return rc;
@@ -359,29 +327,10 @@ int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaSt
   return B2E_OK;
 }
 
-// tq: [T,3H] box 64x128, tkv: [T,3H] box 64x64 (v3 only).  `sc` must have been prepared for `mask`.
-int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
-                     const int64_t* mask, void* ctx, int B, int S, int heads, float* dbg, int sms,
-                     cudaStream_t st) {
-  const int mode = attention_mode();
+// tq: [T,3H] box 64x128, tkv: [T,3H] box 64x64.  `sc` must have been prepared for this batch's mask.
+int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc, void* ctx,
+                     int B, int S, int heads, int sms, cudaStream_t st) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  if (mode == 1 || (dbg && mode != 4)) {
-    if (S > ATT_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "attention v1: S=%d > %d", S, ATT_MAX_S);
-    return launch_attention_v1(tq, mask, ctx, B, S, heads, dbg, st);
-  }
-  if (mode == 2 || mode == 4) {
-    if (S > AT2_MAX_S) return fail(B2E_ERR_UNSUPPORTED, "attention v2: S=%d > %d", S, AT2_MAX_S);
-    {
-      const int arc = ensure_smem_attr(attention2_d64_kernel, AT2_SMEM_BYTES);
-      if (arc) return arc;
-    }
-    dim3 grid(heads, B);
-    attention2_d64_kernel<<<grid, AT2_THREADS, AT2_SMEM_BYTES, st>>>(
-        tq, mask, static_cast<bf16*>(ctx), S, heads * AT2_D, scale_log2e,
-        mode == 4 ? reinterpret_cast<long long*>(dbg) : nullptr);
-    CUDA_TRY(cudaGetLastError());
-    return B2E_OK;
-  }
   {
     const int arc = ensure_smem_attr(attention3_d64_kernel, AT3_SMEM_BYTES);
     if (arc) return arc;
@@ -636,8 +585,6 @@ int validate_batch(const B2EEncoder* e, int B, int S) {
     return fail(B2E_ERR_INVALID, "encoder lives on device %d but device %d is current", e->device, cur);
   if (S > e->desc.max_pos)
     return fail(B2E_ERR_INVALID, "S=%d exceeds max_position_embeddings=%d", S, e->desc.max_pos);
-  if (!attention_supports(S))
-    return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d needs the streaming attention kernel", S, ATT_MAX_S);
   return B2E_OK;
 }
 
@@ -666,8 +613,7 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->L(l, 1), nullptr, M,
                           3 * H, H, B2E_EPI_BIAS, e->sms, st)))
       return rc;
-    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, mask, e->ctx, B, S, d.heads, nullptr,
-                               e->sms, st)))
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st)))
       return rc;
     // the residual add rides on the LayerNorm's coalesced reads, not on the GEMM epilogue
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), nullptr, M, H, H,
@@ -725,8 +671,7 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
       return rc;
     rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
                                                                     M, S, d.heads);
-    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, mask, e->ctx, B, S, d.heads, nullptr,
-                               e->sms, st)))
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st)))
       return rc;
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->E(l, 5), nullptr, M, H, H,
                           B2E_EPI_BIAS, e->sms, st)))
@@ -849,8 +794,6 @@ namespace {
 // Mistral family: head_dim 128, grouped-query heads, SwiGLU MLP, no biases.
 int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_weights, int device,
                    B2EEncoder** out) {
-  if (attention_mode() != 3)
-    return fail(B2E_ERR_UNSUPPORTED, "Mistral needs the streaming attention kernels (unset B2E_ATTENTION)");
   if (desc->head_dim != 128 || desc->kv_heads <= 0 || desc->heads % desc->kv_heads != 0)
     return fail(B2E_ERR_UNSUPPORTED, "need head_dim 128 and heads %% kv_heads == 0 (got %d/%d x %d)",
                 desc->heads, desc->kv_heads, desc->head_dim);
@@ -911,8 +854,6 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
   if (desc->arch == B2E_ARCH_MISTRAL) return create_mistral(desc, weights, n_weights, device, out);
   if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
     return fail(B2E_ERR_UNSUPPORTED, "arch %d: unknown architecture", desc->arch);
-  if (desc->arch == B2E_ARCH_ESM2 && attention_mode() != 3)
-    return fail(B2E_ERR_UNSUPPORTED, "ESM-2 needs the streaming attention kernel (unset B2E_ATTENTION)");
   if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
     return fail(B2E_ERR_UNSUPPORTED, "need head_dim 64 and heads*64 == hidden (got %d x %d, H=%d)",
                 desc->heads, desc->head_dim, desc->hidden);
@@ -1351,17 +1292,16 @@ int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, in
                       float* dbg, void* stream) {
   if (!qkv || !mask || !ctx) return fail(B2E_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || S <= 0 || heads <= 0) return fail(B2E_ERR_INVALID, "empty attention problem");
-  if (!attention_supports(S) || (dbg && S > ATT_MAX_S))
-    return fail(B2E_ERR_UNSUPPORTED, "S=%d > %d needs the streaming attention kernel", S, ATT_MAX_S);
+  if (dbg) return fail(B2E_ERR_UNSUPPORTED, "the score dump of the first attention kernel is gone: pass NULL");
   int rc;
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tq, tkv;
-  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * ATT_D, AT3_KC))) return rc;
+  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, AT3_KC))) return rc;
   if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
-  return launch_attention(tq, tkv, g_attn_scratch, mask, ctx, B, S, heads, dbg, info.sms, st);
+  return launch_attention(tq, tkv, g_attn_scratch, ctx, B, S, heads, info.sms, st);
 }
 
 int b2e_attention_causal_d128(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int heads,
@@ -1370,8 +1310,6 @@ int b2e_attention_causal_d128(const void* qkv, const int64_t* mask, void* ctx, i
   if (B <= 0 || S <= 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads != 0 || window < 0)
     return fail(B2E_ERR_INVALID, "bad causal attention problem B=%d S=%d heads=%d/%d window=%d", B, S,
                 heads, kv_heads, window);
-  if (attention_mode() != 3)
-    return fail(B2E_ERR_UNSUPPORTED, "causal attention needs the streaming kernels (unset B2E_ATTENTION)");
   int rc;
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;

@@ -129,9 +129,9 @@ int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
 /* Building blocks (bf16 row-major): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
 int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epilogue, void* stream);
-/* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; dbg_scores nullable ([128,512] fp32 of CTA 0). */
+/* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; `reserved` must be NULL (it was a debug score dump). */
 int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
-                      int heads, float* dbg_scores, void* stream);
+                      int heads, float* reserved, void* stream);
 /* Causal grouped-query attention, head_dim 128 (Mistral family):
  * qkv [B*S, (heads + 2*kv_heads)*128] with columns q heads | k heads | v heads (rotary already
  * applied) -> ctx [B*S, heads*128].  Key j is visible to query i iff j <= i, attention_mask[b,j] != 0
