@@ -66,6 +66,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int flags = g_gemm2_flags;   // experiment knobs, read once (0 in production)
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
@@ -118,7 +119,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
           mbar_wait(empty_bar + 8u * stage, phase ^ 1u);
           G2_STAMP(0);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-          if (g_gemm2_flags & 4) {   // experiment: no loads, just hand the (stale) stage over
+          if (flags & 4) {   // experiment: no loads, just hand the (stale) stage over
             if (leader) mbar_arrive(full_bar + 8u * stage);
           } else {
             // the peer's complete_tx may reach the leader's barrier before the leader's expect_tx:
@@ -154,7 +155,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
-          if (!(g_gemm2_flags & 2)) {
+          if (!(flags & 2)) {
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k)
               tc_mma_f16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc,
@@ -189,7 +190,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
           (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       if (stamp) G2_STAMP(1);
-      if (g_gemm2_flags & 16) {   // experiment: poll with back-off instead of try_wait's own spin
+      if (flags & 16) {   // experiment: poll with back-off instead of try_wait's own spin
         while (!mbar_test(tfull_bar + 8u * as, aphase)) __nanosleep(256);
       } else {
         mbar_wait(tfull_bar + 8u * as, aphase);
@@ -209,7 +210,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         tmem_ld_wait();
-        if (!(g_gemm2_flags & 1)) {
+        if (!(flags & 1)) {
           const int sidx = local & 1;
           gemm_swiglu_chunk(g, u, staging + sidx * GEMM_STAGING_BYTES, lane);
           fence_proxy_async_smem();
@@ -229,7 +230,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           tmem_ld_wait();
-          if (g_gemm2_flags & 1) continue;
+          if (flags & 1) continue;
           gemm_epilogue_chunk_gbias<EPI>(acc, bias != nullptr ? bias + gcol0 + c * 64 : nullptr,
                                          resid_row + c * 64, row_ok, staging + c * GEMM_STAGING_BYTES,
                                          lane);
