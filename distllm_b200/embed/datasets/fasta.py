@@ -10,6 +10,7 @@ from typing import Union
 from torch.utils.data import DataLoader
 
 from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import LoaderConfig
 from distllm_b200.embed.datasets.utils import make_dataloader
 from distllm_b200.embed.encoders.base import Encoder
 from distllm_b200.utils import BaseConfig
@@ -40,11 +41,8 @@ def write_fasta(sequences: Sequence | list[Sequence], fasta_file: PathLike, mode
         handle.writelines(f'>{s.tag}\n{s.sequence}\n' for s in items)
 
 
-class FastaDatasetConfig(BaseConfig):
+class FastaDatasetConfig(LoaderConfig):
     name: Literal['fasta'] = 'fasta'  # type: ignore[assignment]
-    num_data_workers: int = 4
-    batch_size: int = 8
-    pin_memory: bool = True
 
 
 class FastaDataset:

@@ -9,21 +9,14 @@ from typing import Literal
 from torch.utils.data import DataLoader
 
 from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import LoaderConfig
 from distllm_b200.embed.datasets.utils import make_dataloader
 from distllm_b200.embed.encoders.base import Encoder
-from distllm_b200.utils import BaseConfig
 
 
-class JsonlDatasetConfig(BaseConfig):
+class JsonlDatasetConfig(LoaderConfig):
     name: Literal['jsonl'] = 'jsonl'  # type: ignore[assignment]
-    # The name of the text field in the jsonl file
-    text_field: str = 'text'
-    # Number of data workers for batching.
-    num_data_workers: int = 4
-    # Inference batch size.
-    batch_size: int = 8
-    # Whether to pin memory for the dataloader.
-    pin_memory: bool = True
+    text_field: str = 'text'   # which key of each json row holds the text
 
 
 def read_jsonl(path: Path) -> list[dict]:

@@ -19,6 +19,7 @@ from torch.utils.data import DataLoader
 
 from distllm_b200.embed.datasets.jsonl import read_jsonl
 from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import LoaderConfig
 from distllm_b200.embed.datasets.utils import make_dataloader
 from distllm_b200.embed.encoders.base import Encoder
 from distllm_b200.utils import BaseConfig
@@ -70,16 +71,9 @@ def sentences_to_buffers(split: list[str], buffer_size: int) -> list[str]:
     return [''.join(split[max(0, i - buffer_size) : min(n, i + buffer_size + 1)]) for i in range(n)]
 
 
-class JsonlChunkDatasetConfig(BaseConfig):
+class JsonlChunkDatasetConfig(LoaderConfig):
     name: Literal['jsonl_chunk'] = 'jsonl_chunk'  # type: ignore[assignment]
-    # The name of the text field in the jsonl file
-    text_field: str = 'text'
-    # Number of data workers for batching.
-    num_data_workers: int = 4
-    # Inference batch size.
-    batch_size: int = 8
-    # Whether to pin memory for the dataloader.
-    pin_memory: bool = True
+    text_field: str = 'text'   # which key of each json row holds the text
     min_buffer_length: int = Field(
         default=750,
         description='Buffers with this many characters or fewer are filtered out '

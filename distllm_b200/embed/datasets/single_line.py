@@ -8,18 +8,14 @@ from typing import Literal
 from torch.utils.data import DataLoader
 
 from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import LoaderConfig
 from distllm_b200.embed.datasets.utils import make_dataloader
 from distllm_b200.embed.encoders.base import Encoder
-from distllm_b200.utils import BaseConfig
 
 
-class SequencePerLineDatasetConfig(BaseConfig):
+class SequencePerLineDatasetConfig(LoaderConfig):
     name: Literal['sequence_per_line'] = 'sequence_per_line'  # type: ignore[assignment]
-    # Number of header lines to skip
-    header_lines: int = 1
-    num_data_workers: int = 4
-    batch_size: int = 8
-    pin_memory: bool = True
+    header_lines: int = 1   # lines to skip at the top of the file
 
 
 class SequencePerLineDataset:

@@ -15,6 +15,16 @@ from torch.utils.data import Dataset
 from transformers import BatchEncoding
 from transformers import PreTrainedTokenizer
 
+from distllm_b200.utils import BaseConfig
+
+
+class LoaderConfig(BaseConfig):
+    """DataLoader knobs every dataset config of the reference carries, with its defaults."""
+
+    num_data_workers: int = 4   # DataLoader worker processes (0: tokenise on the main process)
+    batch_size: int = 8         # inference batch size
+    pin_memory: bool = True     # page-locked batches for the H2D copy
+
 
 class InMemoryDataset(Dataset):
     """List of texts with optional per-row metadata."""
