@@ -8,8 +8,9 @@
 // are released by the upper tile's slot without being touched.
 //
 //   warp 9      loader      Q tiles and {K_j, V_j, key-bias_j} ring stages (TMA)
-//   warp 8      MMA issuer  S_j = Q K_j^T (SS, 128x64x16, 8 K-steps over two 64-wide slabs) and
-//                           O += P_j V_j (TS: P from TMEM, V_j as MN-major smem operand, N = 128)
+//   warps 8,10  MMA issuers (one thread per query tile): S_j = Q K_j^T (SS, 128x64x16, 8 K-steps
+//                           over two 64-wide slabs) and O += P_j V_j (TS: P from TMEM, V_j as MN-major
+//                           smem operand, N = 128)
 //   warps 0-3   softmax for query tile A (slot 0)   one row per thread, online softmax in the exp2
 //   warps 4-7   softmax for query tile B (slot 1)   domain with lazy rescale; bf16 P over S's columns
 //
@@ -156,7 +157,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
       tma_prefetch_desc(&tm_ctx);
       for (int i = 0; i < AT4_NST; ++i) {
         mbar_init(kv_full + 8u * i, 1);
-        mbar_init(kv_empty + 8u * i, 1);
+        mbar_init(kv_empty + 8u * i, 2);   // one arrival from each slot's MMA issuer
       }
       for (int i = 0; i < 4; ++i) {
         mbar_init(s_ready + 8u * i, 1);
@@ -238,113 +239,94 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
           cur = nxt;
         }
       }
-    } else if (warp == 8) {
+    } else if (warp == 8 || warp == 10) {
       if (elect_one()) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ MMA issuer of ONE slot
+        // (warp 8: query tile A, warp 10: query tile B).  With head_dim 128 one thread driving both
+        // slots spent ~600 clk per Q K^T or P V event (polls, 8 or 4 MMAs, commits), four events per pair
+        // of chunks -- more than the softmax it feeds.  Each slot's thread walks the item's ring chunks in
+        // order: chunks outside its tile's range only get their ring arrival, the others Q K^T / P V.
+        const int slot = (warp == 8) ? 0 : 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(128, AT4_KC, 0, 0);
         constexpr uint32_t idesc_o = make_idesc_bf16(128, AT4_D, 0, 1);  // B (= V) is MN-major
+        const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
+        const uint32_t q_addr = sb + AT4_SMEM_Q + slot * AT4_QTILE;
         uint32_t chunk_base = 0;   // ring position of this item's first chunk (lo[0])
-        uint32_t q_cnt[2] = {0, 0};   // Q tiles consumed per slot (parity of q_full)
-        uint32_t p_par = 0;           // per (slot,sbuf) bit: parity of the p_ready phase to wait for
-        uint32_t tile_cnt[2] = {0, 0};
+        uint32_t q_cnt = 0;        // Q tiles consumed (parity of q_full)
+        uint32_t p_par = 0;        // bit sbuf: parity of the p_ready phase to wait for
+        uint32_t tile_cnt = 0;
         int item = blockIdx.x;
         At4Item cur = at4_decode(item, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
         for (; item < n_items; item += gridDim.x) {
           const At4Item nxt =
               at4_decode(item + gridDim.x, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
-          const int n_active = (cur.hi[1] > 0) ? 2 : 1;
           const int n_u = cur.hi_u - cur.lo[0];
-          // positions are relative to the item's first ring chunk
-          int c_lo[2], c_hi[2], qk_next[2], pv_next[2];
-          bool q_ok[2] = {false, false};
+          const int my_lo = slot ? cur.lo[1] : cur.lo[0];
+          const int my_hi = slot ? cur.hi[1] : cur.hi[0];
+          const bool active = my_hi > 0;
+          const int c_lo = active ? my_lo - cur.lo[0] : n_u;   // positions relative to the ring's first chunk
+          const int c_hi = active ? my_hi - cur.lo[0] : n_u;
+          auto pass_on = [&](int c) {   // a chunk this slot does not use: arrive once it has been filled
+            const uint32_t rc = chunk_base + c;
+            mbar_wait(kv_full + 8u * (rc % AT4_NST), (rc / AT4_NST) & 1u);
+            mbar_arrive(kv_empty + 8u * (rc % AT4_NST));
+          };
+          auto issue_qk = [&](int c) {
+            const int sbuf = (c - c_lo) & 1;
+            const uint32_t rc = chunk_base + c;
+            const int st = rc % AT4_NST;
+            mbar_wait(kv_full + 8u * st, (rc / AT4_NST) & 1u);
+            tc_fence_after();
+            const uint32_t k_addr = sb + AT4_SMEM_KV + st * 2 * AT4_KVTILE;
+            const uint32_t d = t_slot + static_cast<uint32_t>(sbuf * 64);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            c_lo[s] = cur.lo[s] - cur.lo[0];
-            c_hi[s] = cur.hi[s] - cur.lo[0];
-            qk_next[s] = pv_next[s] = c_lo[s];
-          }
-          int released = 0;
-          int remaining = n_active;
-          while (remaining > 0) {
+            for (int k = 0; k < AT4_D / 16; ++k) {
+              const uint64_t q_desc =
+                  make_smem_desc_sw128(q_addr + (k >> 2) * AT4_QSLAB, 16, 1024) + 2u * (k & 3);
+              const uint64_t k_desc =
+                  make_smem_desc_sw128(k_addr + (k >> 2) * AT4_KVSLAB, 16, 1024) + 2u * (k & 3);
+              tc_mma_f16_ss(d, q_desc, k_desc, idesc_s, static_cast<uint32_t>(k != 0));
+            }
+            tc_commit(s_ready + 8u * (slot * 2 + sbuf));
+            if (c + 1 == c_hi) tc_commit(q_empty + 8u * slot);
+          };
+          for (int c = 0; c < c_lo; ++c) pass_on(c);
+          if (active) {
+            mbar_wait(q_full + 8u * slot, q_cnt & 1u);
+            ++q_cnt;
+            issue_qk(c_lo);
+            for (int c = c_lo; c < c_hi; ++c) {
+              // S of the next chunk goes out before P of this one is awaited (its buffer held the P of
+              // chunk c-1, whose P V was issued one iteration ago)
+              if (c + 1 < c_hi) issue_qk(c + 1);
+              const int sbuf = (c - c_lo) & 1;
+              mbar_wait(p_ready + 8u * (slot * 2 + sbuf), (p_par >> sbuf) & 1u);
+              p_par ^= 1u << sbuf;
+              // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
+              if (c == c_lo && tile_cnt > 0) mbar_wait(o_empty + 8u * slot, (tile_cnt - 1) & 1u);
+              tc_fence_after();
+              const uint32_t rc = chunk_base + c;
+              const int st = rc % AT4_NST;
+              const uint32_t p = t_slot + static_cast<uint32_t>(sbuf * 64);
+              const uint32_t o = t_slot + 128u;
+              const uint32_t v_base = sb + AT4_SMEM_KV + st * 2 * AT4_KVTILE + AT4_KVTILE;
 #pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              if (slot >= n_active || pv_next[slot] >= c_hi[slot]) continue;
-              const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
-              // ---- S = Q K_c^T into S buffer (local chunk number & 1), at most one chunk ahead of P V
-              if (qk_next[slot] < c_hi[slot] && qk_next[slot] < pv_next[slot] + 2) {
-                const int c = qk_next[slot];
-                const int sbuf = (c - c_lo[slot]) & 1;
-                const uint32_t rc = chunk_base + c;
-                const int st = rc % AT4_NST;
-                bool ready = q_ok[slot] || mbar_test(q_full + 8u * slot, q_cnt[slot] & 1u);
-                ready = ready && mbar_test(kv_full + 8u * st, (rc / AT4_NST) & 1u);
-                if (ready) {
-                  if (!q_ok[slot]) {
-                    q_ok[slot] = true;
-                    ++q_cnt[slot];
-                  }
-                  tc_fence_after();
-                  const uint32_t q_addr = sb + AT4_SMEM_Q + slot * AT4_QTILE;
-                  const uint32_t k_addr = sb + AT4_SMEM_KV + st * 2 * AT4_KVTILE;
-                  const uint32_t d = t_slot + static_cast<uint32_t>(sbuf * 64);
-#pragma unroll
-                  for (int k = 0; k < AT4_D / 16; ++k) {
-                    const uint64_t q_desc =
-                        make_smem_desc_sw128(q_addr + (k >> 2) * AT4_QSLAB, 16, 1024) + 2u * (k & 3);
-                    const uint64_t k_desc =
-                        make_smem_desc_sw128(k_addr + (k >> 2) * AT4_KVSLAB, 16, 1024) + 2u * (k & 3);
-                    tc_mma_f16_ss(d, q_desc, k_desc, idesc_s, static_cast<uint32_t>(k != 0));
-                  }
-                  tc_commit(s_ready + 8u * (slot * 2 + sbuf));
-                  if (c + 1 == c_hi[slot]) tc_commit(q_empty + 8u * slot);
-                  ++qk_next[slot];
-                }
+              for (int k = 0; k < AT4_KC / 16; ++k) {
+                // 16 keys = two 8-key groups 1024 B apart (SBO); the two 64-wide d slabs are 8 KiB
+                // apart (LBO)
+                const uint64_t v_desc = make_smem_desc_sw128(v_base + k * 16 * 128, AT4_KVSLAB, 1024);
+                tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
+                              static_cast<uint32_t>((c != c_lo) || k != 0));
               }
-              // ---- O += P V_c once the softmax warpgroup has published P
-              if (pv_next[slot] < qk_next[slot]) {
-                const int c = pv_next[slot];
-                const int sbuf = (c - c_lo[slot]) & 1;
-                const int pidx = slot * 2 + sbuf;
-                if (mbar_test(p_ready + 8u * pidx, (p_par >> pidx) & 1u)) {
-                  p_par ^= 1u << pidx;
-                  // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
-                  if (c == c_lo[slot] && tile_cnt[slot] > 0)
-                    mbar_wait(o_empty + 8u * slot, (tile_cnt[slot] - 1) & 1u);
-                  tc_fence_after();
-                  const uint32_t rc = chunk_base + c;
-                  const int st = rc % AT4_NST;
-                  const uint32_t p = t_slot + static_cast<uint32_t>(sbuf * 64);
-                  const uint32_t o = t_slot + 128u;
-                  const uint32_t v_base = sb + AT4_SMEM_KV + st * 2 * AT4_KVTILE + AT4_KVTILE;
-#pragma unroll
-                  for (int k = 0; k < AT4_KC / 16; ++k) {
-                    // 16 keys = two 8-key groups 1024 B apart (SBO); the two 64-wide d slabs are
-                    // 8 KiB apart (LBO)
-                    const uint64_t v_desc =
-                        make_smem_desc_sw128(v_base + k * 16 * 128, AT4_KVSLAB, 1024);
-                    tc_mma_f16_ts(o, p + static_cast<uint32_t>(8 * k), v_desc, idesc_o,
-                                  static_cast<uint32_t>((c != c_lo[slot]) || k != 0));
-                  }
-                  tc_commit(pv_done + 8u * pidx);
-                  ++pv_next[slot];
-                  if (pv_next[slot] == c_hi[slot]) {
-                    tc_commit(o_ready + 8u * slot);
-                    ++tile_cnt[slot];
-                    --remaining;
-                  }
-                }
+              tc_commit(pv_done + 8u * (slot * 2 + sbuf));
+              tc_commit(kv_empty + 8u * st);   // this slot is done with the stage
+              if (c + 1 == c_hi) {
+                tc_commit(o_ready + 8u * slot);
+                ++tile_cnt;
               }
             }
-            // ring stages no active slot still needs go back to the loader
-            int done = n_u;
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-              if (s < n_active && pv_next[s] < c_hi[s]) done = min(done, pv_next[s]);
-            while (released < done) {
-              tc_commit(kv_empty + 8u * ((chunk_base + released) % AT4_NST));
-              ++released;
-            }
           }
+          for (int c = c_hi; c < n_u; ++c) pass_on(c);
           chunk_base += static_cast<uint32_t>(n_u);
           cur = nxt;
         }
