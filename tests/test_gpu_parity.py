@@ -495,3 +495,40 @@ def test_retriever_query_path_end_to_end(tmp_path, tiny_bert, tiny_native):
     assert res2.total_indices[0] == ref_i[0, :4].tolist()
     with pytest.raises(ValueError, match='at least one of'):
         retriever.search()
+
+
+def test_esm2_full_length_properties():
+    """BASELINE config C5 length (1024 residues -> S = 1026, not a multiple of the 128-row query tile nor of
+    the 64-key chunk) at the 650M layer shape, 2 layers: determinism, unit norm, and the embedding of a
+    right-padded sequence equals the embedding of the same sequence fed without its padding (the per-row
+    mean pooler drops the padding; the encoder must not let padded keys or rows leak)."""
+    from transformers import EsmConfig
+
+    from distllm_b200.embed.encoders.native import NativeEsm2Encoder
+    from distllm_b200.embed.encoders.weights import random_esm_state_dict
+
+    cfg = EsmConfig(vocab_size=33, hidden_size=1280, num_hidden_layers=2, num_attention_heads=20,
+                    intermediate_size=5120, max_position_embeddings=1026, position_embedding_type='rotary',
+                    token_dropout=True, mask_token_id=32, pad_token_id=1, layer_norm_eps=1e-5,
+                    emb_layer_norm_before=False, initializer_range=0.02)
+    dev = torch.device('cuda:0')
+    native = NativeEsm2Encoder(cfg, random_esm_state_dict(cfg, seed=11, device=dev))
+    try:
+        g = torch.Generator().manual_seed(12)
+        s = 1026
+        ids = torch.randint(4, 24, (3, s), generator=g)
+        ids[:, 0] = 0
+        lens = torch.tensor([1026, 700, 65])
+        mask = (torch.arange(s)[None] < lens[:, None]).long()
+        ids = ids.masked_fill(mask == 0, 1)
+        a = native.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, True)
+        b = native.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, True)
+        assert torch.equal(a, b) and torch.isfinite(a).all()
+        np.testing.assert_allclose(a.norm(dim=-1).cpu().numpy(), 1.0, rtol=1e-5)
+        for row, n in ((1, 700), (2, 65)):
+            alone = native.encode_pooled(ids[row:row + 1, :n].contiguous(), mask[row:row + 1, :n].contiguous(),
+                                         None, nv.POOL_MEAN_PER_ROW, True)
+            cos = cosine_rows(alone.cpu().numpy(), a[row:row + 1].cpu().numpy())
+            assert cos.min() > 1 - 1e-5, (row, cos)
+    finally:
+        native.close()
