@@ -26,6 +26,53 @@ from distllm_b200.embed.poolers.base import Pooler
 from distllm_b200.utils import BaseConfig
 
 
+def prefetched(dataloader, depth: int = 2):
+    """Iterate ``dataloader`` one step ahead on a background thread.
+
+    With ``num_workers == 0`` the tokenizer runs inside ``next(iterator)``; the Rust backend releases
+    the GIL, so producing batch i+1 here overlaps the main thread's copy and launches of batch i (the
+    GPU work itself is asynchronous either way).  DataLoaders with worker processes already prefetch and
+    are passed through untouched.  Order and exceptions are preserved.
+    """
+    if getattr(dataloader, 'num_workers', 1) != 0 or depth <= 0:
+        yield from dataloader
+        return
+    import queue
+    import threading
+
+    done = object()
+    box: queue.Queue = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+
+    def produce() -> None:
+        try:
+            for item in dataloader:
+                while not stop.is_set():
+                    try:
+                        box.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            box.put(done)
+        except BaseException as exc:  # noqa: BLE001  handed to the consumer
+            box.put(exc)
+
+    worker = threading.Thread(target=produce, name='b2e-host-feed', daemon=True)
+    worker.start()
+    try:
+        while True:
+            item = box.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+
+
 def _fused_kind(encoder: Encoder, pooler: Pooler) -> int | None:
     if not hasattr(encoder, 'encode_pooled'):
         return None
@@ -46,7 +93,7 @@ def compute_embeddings_device(
                       device=encoder.device)
     kind = _fused_kind(encoder, pooler)
     idx = 0
-    for batch in tqdm(dataloader, disable=not progress):
+    for batch in tqdm(prefetched(dataloader), total=len(dataloader), disable=not progress):
         inputs = batch.to(encoder.device, non_blocking=True)
         batch_size = inputs['attention_mask'].shape[0]
         if kind is not None:

@@ -442,3 +442,37 @@ def test_exact_index_has_no_cpu_fallback():
         ExactIndex(np.zeros((4, 128), np.float32))
     with pytest.raises(ValueError, match='embedding matrix or a dataset_dir'):
         ExactIndex()
+
+
+def test_prefetched_iteration_keeps_order_and_errors():
+    import threading
+
+    from distllm_b200.embed.embedders.full_sequence import prefetched
+
+    class Loader:
+        num_workers = 0
+
+        def __init__(self, n, fail_at=None):
+            self.n, self.fail_at, self.threads = n, fail_at, set()
+
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            for i in range(self.n):
+                self.threads.add(threading.current_thread().name)
+                if i == self.fail_at:
+                    raise KeyError('boom')
+                yield i
+
+    ld = Loader(25)
+    assert list(prefetched(ld)) == list(range(25))
+    assert ld.threads == {'b2e-host-feed'}                     # produced off the main thread
+    with pytest.raises(KeyError, match='boom'):
+        list(prefetched(Loader(10, fail_at=4)))
+    it = prefetched(Loader(1000))                                # abandoned early: the producer stops
+    assert [next(it) for _ in range(3)] == [0, 1, 2]
+    it.close()
+    ld4 = Loader(5)
+    ld4.num_workers = 4                                          # worker processes: passed through
+    assert list(prefetched(ld4)) == list(range(5)) and ld4.threads == {threading.current_thread().name}
