@@ -3,5 +3,6 @@
 from distllm_b200.rag.search import ExactIndex
 from distllm_b200.rag.search import ExactIndexConfig
 from distllm_b200.rag.search import Retriever
+from distllm_b200.rag.search import RetrieverConfig
 
-__all__ = ['ExactIndex', 'ExactIndexConfig', 'Retriever']
+__all__ = ['ExactIndex', 'ExactIndexConfig', 'Retriever', 'RetrieverConfig']

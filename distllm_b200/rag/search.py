@@ -110,6 +110,24 @@ def filter_search_by_score(results: BatchedSearchResults, score_threshold: float
     return BatchedSearchResults(total_scores=new_scores, total_indices=new_indices)
 
 
+class RetrieverConfig(BaseConfig):
+    """Settings of a retriever (distllm/rag/search.py:669-712, with the exact index in place of faiss)."""
+
+    faiss_config: ExactIndexConfig = Field(..., description='Settings for the exact index')
+    encoder_config: dict = Field(..., description='Settings for the encoder (as in the embedding YAML)')
+    pooler_config: dict = Field(..., description='Settings for the pooler')
+    batch_size: int = Field(4, description='Batch size for the embedder model')
+
+    def get_retriever(self) -> 'Retriever':
+        from distllm_b200.embed import get_encoder
+        from distllm_b200.embed import get_pooler
+
+        encoder = get_encoder(dict(self.encoder_config))
+        pooler = get_pooler(dict(self.pooler_config))
+        return Retriever(encoder=encoder, pooler=pooler, faiss_index=ExactIndex(config=self.faiss_config),
+                         batch_size=self.batch_size)
+
+
 class Retriever:
     """Semantic similarity search: same call surface as distllm/rag/search.py:715-881."""
 

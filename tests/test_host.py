@@ -476,3 +476,18 @@ def test_prefetched_iteration_keeps_order_and_errors():
     ld4 = Loader(5)
     ld4.num_workers = 4                                          # worker processes: passed through
     assert list(prefetched(ld4)) == list(range(5)) and ld4.threads == {threading.current_thread().name}
+
+
+def test_retriever_config_roundtrip(tmp_path):
+    from distllm_b200.rag import RetrieverConfig
+
+    cfg = RetrieverConfig(
+        faiss_config={'dataset_dir': str(tmp_path / 'ds'), 'corpus_dtype': 'bfloat16'},
+        encoder_config={'name': 'auto', 'pretrained_model_name_or_path': 'x', 'quantization': False},
+        pooler_config={'name': 'mean'},
+    )
+    assert cfg.batch_size == 4 and cfg.faiss_config.search_algorithm == 'exact'
+    cfg.write_yaml(tmp_path / 'r.yaml')
+    assert RetrieverConfig.from_yaml(tmp_path / 'r.yaml') == cfg
+    with pytest.raises(Exception):  # noqa: B017, PT011  only the exact search exists
+        RetrieverConfig(faiss_config={'search_algorithm': 'hnsw'}, encoder_config={}, pooler_config={})
