@@ -491,3 +491,43 @@ def test_retriever_config_roundtrip(tmp_path):
     assert RetrieverConfig.from_yaml(tmp_path / 'r.yaml') == cfg
     with pytest.raises(Exception):  # noqa: B017, PT011  only the exact search exists
         RetrieverConfig(faiss_config={'search_algorithm': 'hnsw'}, encoder_config={}, pooler_config={})
+
+
+# ------------------------------------------------------------------------------ kernel host-math mirrors
+def _at4_ranges(t: int, nq: int, window: int, kv_chunks: int):
+    """Python mirror of at4_decode (distllm_b200/csrc/attention4.cuh): chunk range a query tile visits."""
+    if t >= nq:
+        return 0, 0
+    hi = min(kv_chunks, 2 * t + 2)
+    lo = max(0, 128 * t - window + 1) // 64 if window > 0 else 0
+    if lo >= hi:
+        lo = hi - 1
+    return lo, hi
+
+
+def _at4_edge(t: int, j: int, window: int) -> bool:
+    key0 = 64 * j
+    return key0 + 63 > 128 * t or (window > 0 and 128 * t + 127 - key0 >= window)
+
+
+@pytest.mark.parametrize('window', [0, 1, 64, 65, 80, 128, 300, 4096])
+def test_causal_window_chunk_ranges_cover_every_visible_key(window):
+    """The chunk range a query tile walks contains every chunk with a visible key of any of its rows, and
+    a chunk classified as interior (unmasked fast path) is fully visible to all 128 rows of the tile."""
+    for s in (1, 63, 64, 65, 128, 129, 400, 1100):
+        for valid in {1, s // 2 + 1, s}:                      # right-padded length
+            nq = (s + 127) // 128
+            kv_chunks = (valid + 63) // 64
+            for t in range(nq):
+                lo, hi = _at4_ranges(t, nq, window, kv_chunks)
+                assert 0 <= lo < hi <= kv_chunks
+                rows = range(128 * t, min(128 * (t + 1), s))
+                for i in rows:
+                    first = max(0, i - window + 1) if window else 0
+                    last = min(i, valid - 1)
+                    if first <= last:                          # the row sees attended keys
+                        assert lo <= first // 64 and last // 64 < hi, (s, valid, t, i)
+                for j in range(lo, hi):
+                    if not _at4_edge(t, j, window):
+                        for i in (128 * t, 128 * t + 127):
+                            assert 64 * j + 63 <= i and (not window or i - 64 * j < window)
