@@ -26,6 +26,7 @@ EXPORTS = (
     'b2e_version',
     'b2e_last_error',
     'b2e_num_weights',
+    'b2e_check_model',
     'b2e_encoder_create',
     'b2e_encoder_destroy',
     'b2e_workspace_bytes',
@@ -41,6 +42,13 @@ EXPORTS = (
     'b2e_attention_causal_d128',
     'b2e_topk_ip',
     'b2e_layernorm',
+)
+# profiling hooks declared in include/b2e_debug.h (tools/ only; nothing in the package calls them)
+DEBUG_EXPORTS = (
+    'b2e_debug_set_att3_clock',
+    'b2e_debug_set_att3_flags',
+    'b2e_debug_set_pair_flags',
+    'b2e_debug_set_clock_buffer',
 )
 
 
@@ -80,6 +88,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_last_error.argtypes = []
     lib.b2e_num_weights.restype = i32
     lib.b2e_num_weights.argtypes = [C.POINTER(ModelDesc)]
+    lib.b2e_check_model.restype = i32
+    lib.b2e_check_model.argtypes = [C.POINTER(ModelDesc)]
     lib.b2e_encoder_create.restype = i32
     lib.b2e_encoder_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp), i32, i32, C.POINTER(vp)]
     lib.b2e_encoder_destroy.restype = None

@@ -41,6 +41,7 @@ def _nvcc() -> str:
 def sources() -> list[Path]:
     return sorted(CSRC.glob('*.cu')) + sorted(CSRC.glob('*.cuh')) + [
         PKG_DIR.parent / 'include' / 'b2e.h',
+        PKG_DIR.parent / 'include' / 'b2e_debug.h',
     ]
 
 

@@ -2,6 +2,7 @@
 // lazily grown workspace, TMA descriptors and launches.  No CPU fallback: without an sm_100 device
 // every compute entry point fails with B2E_ERR_NO_DEVICE.
 #include "../../include/b2e.h"
+#include "../../include/b2e_debug.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -296,15 +297,19 @@ struct AttnScratch {
       ++gen;
     }
     if ((size_t)B * S_pad > cap_bias || (size_t)B > cap_b) ++gen;
+    // pointer nulled and capacity zeroed BEFORE the new allocation: a failed cudaMalloc must not leave
+    // a dangling pointer behind a non-zero capacity
     if ((size_t)B * S_pad > cap_bias) {
-      if (bias) cudaFree(bias);
+      cudaFree(bias);
       bias = nullptr;
+      cap_bias = 0;
       CUDA_TRY(cudaMalloc(&bias, sizeof(float) * (size_t)B * S_pad));
       cap_bias = (size_t)B * S_pad;
     }
     if ((size_t)B > cap_b) {
-      if (kv_chunks) cudaFree(kv_chunks);
+      cudaFree(kv_chunks);
       kv_chunks = nullptr;
+      cap_b = 0;
       CUDA_TRY(cudaMalloc(&kv_chunks, sizeof(int) * B));
       cap_b = B;
     }
@@ -379,15 +384,21 @@ int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, in
     case 4: { constexpr int NV = 4; CALL; break; }                  \
     case 5: { constexpr int NV = 5; CALL; break; }                  \
     case 8: { constexpr int NV = 8; CALL; break; }                  \
+    case 10: { constexpr int NV = 10; CALL; break; }                \
     case 16: { constexpr int NV = 16; CALL; break; }                \
-    default: return fail(B2E_ERR_INVALID, "hidden size %d not supported (need 256*{1,2,3,4,5,8,16})", (H)); \
+    default: return fail(B2E_ERR_INVALID, "hidden size %d not supported (need 256*{1,2,3,4,5,8,10,16})", (H)); \
   }
 
 inline int row_blocks(int rows) { return (rows + ROW_WARPS - 1) / ROW_WARPS; }
 
+// The row kernels are instantiated per H/256 (DISPATCH_NV): reject every other width up front, i.e.
+// at b2e_encoder_create, before any weight is touched, not at the first forward pass.
 int check_h(int H) {
   if (H % 256 != 0) return fail(B2E_ERR_INVALID, "hidden size %d must be a multiple of 256", H);
-  return B2E_OK;
+  switch (H / 256) {
+    case 1: case 2: case 3: case 4: case 5: case 8: case 10: case 16: return B2E_OK;
+  }
+  return fail(B2E_ERR_UNSUPPORTED, "hidden size %d not supported (built: 256 x {1,2,3,4,5,8,10,16})", H);
 }
 
 // Pool-weight scratch shared by the fused and the standalone poolers.
@@ -411,27 +422,36 @@ struct PoolScratch {
       ++gen;
     }
     if ((size_t)B > cap_b || (size_t)S > cap_s || (size_t)B * S > cap_bs || part_elems > cap_part) ++gen;
+    // every branch: free, null the pointers and zero the capacity, THEN allocate (a failed cudaMalloc
+    // leaves "nothing allocated", never a dangling pointer that a smaller later call would reuse)
     if ((size_t)B > cap_b) {
-      if (seq_len) cudaFree(seq_len);
-      if (idx) cudaFree(idx);
-      if (count) cudaFree(count);
+      cudaFree(seq_len); cudaFree(idx); cudaFree(count);
+      seq_len = idx = nullptr;
+      count = nullptr;
+      cap_b = 0;
       CUDA_TRY(cudaMalloc(&seq_len, sizeof(int) * B));
       CUDA_TRY(cudaMalloc(&idx, sizeof(int) * B));
       CUDA_TRY(cudaMalloc(&count, sizeof(float) * B));
       cap_b = B;
     }
     if ((size_t)S > cap_s) {
-      if (kill) cudaFree(kill);
+      cudaFree(kill);
+      kill = nullptr;
+      cap_s = 0;
       CUDA_TRY(cudaMalloc(&kill, sizeof(int) * S));
       cap_s = S;
     }
     if ((size_t)B * S > cap_bs) {
-      if (w) cudaFree(w);
+      cudaFree(w);
+      w = nullptr;
+      cap_bs = 0;
       CUDA_TRY(cudaMalloc(&w, sizeof(float) * (size_t)B * S));
       cap_bs = (size_t)B * S;
     }
     if (part_elems > cap_part) {
-      if (part) cudaFree(part);
+      cudaFree(part);
+      part = nullptr;
+      cap_part = 0;
       CUDA_TRY(cudaMalloc(&part, sizeof(float) * part_elems));
       cap_part = part_elems;
     }
@@ -467,6 +487,21 @@ int launch_finalize(PoolScratch& ps, float* out, int B, int H, int nsplit, int l
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
+
+// Restores the caller's current device on scope exit: create / destroy / embed_host switch to the
+// encoder's device and must not leave torch's notion of the current device changed behind its back.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 thread_local PoolScratch g_pool_scratch;  // for the handle-less standalone poolers
 thread_local AttnScratch g_attn_scratch;  // for the standalone attention op
@@ -571,6 +606,7 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     ++e->ws_gen;
     cudaFree(e->tok_scale);
     e->tok_scale = nullptr;
+    e->cap_scale = 0;
     CUDA_TRY(cudaMalloc(&e->tok_scale, sizeof(float) * B));
     e->cap_scale = B;
   }
@@ -755,9 +791,10 @@ extern "C" {
 
 int b2e_version(void) { return B2E_ABI_VERSION; }
 
-// Profiling aid (not part of include/b2e.h): device buffer of 4 x 256 int64 that CTAs 0 and 1 of
-// the CTA-pair GEMM fill with clock64() stamps ([cta*2 + role][n], role 0 = producer, 1 = MMA).
-// Same idea for the streaming attention kernel: 3 roles x (256 clocks + 256 event codes) int64.
+// Profiling hooks (include/b2e_debug.h, not part of the reference-facing ABI): device buffer of
+// 4 x 256 int64 that CTAs 0 and 1 of the CTA-pair GEMM fill with clock64() stamps ([cta*2 + role][n],
+// role 0 = producer, 1 = MMA).  Same idea for the streaming attention kernel: 3 roles x (256 clocks +
+// 256 event codes) int64.
 int b2e_debug_set_att3_clock(void* device_buffer) {
   long long* p = static_cast<long long*>(device_buffer);
   CUDA_TRY(cudaMemcpyToSymbol(g_att3_clock, &p, sizeof(p)));
@@ -790,30 +827,56 @@ int b2e_num_weights(const B2EModelDesc* desc) {
   return -1;
 }
 
+// Everything b2e_encoder_create would reject about the SHAPE of a model, without touching a device or
+// a weight: callers run it before they upload gigabytes of parameters.
+int b2e_check_model(const B2EModelDesc* desc) {
+  if (!desc) return fail(B2E_ERR_INVALID, "null model description");
+  if (desc->num_layers <= 0 || desc->hidden <= 0 || desc->heads <= 0 || desc->intermediate <= 0)
+    return fail(B2E_ERR_INVALID, "model description has a non-positive size");
+  int rc;
+  if (desc->arch == B2E_ARCH_MISTRAL) {
+    if (desc->head_dim != 128 || desc->kv_heads <= 0 || desc->heads % desc->kv_heads != 0)
+      return fail(B2E_ERR_UNSUPPORTED, "need head_dim 128 and heads %% kv_heads == 0 (got %d/%d x %d)",
+                  desc->heads, desc->kv_heads, desc->head_dim);
+    if (desc->intermediate % 128 != 0)
+      return fail(B2E_ERR_UNSUPPORTED, "intermediate size %d must be a multiple of 128", desc->intermediate);
+    if (desc->sliding_window < 0) return fail(B2E_ERR_INVALID, "negative sliding_window");
+    const int H = desc->hidden, I = desc->intermediate;
+    const int QC = (desc->heads + 2 * desc->kv_heads) * 128, CC = desc->heads * 128;
+    if ((rc = check_h(H))) return rc;
+    if ((rc = check_gemm_shape(128, QC, H))) return rc;
+    if ((rc = check_gemm_shape(128, H, CC))) return rc;
+    if ((rc = check_gemm_shape(128, 2 * I, H))) return rc;
+    return check_gemm_shape(128, H, I);
+  }
+  if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
+    return fail(B2E_ERR_UNSUPPORTED, "arch %d: unknown architecture", desc->arch);
+  if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
+    return fail(B2E_ERR_UNSUPPORTED,
+                "need head_dim 64 and heads*64 == hidden (got %d heads x %d, H=%d); of the ESM-2 family that "
+                "is esm2_t33_650M (H=1280) and esm2_t36_3B (H=2560)",
+                desc->heads, desc->head_dim, desc->hidden);
+  if ((rc = check_h(desc->hidden))) return rc;
+  if ((rc = check_gemm_shape(128, 3 * desc->hidden, desc->hidden))) return rc;
+  if ((rc = check_gemm_shape(128, desc->intermediate, desc->hidden))) return rc;
+  return check_gemm_shape(128, desc->hidden, desc->intermediate);
+}
+
 namespace {
 // Mistral family: head_dim 128, grouped-query heads, SwiGLU MLP, no biases.
 int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_weights, int device,
                    B2EEncoder** out) {
-  if (desc->head_dim != 128 || desc->kv_heads <= 0 || desc->heads % desc->kv_heads != 0)
-    return fail(B2E_ERR_UNSUPPORTED, "need head_dim 128 and heads %% kv_heads == 0 (got %d/%d x %d)",
-                desc->heads, desc->kv_heads, desc->head_dim);
-  if (desc->intermediate % 128 != 0)
-    return fail(B2E_ERR_UNSUPPORTED, "intermediate size %d must be a multiple of 128", desc->intermediate);
-  if (desc->sliding_window < 0) return fail(B2E_ERR_INVALID, "negative sliding_window");
   const int L = desc->num_layers, H = desc->hidden, I = desc->intermediate;
   const int QC = (desc->heads + 2 * desc->kv_heads) * 128, CC = desc->heads * 128;
   int rc;
-  if ((rc = check_h(H))) return rc;
-  if ((rc = check_gemm_shape(128, QC, H))) return rc;
-  if ((rc = check_gemm_shape(128, H, CC))) return rc;
-  if ((rc = check_gemm_shape(128, 2 * I, H))) return rc;
-  if ((rc = check_gemm_shape(128, H, I))) return rc;
+  if ((rc = b2e_check_model(desc))) return rc;
   if (n_weights != b2e_num_weights(desc))
     return fail(B2E_ERR_INVALID, "expected %d weight pointers, got %d", b2e_num_weights(desc), n_weights);
   for (int i = 0; i < n_weights; ++i)
     if (!weights[i]) return fail(B2E_ERR_INVALID, "weight pointer %d is null", i);
   DeviceInfo info;
   if ((rc = device_info(device, &info))) return rc;
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(device));
   B2EEncoder* e = new B2EEncoder();
   e->desc = *desc;
@@ -852,16 +915,8 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
   if (!desc || !weights || !out) return fail(B2E_ERR_INVALID, "null argument");
   *out = nullptr;
   if (desc->arch == B2E_ARCH_MISTRAL) return create_mistral(desc, weights, n_weights, device, out);
-  if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
-    return fail(B2E_ERR_UNSUPPORTED, "arch %d: unknown architecture", desc->arch);
-  if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
-    return fail(B2E_ERR_UNSUPPORTED, "need head_dim 64 and heads*64 == hidden (got %d x %d, H=%d)",
-                desc->heads, desc->head_dim, desc->hidden);
   int rc;
-  if ((rc = check_h(desc->hidden))) return rc;
-  if ((rc = check_gemm_shape(128, 3 * desc->hidden, desc->hidden))) return rc;
-  if ((rc = check_gemm_shape(128, desc->intermediate, desc->hidden))) return rc;
-  if ((rc = check_gemm_shape(128, desc->hidden, desc->intermediate))) return rc;
+  if ((rc = b2e_check_model(desc))) return rc;
   if (n_weights != b2e_num_weights(desc))
     return fail(B2E_ERR_INVALID, "expected %d weight pointers, got %d", b2e_num_weights(desc),
                 n_weights);
@@ -869,6 +924,7 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
     if (!weights[i]) return fail(B2E_ERR_INVALID, "weight pointer %d is null", i);
   DeviceInfo info;
   if ((rc = device_info(device, &info))) return rc;
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(device));
 
   B2EEncoder* e = new B2EEncoder();
@@ -911,6 +967,7 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
 
 void b2e_encoder_destroy(B2EEncoder* e) {
   if (!e) return;
+  DeviceGuard guard;
   cudaSetDevice(e->device);
   cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
   cudaFree(e->stage_in); cudaFree(e->stage_out);
@@ -1076,6 +1133,7 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
   if (n_rows == 0) return B2E_OK;
   if (!ids || !mask || !out_host) return fail(B2E_ERR_INVALID, "null host pointer");
   int rc;
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(e->device));   // host entry point: it owns its device context and stream
   if ((rc = validate_batch(e, batch, S))) return rc;
   if (!e->own_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
@@ -1087,6 +1145,7 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     ++e->ws_gen;
     cudaFree(e->stage_in);
     e->stage_in = nullptr;
+    e->stage_cap = 0;
     CUDA_TRY(cudaMalloc(&e->stage_in, 2 * slot * sizeof(int64_t)));
     e->stage_cap = 2 * slot;
   }
@@ -1095,6 +1154,7 @@ int b2e_embed_host(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     ++e->ws_gen;
     cudaFree(e->stage_out);
     e->stage_out = nullptr;
+    e->stage_out_cap = 0;
     CUDA_TRY(cudaMalloc(&e->stage_out, out_elems * sizeof(float)));
     e->stage_out_cap = out_elems;
   }

@@ -2,9 +2,9 @@
 
 ``embedding_worker`` keeps the signature, timers and on-disk result of
 distllm/distributed_embedding.py:23-80.  The driver replaces the Parsl pool
-(distributed_embedding.py:112-161) with ``torchrun``: one process per GPU, input files sharded
-contiguously by rank, no traffic between ranks while embedding, and (with ``--gather``) a single
-NCCL all-gather of the pooled embedding matrix at the end.
+(distributed_embedding.py:112-161) with ``torchrun``: one process per GPU, the DOCUMENTS of the input
+files sharded contiguously by rank, no traffic between ranks while embedding, and (with ``--gather``)
+a single NCCL all-gather of the device-resident pooled embedding matrix at the end.
 
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         -m distllm_b200.distributed_embedding --config embed.yaml [--gather]
@@ -36,8 +36,13 @@ def embed_file(  # noqa: PLR0913
     pooler_kwargs: dict[str, Any],
     embedder_kwargs: dict[str, Any],
     writer_kwargs: dict[str, Any],
+    source_path: Path | None = None,
 ) -> EmbedderResult:
-    """Embed one file, write it under ``output_dir/<uuid4>/`` and hand the result back."""
+    """Embed one file, write it under ``output_dir/<uuid4>/`` and hand the result back.
+
+    ``source_path``: when ``input_path`` is a document-range piece of a larger file (the multi-GPU
+    driver), the file the piece was cut from; metadata that records the input path (the FASTA reader's
+    ``paths``) is pointed back at it before writing."""
     from uuid import uuid4
 
     from distllm_b200.embed import get_dataset
@@ -63,6 +68,11 @@ def embed_file(  # noqa: PLR0913
 
     with Timer('computed-embeddings', input_path):
         result = embedder.embed(dataloader, encoder, pooler)
+
+    if source_path is not None and result.metadata:
+        for meta in result.metadata:
+            if meta.get('paths') == str(input_path):
+                meta['paths'] = str(source_path)
 
     dataset_dir = Path(output_dir) / f'{uuid4()}'
     dataset_dir.mkdir(parents=True, exist_ok=True)
@@ -111,26 +121,46 @@ class Config(BaseConfig):
 
 
 def main(argv: list[str] | None = None) -> None:
+    """One process per GPU (torchrun).  The global document sequence -- input files in sorted order,
+    documents in file order -- is cut into ``world`` contiguous ranges (a document never
+    straddles ranks, and one large input file still feeds every GPU); each rank embeds its range with
+    ``embed_file`` and, with ``--gather``, the device-resident pooled rows of all ranks meet in ONE
+    all-gather (no host round trip before the collective); rank 0 writes ``embeddings_all.npy``."""
+    import shutil
+    import traceback
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from distllm_b200.sharding import all_gather_rows
-    from distllm_b200.sharding import shard_list
+    from distllm_b200.sharding import all_ranks_ok
+    from distllm_b200.sharding import count_documents
+    from distllm_b200.sharding import materialize_piece
+    from distllm_b200.sharding import plan_document_shards
     from distllm_b200.sharding import world_info
 
     parser = ArgumentParser(description='Embed text (one process per GPU under torchrun)')
     parser.add_argument('--config', type=Path, required=True, help='Path to the .yaml configuration file')
     parser.add_argument('--gather', action='store_true',
                         help='all-gather the pooled embedding matrix; rank 0 writes embeddings_all.npy')
+    parser.add_argument('--shard_by', choices=['document', 'file'], default='document',
+                        help='unit of the contiguous per-rank ranges (default: document)')
     args = parser.parse_args(argv)
 
     config = Config.from_yaml(args.config)
     rank, world, local_rank = world_info()
-    if torch.cuda.is_available():
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        # one GPU per rank; ranks wrap around only when there are fewer GPUs than ranks (the 2-rank test
+        # of this driver on a single-GPU box, which also has to use gloo: B2E_DIST_BACKEND=gloo)
+        local_rank %= torch.cuda.device_count()
         torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank) if use_cuda else torch.device('cpu')
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+        import os
+
+        dist.init_process_group(os.environ.get('B2E_DIST_BACKEND') or ('nccl' if use_cuda else 'gloo'))
 
     embedding_dir = config.output_dir / 'embeddings'
     embedding_dir.mkdir(parents=True, exist_ok=True)
@@ -144,25 +174,53 @@ def main(argv: list[str] | None = None) -> None:
     if rank == 0:
         print(f'Found {len(input_files)} input files to embed')
 
-    local_rows = []
-    for path in shard_list(input_files, world, rank):
-        result = embed_file(
-            path,
-            embedding_dir,
-            dataset_kwargs=config.dataset_config.model_dump(),
-            encoder_kwargs=config.encoder_config.model_dump(),
-            pooler_kwargs=config.pooler_config.model_dump(),
-            embedder_kwargs=config.embedder_config.model_dump(),
-            writer_kwargs=config.writer_config.model_dump(),
-        )
-        local_rows.append(torch.from_numpy(np.ascontiguousarray(result.embeddings)))
+    dataset_kwargs = config.dataset_config.model_dump()
+    dataset_name = dataset_kwargs['name']
+    header_lines = int(dataset_kwargs.get('header_lines', 1))
+    scratch = config.output_dir / '.shards' / f'rank{rank}'
+    local_rows: list[torch.Tensor] = []
+    error: str | None = None
+    try:
+        if args.shard_by == 'file':
+            counts = [1] * len(input_files)
+        else:
+            counts = [count_documents(f, dataset_name, header_lines) for f in input_files]
+        for file_index, lo, hi in plan_document_shards(counts, world, rank):
+            path = input_files[file_index]
+            piece = path if args.shard_by == 'file' else materialize_piece(
+                path, lo, hi, counts[file_index], dataset_name, scratch, header_lines)
+            result = embed_file(
+                piece,
+                embedding_dir,
+                dataset_kwargs=dataset_kwargs,
+                encoder_kwargs=config.encoder_config.model_dump(),
+                pooler_kwargs=config.pooler_config.model_dump(),
+                embedder_kwargs=config.embedder_config.model_dump(),
+                writer_kwargs=config.writer_config.model_dump(),
+                source_path=None if piece == path else path,
+            )
+            if args.gather:
+                rows = result.device_embeddings
+                if rows is None:   # an embedder without the device-resident matrix (third-party plugin)
+                    rows = torch.from_numpy(np.ascontiguousarray(result.embeddings)).to(device)
+                local_rows.append(rows.to(device=device, dtype=torch.float32))
+    except Exception:  # noqa: BLE001  reported collectively below: never raise on a subset of ranks
+        error = traceback.format_exc()
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+
+    # every rank learns whether any rank failed BEFORE the data collective is entered
+    if not all_ranks_ok(error is None, device):
+        if error is not None:
+            print(f'[rank {rank}] embedding failed:\n{error}', flush=True)
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        raise SystemExit(1)
 
     if args.gather:
-        if not local_rows:
-            raise RuntimeError('rank has no input files; --gather needs at least one file per rank')
-        local = torch.cat(local_rows)
-        device = torch.device('cuda', local_rank) if torch.cuda.is_available() else torch.device('cpu')
-        full = all_gather_rows(local.to(device))
+        # a rank without documents (world > number of documents) contributes zero rows
+        local = torch.cat(local_rows) if local_rows else None
+        full = all_gather_rows(local, device=device)
         if rank == 0:
             np.save(config.output_dir / 'embeddings_all.npy', full.cpu().numpy())
     if dist.is_initialized():

@@ -9,6 +9,8 @@ from distllm_b200.embed._factory import build_from_strategies
 from distllm_b200.embed.datasets.base import Dataset
 from distllm_b200.embed.datasets.fasta import FastaDataset
 from distllm_b200.embed.datasets.fasta import FastaDatasetConfig
+from distllm_b200.embed.datasets.huggingface import HuggingFaceDataset
+from distllm_b200.embed.datasets.huggingface import HuggingFaceDatasetConfig
 from distllm_b200.embed.datasets.jsonl import JsonlDataset
 from distllm_b200.embed.datasets.jsonl import JsonlDatasetConfig
 from distllm_b200.embed.datasets.jsonl_chunk import JsonlChunkDataset
@@ -22,6 +24,7 @@ DatasetConfigs = Union[
     JsonlDatasetConfig,
     JsonlChunkDatasetConfig,
     SequencePerLineDatasetConfig,
+    HuggingFaceDatasetConfig,
 ]
 
 STRATEGIES: dict[str, tuple[type[BaseConfig], type[Dataset]]] = {
@@ -29,6 +32,7 @@ STRATEGIES: dict[str, tuple[type[BaseConfig], type[Dataset]]] = {
     'jsonl': (JsonlDatasetConfig, JsonlDataset),
     'jsonl_chunk': (JsonlChunkDatasetConfig, JsonlChunkDataset),
     'sequence_per_line': (SequencePerLineDatasetConfig, SequencePerLineDataset),
+    'huggingface': (HuggingFaceDatasetConfig, HuggingFaceDataset),
 }
 
 

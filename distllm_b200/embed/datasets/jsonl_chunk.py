@@ -42,20 +42,44 @@ def _regex_spans(text: str) -> list[tuple[int, int]]:
     return [(s, e) for s, e in spans if e > s]
 
 
-def _span_tokenizer() -> Callable[[str], list[tuple[int, int]]]:
+def _span_tokenizer(allow_regex_fallback: bool = True) -> Callable[[str], list[tuple[int, int]]]:
+    """Punkt ``span_tokenize`` (what the reference uses, jsonl_chunk.py:26-28).  Without nltk the regex
+    stand-in is used ONLY when allowed, and never silently: its sentence boundaries differ from Punkt's
+    on abbreviations and the like, so buffers, chunks and embeddings then differ from the reference."""
     try:
         import nltk
 
         punkt = nltk.tokenize.PunktSentenceTokenizer()
         return lambda text: list(punkt.span_tokenize(text))
     except ImportError:
+        if not allow_regex_fallback:
+            raise ImportError(
+                'nltk is required for the reference sentence splitter (PunktSentenceTokenizer); '
+                'install it or set sentence_splitter="regex" in the jsonl_chunk dataset config') from None
+        import warnings
+
+        warnings.warn(
+            'nltk is not installed: jsonl_chunk splits sentences with a regex stand-in whose boundaries '
+            'differ from the reference (Punkt) on abbreviations; chunk texts may differ from distllm. '
+            'Set sentence_splitter="regex" to silence this, or install nltk.',
+            RuntimeWarning, stacklevel=3)
         return _regex_spans
 
 
-def split_by_sentence_tokenizer() -> Callable[[str], list[str]]:
+def split_by_sentence_tokenizer(splitter: str = 'auto') -> Callable[[str], list[str]]:
     """Sentence splitter whose pieces concatenate back to the original text (minus leading junk):
-    piece ``i`` runs from the start of sentence ``i`` to the start of sentence ``i+1``."""
-    spans_of = _span_tokenizer()
+    piece ``i`` runs from the start of sentence ``i`` to the start of sentence ``i+1``.
+
+    ``splitter``: 'punkt' (nltk required, the reference), 'regex' (explicit opt-in to the stand-in),
+    'auto' (punkt when nltk is importable, else the stand-in with a RuntimeWarning)."""
+    if splitter == 'regex':
+        spans_of = _regex_spans
+    elif splitter == 'punkt':
+        spans_of = _span_tokenizer(allow_regex_fallback=False)
+    elif splitter == 'auto':
+        spans_of = _span_tokenizer()
+    else:
+        raise ValueError(f"sentence_splitter must be 'auto', 'punkt' or 'regex', got {splitter!r}")
 
     def split(text: str) -> list[str]:
         starts = [s for s, _ in spans_of(text)]
@@ -84,12 +108,15 @@ class JsonlChunkDatasetConfig(LoaderConfig):
         description='Number of neighbouring sentences on each side grouped with a sentence '
         'when evaluating semantic similarity.',
     )
+    # not in the reference (it hard-requires nltk): which sentence splitter to use, see
+    # split_by_sentence_tokenizer
+    sentence_splitter: Literal['auto', 'punkt', 'regex'] = 'auto'
 
 
 class JsonlChunkDataset:
     def __init__(self, config: JsonlChunkDatasetConfig):
         self.config = config
-        self.splitter = split_by_sentence_tokenizer()
+        self.splitter = split_by_sentence_tokenizer(config.sentence_splitter)
 
     def get_dataloader(self, data_file: Path, encoder: Encoder) -> DataLoader:
         rows: list[dict[str, Any]] = read_jsonl(data_file)

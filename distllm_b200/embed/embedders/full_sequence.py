@@ -26,13 +26,15 @@ from distllm_b200.embed.poolers.base import Pooler
 from distllm_b200.utils import BaseConfig
 
 
-def prefetched(dataloader, depth: int = 2):
+def prefetched(dataloader, depth: int = 2, device: torch.device | None = None):
     """Iterate ``dataloader`` one step ahead on a background thread.
 
     With ``num_workers == 0`` the tokenizer runs inside ``next(iterator)``; the Rust backend releases
     the GIL, so producing batch i+1 here overlaps the main thread's copy and launches of batch i (the
     GPU work itself is asynchronous either way).  DataLoaders with worker processes already prefetch and
-    are passed through untouched.  Order and exceptions are preserved.
+    are passed through untouched.  Order and exceptions are preserved.  ``device``: the CUDA device the
+    consumer works on; the producer thread makes it current before it pins memory (DataLoader's own pin
+    thread does the same), else pinning would initialise a context on device 0.
     """
     if getattr(dataloader, 'num_workers', 1) != 0 or depth <= 0:
         yield from dataloader
@@ -44,20 +46,27 @@ def prefetched(dataloader, depth: int = 2):
     box: queue.Queue = queue.Queue(maxsize=depth)
     stop = threading.Event()
 
+    def put(item) -> bool:
+        """Stop-aware put: gives up (False) once the consumer has gone away, so the thread never blocks
+        forever on a full queue holding the DataLoader iterator and its pinned batches."""
+        while not stop.is_set():
+            try:
+                box.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
     def produce() -> None:
         try:
+            if device is not None and device.type == 'cuda' and torch.cuda.is_available():
+                torch.cuda.set_device(device)
             for item in dataloader:
-                while not stop.is_set():
-                    try:
-                        box.put(item, timeout=0.1)
-                        break
-                    except queue.Full:
-                        continue
-                if stop.is_set():
+                if not put(item):
                     return
-            box.put(done)
+            put(done)
         except BaseException as exc:  # noqa: BLE001  handed to the consumer
-            box.put(exc)
+            put(exc)
 
     worker = threading.Thread(target=produce, name='b2e-host-feed', daemon=True)
     worker.start()
@@ -71,6 +80,13 @@ def prefetched(dataloader, depth: int = 2):
             yield item
     finally:
         stop.set()
+        # drain so that a producer blocked in put() sees the flag promptly, then wait for it to leave
+        try:
+            while True:
+                box.get_nowait()
+        except queue.Empty:
+            pass
+        worker.join(timeout=5.0)
 
 
 def _fused_kind(encoder: Encoder, pooler: Pooler) -> int | None:
@@ -93,7 +109,8 @@ def compute_embeddings_device(
                       device=encoder.device)
     kind = _fused_kind(encoder, pooler)
     idx = 0
-    for batch in tqdm(prefetched(dataloader), total=len(dataloader), disable=not progress):
+    for batch in tqdm(prefetched(dataloader, device=encoder.device), total=len(dataloader),
+                      disable=not progress):
         inputs = batch.to(encoder.device, non_blocking=True)
         batch_size = inputs['attention_mask'].shape[0]
         if kind is not None:
@@ -108,6 +125,17 @@ def compute_embeddings_device(
     return out
 
 
+def compute_embeddings_pair(
+    dataloader: DataLoader,
+    encoder: Encoder,
+    pooler: Pooler,
+    normalize: bool = False,
+) -> tuple[torch.Tensor, np.ndarray]:
+    """(device fp32 ``[N,H]``, host ``[N,H]`` array in ``encoder.dtype``): one pass, one D2H copy."""
+    device_out = compute_embeddings_device(dataloader, encoder, pooler, normalize)
+    return device_out, device_out.to(encoder.dtype).cpu().numpy()
+
+
 def compute_embeddings(
     dataloader: DataLoader,
     encoder: Encoder,
@@ -115,8 +143,7 @@ def compute_embeddings(
     normalize: bool = False,
 ) -> np.ndarray:
     """Host ``[N,H]`` array in ``encoder.dtype`` (the reference's return contract, :80)."""
-    device_out = compute_embeddings_device(dataloader, encoder, pooler, normalize)
-    return device_out.to(encoder.dtype).cpu().numpy()
+    return compute_embeddings_pair(dataloader, encoder, pooler, normalize)[1]
 
 
 class FullSequenceEmbedderConfig(BaseConfig):
@@ -136,7 +163,7 @@ class FullSequenceEmbedder:
         self.config = config
 
     def embed(self, dataloader: DataLoader, encoder: Encoder, pooler: Pooler) -> EmbedderResult:
-        embeddings = compute_embeddings(
+        device_rows, embeddings = compute_embeddings_pair(
             dataloader=dataloader,
             encoder=encoder,
             pooler=pooler,
@@ -146,4 +173,5 @@ class FullSequenceEmbedder:
             embeddings=embeddings,
             text=dataloader.dataset.data,
             metadata=dataloader.dataset.metadata,
+            device_embeddings=device_rows,
         )

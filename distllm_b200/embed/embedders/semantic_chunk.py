@@ -22,7 +22,7 @@ from distllm_b200 import _native
 from distllm_b200.embed.datasets.utils import DataCollator
 from distllm_b200.embed.datasets.utils import InMemoryDataset
 from distllm_b200.embed.embedders.base import EmbedderResult
-from distllm_b200.embed.embedders.full_sequence import compute_embeddings
+from distllm_b200.embed.embedders.full_sequence import compute_embeddings_pair
 from distllm_b200.embed.embedders.full_sequence import compute_embeddings_device
 from distllm_b200.embed.encoders.base import Encoder
 from distllm_b200.embed.poolers.base import Pooler
@@ -172,10 +172,11 @@ class SemanticChunkEmbedder:
             dataset=chunks,
             collate_fn=DataCollator(encoder.tokenizer),
         )
-        chunk_embeds = compute_embeddings(
+        device_rows, chunk_embeds = compute_embeddings_pair(
             dataloader=chunk_loader,
             encoder=encoder,
             pooler=pooler,
             normalize=cfg.normalize_embeddings,
         )
-        return EmbedderResult(embeddings=chunk_embeds, text=chunks.data, metadata=chunks.metadata)
+        return EmbedderResult(embeddings=chunk_embeds, text=chunks.data, metadata=chunks.metadata,
+                              device_embeddings=device_rows)

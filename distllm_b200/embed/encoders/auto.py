@@ -59,6 +59,7 @@ class AutoEncoder:
                 f'model_type={hf_config.model_type!r} has no native sm_100a forward pass yet '
                 f'(built: {_SUPPORTED_MODEL_TYPES}); there is no eager fallback.',
             )
+        _NATIVE_BY_MODEL_TYPE[hf_config.model_type].validate(hf_config)   # before any weight is loaded
         if config.quantization:
             warnings.warn(
                 'quantization=True (bitsandbytes NF4) is not reproduced by the native encoder; '

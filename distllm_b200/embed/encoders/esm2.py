@@ -22,8 +22,11 @@ class Esm2EncoderConfig(BaseConfig):
     """Config for the ESM-2 encoder (fields as in the reference, esm2.py:15-34)."""
 
     name: Literal['esm2'] = 'esm2'  # type: ignore[assignment]
-    # The model id, options:
-    # [facebook/esm2_t6_8M_UR50D, ..., facebook/esm2_t33_650M_UR50D, ...]
+    # The model id.  The default is the reference's (esm2.py:21); the native kernels are built for
+    # 64-wide attention heads and hidden sizes of 256 x {1,2,3,4,5,8,10,16}: of the published ESM-2 family
+    # that is facebook/esm2_t33_650M_UR50D (H=1280) and facebook/esm2_t36_3B_UR50D (H=2560).  The 8M / 35M /
+    # 150M checkpoints (16-, 24- and 32-wide heads) and the 15B one (128-wide heads) are rejected when the
+    # encoder is built, before any weight is loaded; there is no eager fallback.
     pretrained_model_name_or_path: str = 'facebook/esm2_t6_8M_UR50D'
     # The model tokenizer
     tokenizer_path: str | None = None
@@ -48,6 +51,7 @@ class Esm2Encoder:
         hf_config = AutoConfig.from_pretrained(config.pretrained_model_name_or_path)
         if hf_config.model_type != 'esm':
             raise NotImplementedError(f'model_type={hf_config.model_type!r} is not an ESM checkpoint')
+        NativeEsm2Encoder.validate(hf_config)   # unsupported shapes fail here, before the weights load
         model = EsmForMaskedLM.from_pretrained(config.pretrained_model_name_or_path)
         tokenizer = EsmTokenizer.from_pretrained(
             config.tokenizer_path or config.pretrained_model_name_or_path,

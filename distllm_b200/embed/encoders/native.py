@@ -33,6 +33,9 @@ class NativeBertEncoder:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self.hf_config = hf_config
         self.desc = self._DESC(hf_config)
+        # shape validation BEFORE the weights are converted and uploaded (an unsupported checkpoint must
+        # not cost gigabytes of transfers first)
+        _native.check(lib.b2e_check_model(C.byref(self.desc)))
         self.hidden_size = hf_config.hidden_size
         self.max_positions = hf_config.max_position_embeddings
         self._weights = self._WEIGHTS(state_dict, hf_config.num_hidden_layers, self.device)
@@ -46,6 +49,14 @@ class NativeBertEncoder:
                                              C.byref(handle)))
         self._handle = handle
         self._lib = lib
+
+    @classmethod
+    def validate(cls, hf_config) -> None:
+        """Raise ``NativeError`` / ``NotImplementedError`` when this checkpoint's shape has no native forward
+        pass.  Needs no device and no weights: the encoders call it right after reading ``config.json``,
+        before ``from_pretrained`` loads a single parameter."""
+        desc = cls._DESC(hf_config)
+        _native.check(_native.load().b2e_check_model(C.byref(desc)))
 
     def close(self) -> None:
         if getattr(self, '_handle', None):

@@ -30,6 +30,10 @@ class EmbedderResult:
     embeddings: np.ndarray                       # [N, H]
     text: list[str]                              # N strings
     metadata: list[dict[str, Any]] | None = None
+    # not in the reference (embedders/base.py:17-26): the same rows as a device-resident fp32 tensor, kept
+    # by the native embedders so that the multi-GPU driver can all-gather them without a host round trip;
+    # writers ignore it
+    device_embeddings: torch.Tensor | None = None
 
 
 class Encoder(Protocol):

@@ -39,31 +39,133 @@ def shard_list(items: list, world_size: int, rank: int) -> list:
     return items[lo:hi]
 
 
-def all_gather_rows(local: torch.Tensor, group: dist.ProcessGroup | None = None) -> torch.Tensor:
+def all_gather_rows(local: torch.Tensor | None, group: dist.ProcessGroup | None = None,
+                    device: torch.device | None = None) -> torch.Tensor:
     """Concatenate per-rank row blocks ``[n_r, H]`` in rank order on every rank.
 
-    Row counts differ per rank, so counts are exchanged first (``world`` int64s), blocks are padded
-    to the largest count, gathered with one ``all_gather_into_tensor`` and the padding is dropped.
-    Without an initialised process group this is the identity.
+    Row counts differ per rank, so (count, width) pairs are exchanged first, blocks are padded to the
+    largest count, gathered with ONE ``all_gather_into_tensor`` and the padding is dropped.  A rank
+    with nothing to contribute passes ``None`` or a zero-row tensor (it need not know the width: a rank
+    that received no document never built an encoder) -- every rank still enters both collectives, so
+    no rank can leave the others hanging.  Without an initialised process group this is the identity.
     """
     if not (dist.is_available() and dist.is_initialized()):
+        if local is None:
+            raise ValueError('all_gather_rows(None) needs an initialised process group')
         return local
     world = dist.get_world_size(group)
     if world == 1:
+        if local is None:
+            raise ValueError('all_gather_rows(None) with a world of one')
         return local
-    count = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    counts = torch.empty(world, dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(counts, count, group=group)
-    counts_host = counts.tolist()
+    if local is None:
+        if device is None:
+            raise ValueError('all_gather_rows(None) needs the device the collective runs on')
+        local = torch.empty((0, 0), dtype=torch.float32, device=device)
+    if local.is_cuda and dist.get_backend(group) == 'gloo':
+        # gloo moves host memory: CUDA rows are staged through the host (CPU tests, and two ranks sharing
+        # one GPU in the single-GPU driver test -- NCCL refuses two ranks on one device)
+        return all_gather_rows(local.cpu(), group=group).to(local.device)
+    shape = torch.tensor([local.shape[0], local.shape[1]], dtype=torch.int64, device=local.device)
+    shapes = torch.empty(world * 2, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(shapes, shape, group=group)
+    shapes_host = shapes.view(world, 2).tolist()
+    counts_host = [int(n) for n, _ in shapes_host]
+    widths = {int(h) for n, h in shapes_host if n > 0}
+    if len(widths) > 1:
+        raise ValueError(f'ranks disagree on the embedding width: {sorted(widths)}')
+    width = widths.pop() if widths else int(local.shape[1])
     n_max = max(counts_host)
-    width = local.shape[1]
+    if n_max == 0:
+        return torch.empty((0, width), dtype=local.dtype, device=local.device)
     padded = local
-    if local.shape[0] != n_max:
+    if local.shape[0] != n_max or local.shape[1] != width:
         padded = torch.zeros((n_max, width), dtype=local.dtype, device=local.device)
-        padded[: local.shape[0]] = local
+        if local.shape[0]:
+            padded[: local.shape[0]] = local
     gathered = torch.empty((world * n_max, width), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
     if all(c == n_max for c in counts_host):
         return gathered
     blocks = gathered.view(world, n_max, width)
     return torch.cat([blocks[r, : counts_host[r]] for r in range(world)], dim=0)
+
+
+def all_ranks_ok(ok: bool, device: torch.device, group: dist.ProcessGroup | None = None) -> bool:
+    """Collective AND of a per-rank success flag: every rank learns whether ANY rank failed, so a job
+    aborts on all ranks together instead of one rank raising while the others wait in a collective."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return ok
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return int(flag.item()) == 0
+
+
+# ----------------------------------------------------------------------------------- documents
+# SURVEY 8(e): the unit of sharding is the DOCUMENT, not the file.  A document is one jsonl line, one
+# FASTA record, one line of a sequence-per-line file or one row of a saved HF dataset; a document's
+# sentence buffers never straddle ranks, and with one big input file all GPUs still get work.
+
+
+def count_documents(path, dataset_name: str, header_lines: int = 1) -> int:
+    """Documents in ``path`` as the reader of ``dataset_name`` would see them."""
+    from pathlib import Path
+
+    path = Path(path)
+    if dataset_name in ('jsonl', 'jsonl_chunk'):
+        # the readers split ``read_text().strip()`` on newlines (embed/datasets/jsonl.py)
+        text = path.read_text().strip()
+        return len(text.split('\n')) if text else 0
+    if dataset_name == 'fasta':
+        return sum(1 for line in path.read_text().split('\n') if line.startswith('>'))
+    if dataset_name == 'sequence_per_line':
+        return max(0, len(path.read_text().splitlines()) - header_lines)
+    if dataset_name == 'huggingface':
+        from datasets import Dataset
+
+        return len(Dataset.load_from_disk(str(path)))
+    raise ValueError(f'no document counter for dataset {dataset_name!r}')
+
+
+def plan_document_shards(doc_counts: list[int], world_size: int, rank: int) -> list[tuple[int, int, int]]:
+    """This rank's contiguous range of the global document sequence (files in order, documents in file
+    order), as ``(file_index, lo, hi)`` pieces with ``[lo, hi)`` local to that file."""
+    lo, hi = shard_range(sum(doc_counts), world_size, rank)
+    pieces = []
+    base = 0
+    for i, n in enumerate(doc_counts):
+        a, b = max(lo, base), min(hi, base + n)
+        if a < b:
+            pieces.append((i, a - base, b - base))
+        base += n
+    return pieces
+
+
+def materialize_piece(path, lo: int, hi: int, n_docs: int, dataset_name: str, scratch_dir,
+                      header_lines: int = 1):
+    """A file holding documents ``[lo, hi)`` of ``path`` in the same format.  The whole file is returned
+    as is; a partial piece is written under ``scratch_dir`` (readers take a path, distllm's Dataset
+    protocol has no row-range argument: embed/datasets/base.py:14-40)."""
+    from pathlib import Path
+
+    path = Path(path)
+    if lo == 0 and hi == n_docs:
+        return path
+    scratch_dir = Path(scratch_dir)
+    scratch_dir.mkdir(parents=True, exist_ok=True)
+    out = scratch_dir / f'{path.stem}.docs{lo}-{hi}{path.suffix}'
+    if dataset_name in ('jsonl', 'jsonl_chunk'):
+        out.write_text('\n'.join(path.read_text().strip().split('\n')[lo:hi]) + '\n')
+    elif dataset_name == 'fasta':
+        blocks = ('\n' + path.read_text()).split('\n>')[1:]
+        out.write_text(''.join('>' + b.rstrip('\n') + '\n' for b in blocks[lo:hi]))
+    elif dataset_name == 'sequence_per_line':
+        lines = path.read_text().splitlines()
+        out.write_text('\n'.join(lines[:header_lines] + lines[header_lines + lo:header_lines + hi]) + '\n')
+    elif dataset_name == 'huggingface':
+        from datasets import Dataset
+
+        Dataset.load_from_disk(str(path)).select(range(lo, hi)).save_to_disk(str(out))
+    else:
+        raise ValueError(f'no document slicer for dataset {dataset_name!r}')
+    return out

@@ -88,6 +88,11 @@ const char* b2e_last_error(void);
  * with rows interleaved in blocks of 64 (see B2E_EPI_SWIGLU), desc.sliding_window = 0 means none, and
  * token_type_ids are ignored. */
 int b2e_num_weights(const B2EModelDesc* desc);
+/* Shape validation only (no device, no weights): 0 when b2e_encoder_create would accept `desc`,
+ * else the error it would fail with.  BERT / ESM-2: head_dim 64, heads*64 == H, H in 256 x
+ * {1,2,3,4,5,8,10,16}, I % 128 == 0; Mistral: head_dim 128 (see above).  Call it BEFORE uploading
+ * weights (distllm/embed/encoders/auto.py:59-63 loads the checkpoint unconditionally). */
+int b2e_check_model(const B2EModelDesc* desc);
 int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int n_weights,
                        int device, B2EEncoder** out);
 void b2e_encoder_destroy(B2EEncoder* enc);

@@ -1,0 +1,28 @@
+/* b2e_debug.h -- profiling / experiment hooks of libb2e.so.
+ *
+ * NOT part of the reference-facing ABI (include/b2e.h): nothing in distllm would bind these.  They
+ * exist for the timeline tools under tools/ (att3_timeline.py, gemm_timeline.py, pair_experiments.py)
+ * and are declared here so that every symbol the shared library exports is declared in a header.
+ * All of them write a __device__ global of the kernels' translation unit; 0 on success.
+ */
+#ifndef B2E_DEBUG_H_
+#define B2E_DEBUG_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* device buffer of 4 x 512 int64: CTA 0 of the streaming attention kernels records (clock64, event
+ * code) pairs per role (softmax slot A/B, MMA issuer, loader); NULL switches it off */
+int b2e_debug_set_att3_clock(void* device_buffer);
+/* softmax scheduling experiments of the attention kernels (see attention3.cuh g_att3_flags) */
+int b2e_debug_set_att3_flags(int flags);
+/* CTA-pair GEMM: bit 0 = skip the epilogue's math and stores (experiment) */
+int b2e_debug_set_pair_flags(int flags);
+/* device buffer of 4 x 256 int64 filled with clock64() stamps by CTAs 0/1 of the CTA-pair GEMM */
+int b2e_debug_set_clock_buffer(void* device_buffer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2E_DEBUG_H_ */

@@ -9,6 +9,8 @@ What is recorded (all seeded, fp32, CPU):
                        batches (outputs + the mask after the in-place edit)
   semantic_golden.npz  distllm.embed.embedders.semantic_chunk.calculate_distances_between_buffer and
                        build_chunks on random embeddings, incl. 1- and 2-row documents
+  worker_golden.npz    the reference's own embedding_worker, file in -> files out (jsonl_chunk +
+                       semantic_chunk + mean + numpy writer) on the tiny BERT checkpoint
   bert_tiny_golden.npz the reference's own AutoEncoder + poolers + compute_embeddings
                        (distllm/embed/embedders/full_sequence.py:20-80) driven through a real DataLoader
                        and tokenizer on a tiny seeded BERT checkpoint: token batches, first-batch hidden
@@ -99,6 +101,40 @@ def make_semantic_golden() -> None:
     np.savez_compressed(GOLDEN / 'semantic_golden.npz', **out)
 
 
+def tiny_bert_vocab() -> list[str]:
+    words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
+    return ['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]
+
+
+def tiny_bert_texts() -> list[str]:
+    """The 14 texts behind bert_tiny_golden.npz (80 words -> truncated to 64 tokens)."""
+    words = tiny_bert_vocab()[5:]
+    rng = np.random.default_rng(5)
+    lengths = [3, 17, 40, 1, 25, 25, 9, 62, 80, 12, 30, 2, 44, 7]
+    return [' '.join(rng.choice(words, size=n)) for n in lengths]
+
+
+def write_tiny_bert_checkpoint(ckpt_dir: Path) -> None:
+    """HF checkpoint directory (config.json, weights, tokenizer files) of the tiny seeded BERT."""
+    from transformers import BertConfig
+    from transformers import BertModel
+    from transformers import BertTokenizerFast
+
+    from distllm_b200.embed.encoders.weights import random_bert_state_dict
+
+    cfg = BertConfig(**TINY)
+    sd = random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
+    model = BertModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith('pooler.') for k in missing), (missing, unexpected)
+    ckpt_dir = Path(ckpt_dir)
+    ckpt_dir.mkdir(parents=True, exist_ok=True)
+    (ckpt_dir / 'vocab.txt').write_text('\n'.join(tiny_bert_vocab()) + '\n')
+    tok = BertTokenizerFast(vocab_file=str(ckpt_dir / 'vocab.txt'), do_lower_case=False)
+    model.eval().save_pretrained(ckpt_dir)
+    tok.save_pretrained(ckpt_dir)
+
+
 def make_bert_golden() -> None:
     from torch.utils.data import DataLoader
     from transformers import BertConfig
@@ -118,24 +154,12 @@ def make_bert_golden() -> None:
 
     cfg = BertConfig(**TINY)
     sd = random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
-    model = BertModel(cfg)
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    assert not unexpected and all(k.startswith('pooler.') for k in missing), (missing, unexpected)
-    model.eval()
-
-    words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
-    vocab = ['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]
-    rng = np.random.default_rng(5)
-    n_texts = 14
-    lengths = [3, 17, 40, 1, 25, 25, 9, 62, 80, 12, 30, 2, 44, 7]  # 80 words -> truncated to 64 tokens
-    texts = [' '.join(rng.choice(words, size=n)) for n in lengths]
+    texts = tiny_bert_texts()
+    n_texts = len(texts)
 
     with tempfile.TemporaryDirectory() as tmp:
         tmp_path = Path(tmp)
-        (tmp_path / 'vocab.txt').write_text('\n'.join(vocab) + '\n')
-        tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
-        model.save_pretrained(tmp_path / 'ckpt')
-        tok.save_pretrained(tmp_path / 'ckpt')
+        write_tiny_bert_checkpoint(tmp_path / 'ckpt')
 
         encoder = AutoEncoder(AutoEncoderConfig(
             pretrained_model_name_or_path=str(tmp_path / 'ckpt'), quantization=False, eval_mode=True))
@@ -173,6 +197,39 @@ ESM_VOCAB = ['<cls>', '<pad>', '<eos>', '<unk>', 'L', 'A', 'G', 'V', 'S', 'E', '
              '<mask>']
 
 
+def tiny_esm_seqs() -> list[str]:
+    """The 10 sequences behind esm_tiny_golden.npz (200 residues -> truncated to 160 tokens)."""
+    rng = np.random.default_rng(9)
+    residues = list('LAGVSERTIDPKQNFYMHWC')
+    lengths = [12, 150, 33, 1, 64, 64, 200, 7, 90, 41]
+    seqs = [''.join(rng.choice(residues, size=n)) for n in lengths]
+    seqs[2] = seqs[2][:10] + '<mask>' + seqs[2][10:20] + '<mask>' + seqs[2][20:]  # token-dropout rows
+    return seqs
+
+
+def write_tiny_esm_checkpoint(ckpt_dir: Path) -> None:
+    from transformers import EsmConfig
+    from transformers import EsmForMaskedLM
+    from transformers import EsmTokenizer
+
+    from distllm_b200.embed.encoders.weights import random_esm_state_dict
+
+    cfg = EsmConfig(**TINY_ESM)
+    sd = random_esm_state_dict(cfg, seed=TINY_ESM_SEED, device='cpu')
+    model = EsmForMaskedLM(cfg)
+    missing, unexpected = model.load_state_dict({'esm.' + k: v for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    # missing = parts the hot path never touches (LM head, contact head) and the rotary inv_freq buffers
+    assert all(k.startswith(('lm_head.', 'esm.contact_head.', 'esm.embeddings.position'))
+               or k.endswith('rotary_embeddings.inv_freq') for k in missing), missing
+    ckpt_dir = Path(ckpt_dir)
+    ckpt_dir.mkdir(parents=True, exist_ok=True)
+    (ckpt_dir / 'vocab.txt').write_text('\n'.join(ESM_VOCAB) + '\n')
+    tok = EsmTokenizer(str(ckpt_dir / 'vocab.txt'))
+    model.eval().save_pretrained(ckpt_dir)
+    tok.save_pretrained(ckpt_dir)
+
+
 def make_esm_golden() -> None:
     """The reference's own Esm2Encoder (HF EsmForMaskedLM) + MeanPooler + compute_embeddings on a
     tiny seeded ESM-2 checkpoint with rotary positions and token dropout."""
@@ -192,26 +249,11 @@ def make_esm_golden() -> None:
 
     cfg = EsmConfig(**TINY_ESM)
     sd = random_esm_state_dict(cfg, seed=TINY_ESM_SEED, device='cpu')
-    model = EsmForMaskedLM(cfg)
-    missing, unexpected = model.load_state_dict({'esm.' + k: v for k, v in sd.items()}, strict=False)
-    assert not unexpected, unexpected
-    # missing = parts the hot path never touches (LM head, contact head) and the rotary inv_freq buffers
-    assert all(k.startswith(('lm_head.', 'esm.contact_head.', 'esm.embeddings.position'))
-               or k.endswith('rotary_embeddings.inv_freq') for k in missing), missing
-    model.eval()
-
-    rng = np.random.default_rng(9)
-    residues = list('LAGVSERTIDPKQNFYMHWC')
-    lengths = [12, 150, 33, 1, 64, 64, 200, 7, 90, 41]   # 200 residues -> truncated to 160 tokens
-    seqs = [''.join(rng.choice(residues, size=n)) for n in lengths]
-    seqs[2] = seqs[2][:10] + '<mask>' + seqs[2][10:20] + '<mask>' + seqs[2][20:]  # token-dropout rows
+    seqs = tiny_esm_seqs()
 
     with tempfile.TemporaryDirectory() as tmp:
         tmp_path = Path(tmp)
-        (tmp_path / 'vocab.txt').write_text('\n'.join(ESM_VOCAB) + '\n')
-        tok = EsmTokenizer(str(tmp_path / 'vocab.txt'))
-        model.save_pretrained(tmp_path / 'ckpt')
-        tok.save_pretrained(tmp_path / 'ckpt')
+        write_tiny_esm_checkpoint(tmp_path / 'ckpt')
         encoder = Esm2Encoder(Esm2EncoderConfig(
             pretrained_model_name_or_path=str(tmp_path / 'ckpt'), half_precision=False))
         assert encoder.tokenizer.model_max_length == TINY_ESM['max_position_embeddings']
@@ -241,6 +283,41 @@ TINY_MISTRAL_SEED = 2468
 TINY_MISTRAL_WINDOW = 80   # second variant: same weights, sliding-window attention
 
 
+def tiny_mistral_texts() -> list[str]:
+    """The 12 texts behind mistral_tiny_golden.npz (400 words -> truncated to 320 tokens)."""
+    words = [f'w{i:03d}' for i in range(TINY_MISTRAL['vocab_size'] - 4)]
+    rng = np.random.default_rng(21)
+    lengths = [5, 150, 33, 1, 64, 63, 400, 7, 127, 128, 200, 90]
+    return [' '.join(rng.choice(words, size=n)) for n in lengths]
+
+
+def write_tiny_mistral_checkpoint(ckpt_dir: Path, window: int | None = None) -> None:
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from tokenizers.processors import TemplateProcessing
+    from transformers import MistralConfig
+    from transformers import MistralModel
+    from transformers import PreTrainedTokenizerFast
+
+    from distllm_b200.embed.encoders.weights import random_mistral_state_dict
+
+    words = [f'w{i:03d}' for i in range(TINY_MISTRAL['vocab_size'] - 4)]
+    vocab = {t: i for i, t in enumerate(['<pad>', '<s>', '</s>', '<unk>', *words])}
+    cfg = MistralConfig(**{**TINY_MISTRAL, 'sliding_window': window})
+    sd = random_mistral_state_dict(cfg, seed=TINY_MISTRAL_SEED, device='cpu')
+    model = MistralModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all('rotary_emb' in k for k in missing), (missing, unexpected)
+    raw = Tokenizer(WordLevel(vocab, unk_token='<unk>'))
+    raw.pre_tokenizer = Whitespace()
+    raw.post_processor = TemplateProcessing(single='<s> $A', special_tokens=[('<s>', 1)])
+    tok = PreTrainedTokenizerFast(tokenizer_object=raw, pad_token='<pad>', bos_token='<s>',
+                                  eos_token='</s>', unk_token='<unk>')
+    model.eval().save_pretrained(ckpt_dir)
+    tok.save_pretrained(ckpt_dir)
+
+
 def make_mistral_golden() -> None:
     """The reference's AutoEncoder (HF MistralModel: grouped-query causal attention, rotary, RMSNorm,
     SwiGLU) + LastTokenPooler / MeanPooler + compute_embeddings on a tiny seeded checkpoint, with
@@ -265,30 +342,16 @@ def make_mistral_golden() -> None:
     from distllm.embed.poolers.mean import MeanPoolerConfig
     from distllm_b200.embed.encoders.weights import random_mistral_state_dict
 
-    words = [f'w{i:03d}' for i in range(TINY_MISTRAL['vocab_size'] - 4)]
-    vocab = {t: i for i, t in enumerate(['<pad>', '<s>', '</s>', '<unk>', *words])}
-    rng = np.random.default_rng(21)
-    lengths = [5, 150, 33, 1, 64, 63, 400, 7, 127, 128, 200, 90]   # 400 words -> truncated to 320 tokens
-    texts = [' '.join(rng.choice(words, size=n)) for n in lengths]
+    texts = tiny_mistral_texts()
     out = {'n_texts': np.array(len(texts))}
 
     for variant, window in (('full', None), ('window', TINY_MISTRAL_WINDOW)):
         cfg = MistralConfig(**{**TINY_MISTRAL, 'sliding_window': window})
         sd = random_mistral_state_dict(cfg, seed=TINY_MISTRAL_SEED, device='cpu')
-        model = MistralModel(cfg)
-        missing, unexpected = model.load_state_dict(sd, strict=False)
-        assert not unexpected and all('rotary_emb' in k for k in missing), (missing, unexpected)
-        model.eval()
         out['weights_sha256'] = np.array(weights_digest(sd))
         with tempfile.TemporaryDirectory() as tmp:
             tmp_path = Path(tmp)
-            raw = Tokenizer(WordLevel(vocab, unk_token='<unk>'))
-            raw.pre_tokenizer = Whitespace()
-            raw.post_processor = TemplateProcessing(single='<s> $A', special_tokens=[('<s>', 1)])
-            tok = PreTrainedTokenizerFast(tokenizer_object=raw, pad_token='<pad>', bos_token='<s>',
-                                          eos_token='</s>', unk_token='<unk>')
-            model.save_pretrained(tmp_path / 'ckpt')
-            tok.save_pretrained(tmp_path / 'ckpt')
+            write_tiny_mistral_checkpoint(tmp_path / 'ckpt', window)
             encoder = AutoEncoder(AutoEncoderConfig(
                 pretrained_model_name_or_path=str(tmp_path / 'ckpt'), quantization=False, eval_mode=True))
             assert type(encoder.model).__name__ == 'MistralModel'
@@ -317,6 +380,55 @@ def make_mistral_golden() -> None:
     np.savez_compressed(GOLDEN / 'mistral_tiny_golden.npz', **out)
 
 
+WORKER_DATASET = {'name': 'jsonl_chunk', 'buffer_size': 1, 'min_buffer_length': 20, 'batch_size': 5,
+                  'num_data_workers': 0, 'pin_memory': False}
+WORKER_EMBEDDER = {'name': 'semantic_chunk', 'breakpoint_percentile_threshold': 80, 'chunk_batch_size': 4,
+                   'min_chunk_length': 10}
+
+
+def worker_docs() -> list[dict]:
+    """Three documents of 12-14 short sentences for the semantic-chunk worker golden."""
+    words = tiny_bert_vocab()[5:]
+    rng = np.random.default_rng(0)
+    docs = []
+    for d in range(3):
+        sents = [('S' + ' '.join(rng.choice(words, size=rng.integers(5, 9))) + '. ') for _ in range(12 + d)]
+        docs.append({'text': ''.join(sents), 'path': f'doc{d}'})
+    return docs
+
+
+def make_worker_golden() -> None:
+    """The reference's own ``embedding_worker`` (distllm/distributed_embedding.py:23-80), file in -> files out,
+    on the tiny BERT checkpoint: jsonl_chunk dataset -> semantic_chunk embedder -> mean pooler -> numpy writer.
+    parsl / nltk are the stand-ins of oracle/ref_shims.py (the sentence splitter is the regex one on both
+    sides)."""
+    import json
+
+    from oracle import ref_shims
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp_path = Path(tmp)
+        write_tiny_bert_checkpoint(tmp_path / 'ckpt')
+        f = tmp_path / 'docs.jsonl'
+        f.write_text('\n'.join(json.dumps(d) for d in worker_docs()))
+        timers = ref_shims.run_embedding_worker(
+            f, tmp_path / 'out',
+            dataset_kwargs=dict(WORKER_DATASET),
+            encoder_kwargs={'name': 'auto', 'pretrained_model_name_or_path': str(tmp_path / 'ckpt'),
+                            'quantization': False, 'eval_mode': True},
+            pooler_kwargs={'name': 'mean'},
+            embedder_kwargs=dict(WORKER_EMBEDDER),
+            writer_kwargs={'name': 'numpy'},
+        )
+        assert timers['computed-embeddings'] >= 0
+        out = next((tmp_path / 'out').iterdir())
+        emb = np.load(out / 'embeddings.npy')
+        text = np.load(out / 'text.npy')
+        meta = np.load(out / 'metadata.npy', allow_pickle=True)
+        np.savez_compressed(GOLDEN / 'worker_golden.npz', embeddings=emb, text=text,
+                            paths=np.array([m['path'] for m in meta]))
+
+
 def main() -> None:
     if not REFERENCE.exists():
         raise SystemExit('/root/reference is not available: golden vectors can only be (re)generated '
@@ -330,6 +442,7 @@ def main() -> None:
     make_bert_golden()
     make_esm_golden()
     make_mistral_golden()
+    make_worker_golden()
     for f in sorted(GOLDEN.glob('*.npz')):
         print(f.name, f.stat().st_size, 'bytes')
 

@@ -13,11 +13,53 @@ import torch
 from distllm_b200 import _native
 
 HEADER = Path(__file__).resolve().parents[1] / 'include' / 'b2e.h'
+DEBUG_HEADER = HEADER.with_name('b2e_debug.h')
 
 
-def declared_symbols() -> list[str]:
-    text = re.sub(r'/\*.*?\*/', '', HEADER.read_text(), flags=re.S)
+def declared_symbols(header: Path = HEADER) -> list[str]:
+    text = re.sub(r'/\*.*?\*/', '', header.read_text(), flags=re.S)
     return sorted(set(re.findall(r'\b(b2e_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_every_exported_b2e_symbol_is_declared_in_a_header():
+    """`nm -D` of the shipped library: the b2e_* dynamic symbols are exactly b2e.h (the reference-facing
+    ABI) plus b2e_debug.h (profiling hooks for tools/)."""
+    import shutil
+    import subprocess
+
+    nm = shutil.which('nm')
+    if nm is None:
+        pytest.skip('binutils nm not available')
+    out = subprocess.run([nm, '-D', '--defined-only', str(_native.LIB_PATH)], capture_output=True, text=True,
+                         check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith('b2e_')}
+    assert exported == set(declared_symbols()) | set(declared_symbols(DEBUG_HEADER))
+    assert set(declared_symbols(DEBUG_HEADER)) == set(_native.DEBUG_EXPORTS)
+
+
+def test_check_model_rejects_unsupported_shapes_before_any_upload():
+    """b2e_check_model needs neither a device nor weights (the default ESM-2 checkpoint, H=320
+    with 16-wide heads, must fail before its parameters are converted and uploaded)."""
+    lib = _native.load()
+    ok = _native.ModelDesc(arch=_native.ARCH_ESM2, num_layers=33, hidden=1280, heads=20, kv_heads=20,
+                           head_dim=64, intermediate=5120, vocab=33, max_pos=1026)
+    assert lib.b2e_check_model(C.byref(ok)) == 0
+    big = _native.ModelDesc(arch=_native.ARCH_ESM2, num_layers=36, hidden=2560, heads=40, kv_heads=40,
+                            head_dim=64, intermediate=10240, vocab=33, max_pos=1026)
+    assert lib.b2e_check_model(C.byref(big)) == 0   # esm2_t36_3B
+    tiny = _native.ModelDesc(arch=_native.ARCH_ESM2, num_layers=6, hidden=320, heads=20, kv_heads=20,
+                             head_dim=16, intermediate=1280, vocab=33, max_pos=1026)
+    assert lib.b2e_check_model(C.byref(tiny)) == 3
+    assert b'head_dim 64' in lib.b2e_last_error()
+    odd = _native.ModelDesc(arch=_native.ARCH_BERT, num_layers=2, hidden=1536 + 256, heads=28, kv_heads=28,
+                            head_dim=64, intermediate=4096, vocab=100, max_pos=64)
+    assert lib.b2e_check_model(C.byref(odd)) == 3 and b'hidden size 1792' in lib.b2e_last_error()
+    mistral = _native.ModelDesc(arch=_native.ARCH_MISTRAL, num_layers=32, hidden=4096, heads=32, kv_heads=8,
+                                head_dim=128, intermediate=14336, vocab=32000, max_pos=4096)
+    assert lib.b2e_check_model(C.byref(mistral)) == 0
+    mistral.head_dim = 64
+    assert lib.b2e_check_model(C.byref(mistral)) == 3
+    assert lib.b2e_check_model(None) == 1
 
 
 def test_header_symbols_all_exported():

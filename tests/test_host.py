@@ -473,6 +473,13 @@ def test_prefetched_iteration_keeps_order_and_errors():
     it = prefetched(Loader(1000))                                # abandoned early: the producer stops
     assert [next(it) for _ in range(3)] == [0, 1, 2]
     it.close()
+    # ... and its thread is gone: also when it was blocked on a FULL queue holding the final sentinel
+    # (3 items, depth 2, consumer leaves after the first) or an exception
+    for loader in (Loader(3), Loader(3, fail_at=2)):
+        it = prefetched(loader, depth=2)
+        assert next(it) == 0
+        it.close()
+    assert not [t for t in threading.enumerate() if t.name == 'b2e-host-feed' and t.is_alive()]
     ld4 = Loader(5)
     ld4.num_workers = 4                                          # worker processes: passed through
     assert list(prefetched(ld4)) == list(range(5)) and ld4.threads == {threading.current_thread().name}
@@ -531,3 +538,44 @@ def test_causal_window_chunk_ranges_cover_every_visible_key(window):
                     if not _at4_edge(t, j, window):
                         for i in (128 * t, 128 * t + 127):
                             assert 64 * j + 63 <= i and (not window or i - 64 * j < window)
+
+
+def test_huggingface_dataset_strategy(tmp_path):
+    """`huggingface` dataset strategy (ref embed/datasets/huggingface.py:18-83): text column + optional
+    metadata columns of a save_to_disk directory."""
+    import datasets
+
+    class FakeEncoder:
+        tokenizer = staticmethod(lambda batch, **kw: batch)
+
+    rows = {'text': [f'row {i}' for i in range(5)], 'path': [f'p{i}' for i in range(5)], 'n': list(range(5))}
+    datasets.Dataset.from_dict(rows).save_to_disk(str(tmp_path / 'ds'))
+    cfg = get_dataset({'name': 'huggingface'}).config
+    assert (cfg.text_field, cfg.metadata_fields, cfg.num_data_workers, cfg.batch_size, cfg.pin_memory) == (
+        'text', [], 4, 8, True)
+    plain = get_dataset({'name': 'huggingface', 'num_data_workers': 0, 'pin_memory': False})
+    loader = plain.get_dataloader(tmp_path / 'ds', FakeEncoder())
+    assert loader.dataset.data == rows['text'] and loader.dataset.metadata is None
+    with_meta = get_dataset({'name': 'huggingface', 'metadata_fields': ['path', 'n'], 'num_data_workers': 0,
+                             'pin_memory': False, 'batch_size': 2})
+    loader = with_meta.get_dataloader(tmp_path / 'ds', FakeEncoder())
+    assert loader.dataset.metadata == [{'path': f'p{i}', 'n': i} for i in range(5)]
+    assert loader.batch_size == 2
+
+
+def test_sentence_splitter_choice_is_explicit():
+    """Without nltk the regex stand-in is never silent: 'auto' warns, 'punkt' raises, 'regex' is the opt-in."""
+    import importlib.util
+    import warnings
+
+    if importlib.util.find_spec('nltk') is not None:
+        pytest.skip('nltk installed: the reference splitter is used')
+    with pytest.warns(RuntimeWarning, match='nltk is not installed'):
+        split_by_sentence_tokenizer('auto')
+    with pytest.raises(ImportError, match='nltk is required'):
+        split_by_sentence_tokenizer('punkt')
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        assert ''.join(split_by_sentence_tokenizer('regex')('One. Two.')) == 'One. Two.'
+    with pytest.raises(ValueError):
+        split_by_sentence_tokenizer('other')
