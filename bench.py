@@ -51,7 +51,8 @@ sys.path.insert(0, str(REPO))
 
 # the reference arm is the reference's CPU path: it moves its model to CUDA whenever a device is visible
 # (distllm/embed/encoders/auto.py:86-90), so the devices are hidden BEFORE torch initialises
-if '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:][:1] == ['reference']:
+if '--impl=reference' in sys.argv or (
+        '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:][:1] == ['reference']):
     os.environ['CUDA_VISIBLE_DEVICES'] = ''
 
 import torch  # noqa: E402

@@ -511,6 +511,7 @@ thread_local AttnScratch g_attn_scratch;  // for the standalone attention op
 // ================================================================== encoder handle
 struct B2EEncoder {
   B2EModelDesc desc;
+  int full_layers = 0;   // desc.num_layers as created (b2e_debug_set_layers may lower desc.num_layers)
   std::vector<const void*> w;
   int device = 0;
   int sms = 0;
@@ -817,6 +818,18 @@ int b2e_debug_set_clock_buffer(void* device_buffer) {
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_clock, &p, sizeof(p)));
   return B2E_OK;
 }
+// Run only the first n layers from now on (1 <= n <= the model's depth; 0 restores the full depth).  The
+// output is what a checkpoint truncated to n layers would give: BERT's hidden_states[n]; for the pre-norm
+// families the final norm applied to the residual stream after n layers.  Used by tools/drift_report.py.
+int b2e_debug_set_layers(B2EEncoder* e, int n) {
+  if (!e) return fail(B2E_ERR_INVALID, "null encoder handle");
+  if (n == 0) n = e->full_layers;
+  if (n < 1 || n > e->full_layers)
+    return fail(B2E_ERR_INVALID, "layer count %d outside [1, %d]", n, e->full_layers);
+  if (n != e->desc.num_layers) e->drop_graphs();
+  e->desc.num_layers = n;
+  return B2E_OK;
+}
 const char* b2e_last_error(void) { return g_err.c_str(); }
 
 int b2e_num_weights(const B2EModelDesc* desc) {
@@ -880,6 +893,7 @@ int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_w
   CUDA_TRY(cudaSetDevice(device));
   B2EEncoder* e = new B2EEncoder();
   e->desc = *desc;
+  e->full_layers = desc->num_layers;
   e->w.assign(weights, weights + n_weights);
   e->device = device;
   e->sms = info.sms;
@@ -929,6 +943,7 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
 
   B2EEncoder* e = new B2EEncoder();
   e->desc = *desc;
+  e->full_layers = desc->num_layers;
   e->w.assign(weights, weights + n_weights);
   e->device = device;
   e->sms = info.sms;

@@ -12,6 +12,11 @@
 extern "C" {
 #endif
 
+struct B2EEncoder;
+/* run only the first n layers of an encoder handle from now on (0 = full depth again): the per-layer
+ * drift report (tools/drift_report.py) compares every depth with the CPU oracle */
+int b2e_debug_set_layers(struct B2EEncoder* enc, int n_layers);
+
 /* device buffer of 4 x 512 int64: CTA 0 of the streaming attention kernels records (clock64, event
  * code) pairs per role (softmax slot A/B, MMA issuer, loader); NULL switches it off */
 int b2e_debug_set_att3_clock(void* device_buffer);

@@ -49,8 +49,12 @@ def esm_forward(
     hf_config,
     input_ids: torch.Tensor,
     attention_mask: torch.Tensor,
-) -> torch.Tensor:
-    """Last hidden state ``[B,S,H]`` fp32 (== ``EsmForMaskedLM(...).hidden_states[-1]``)."""
+    return_all: bool = False,
+):
+    """Last hidden state ``[B,S,H]`` fp32 (== ``EsmForMaskedLM(...).hidden_states[-1]``).
+
+    ``return_all``: list over l = 1..L of ``emb_layer_norm_after(residual stream after l layers)`` -- what a
+    model truncated to l layers would return (used by the per-layer drift report)."""
     sd = _sd(state_dict)
     eps = hf_config.layer_norm_eps
     heads = hf_config.num_attention_heads
@@ -70,6 +74,7 @@ def esm_forward(
     key_bias = torch.zeros(b, 1, 1, s)
     key_bias.masked_fill_(attention_mask.view(b, 1, 1, s) == 0, torch.finfo(torch.float32).min)
 
+    states = []
     for layer in range(hf_config.num_hidden_layers):
         p = f'encoder.layer.{layer}.'
 
@@ -91,5 +96,10 @@ def esm_forward(
         inter = lin(y, 'intermediate.dense')
         inter = inter * 0.5 * (1.0 + torch.erf(inter / math.sqrt(2.0)))
         x = x + lin(inter, 'output.dense')
+        if return_all:
+            states.append(F.layer_norm(x, (h,), sd['encoder.emb_layer_norm_after.weight'],
+                                       sd['encoder.emb_layer_norm_after.bias'], eps))
+    if return_all:
+        return states
     return F.layer_norm(x, (h,), sd['encoder.emb_layer_norm_after.weight'],
                         sd['encoder.emb_layer_norm_after.bias'], eps)

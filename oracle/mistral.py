@@ -29,11 +29,20 @@ import torch
 import torch.nn.functional as F  # noqa: N812
 
 
-def _sd(state_dict: Mapping[str, torch.Tensor]) -> dict[str, torch.Tensor]:
-    return {
-        (k[6:] if k.startswith('model.') else k): v.detach().to('cpu', torch.float32)
-        for k, v in state_dict.items()
-    }
+class _LazyF32:
+    """State-dict view that strips the ``model.`` prefix and converts a tensor to CPU fp32 only when it is
+    read: a 7B-parameter checkpoint (28 GB as fp32) is then walked one projection at a time, e.g. straight
+    from bf16 device tensors."""
+
+    def __init__(self, state_dict: Mapping[str, torch.Tensor]) -> None:
+        self._sd = {(k[6:] if k.startswith('model.') else k): v for k, v in state_dict.items()}
+
+    def __getitem__(self, key: str) -> torch.Tensor:
+        return self._sd[key].detach().to('cpu', torch.float32)
+
+
+def _sd(state_dict: Mapping[str, torch.Tensor]) -> _LazyF32:
+    return _LazyF32(state_dict)
 
 
 def rope_theta_of(hf_config) -> float:
@@ -75,8 +84,12 @@ def mistral_forward(
     hf_config,
     input_ids: torch.Tensor,
     attention_mask: torch.Tensor,
-) -> torch.Tensor:
-    """Last hidden state ``[B,S,H]`` fp32 (== ``MistralModel(...).hidden_states[-1]``)."""
+    return_all: bool = False,
+):
+    """Last hidden state ``[B,S,H]`` fp32 (== ``MistralModel(...).hidden_states[-1]``).
+
+    ``return_all``: list over l = 1..L of ``final_norm(residual stream after l layers)`` -- what a model
+    truncated to l layers would return (the per-layer drift report compares against these)."""
     sd = _sd(state_dict)
     eps = hf_config.rms_norm_eps
     heads, kv_heads = hf_config.num_attention_heads, hf_config.num_key_value_heads
@@ -88,6 +101,7 @@ def mistral_forward(
     dead = ~vis.any(-1, keepdim=True)  # [B,1,S,1] query rows without a visible key
 
     x = sd['embed_tokens.weight'][input_ids]
+    states = []
     for layer in range(hf_config.num_hidden_layers):
         p = f'layers.{layer}.'
         y = _rms(x, sd[p + 'input_layernorm.weight'], eps)
@@ -106,4 +120,6 @@ def mistral_forward(
         gate = F.linear(y, sd[p + 'mlp.gate_proj.weight'])
         up = F.linear(y, sd[p + 'mlp.up_proj.weight'])
         x = x + F.linear(F.silu(gate) * up, sd[p + 'mlp.down_proj.weight'])
-    return _rms(x, sd['norm.weight'], eps)
+        if return_all:
+            states.append(_rms(x, sd['norm.weight'], eps))
+    return states if return_all else _rms(x, sd['norm.weight'], eps)

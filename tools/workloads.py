@@ -36,7 +36,7 @@ def write_bert_checkpoint(ckpt_dir: Path, cfg: dict | None = None, seed: int = 0
     ckpt_dir.mkdir(parents=True, exist_ok=True)
     state = torch.random.get_rng_state()
     torch.manual_seed(seed)
-    model = BertModel(BertConfig(**cfg), add_pooling_layer=False).eval()
+    model = BertModel(BertConfig(**cfg)).eval()
     torch.random.set_rng_state(state)
     # HF zero-initialises every bias and sets LayerNorm to (1, 0); give them small seeded values so that
     # the bias / gamma / beta paths carry information on both arms
@@ -86,3 +86,38 @@ def write_semantic_docs(path: Path, n_docs: int, n_sentences: int, vocab_size: i
                      + '. ' for _ in range(n_sentences)]
             f.write(json.dumps({'text': ''.join(sents), 'path': f'doc{d}'}) + '\n')
     return Path(path)
+
+
+# ------------------------------------------------------------------------------- outlier weights
+# Trained checkpoints are not N(0, 0.02): a handful of hidden channels carry values tens of times larger
+# than the rest and the LayerNorm / RMSNorm gains spread over orders of magnitude.  The parity tests run
+# every family on such weights too.
+
+_OUT_ROWS = {
+    'bert': ('attention.output.dense.weight', 'output.dense.weight'),
+    'esm': ('attention.output.dense.weight', 'output.dense.weight'),
+    'mistral': ('self_attn.o_proj.weight', 'mlp.down_proj.weight'),
+}
+
+
+def add_outliers(state_dict: dict, family: str, seed: int = 0, n_channels: int = 4, scale: float = 50.0,
+                 gain_range: tuple[float, float] = (0.1, 10.0)) -> dict:
+    """In place: (i) the rows of every block-output projection that write ``n_channels`` fixed hidden
+    channels are multiplied by ``scale`` (those channels of the residual stream become massive), (ii) every
+    norm gain is redrawn log-uniformly from ``gain_range`` and every norm bias from N(0, 0.5).  Works on HF
+    state-dict names of BertModel / EsmModel / MistralModel (any device / dtype); returns the dict."""
+    g = torch.Generator().manual_seed(seed)
+    out_names = _OUT_ROWS[family]
+    hidden = next(v.shape[0] for k, v in state_dict.items() if k.endswith(out_names[0]))
+    channels = torch.randperm(hidden, generator=g)[:n_channels]
+    lo, hi = float(np.log(gain_range[0])), float(np.log(gain_range[1]))
+    for name, t in state_dict.items():
+        if name.endswith(out_names):
+            t[channels.to(t.device)] *= scale
+        elif t.dim() == 1 and ('LayerNorm.weight' in name or 'layer_norm_after.weight' in name
+                               or name.endswith('layernorm.weight') or name == 'norm.weight'):
+            gain = torch.exp(torch.rand(t.shape, generator=g) * (hi - lo) + lo)
+            t.copy_(gain.to(device=t.device, dtype=t.dtype))
+        elif t.dim() == 1 and ('LayerNorm.bias' in name or 'layer_norm_after.bias' in name):
+            t.copy_((0.5 * torch.randn(t.shape, generator=g)).to(device=t.device, dtype=t.dtype))
+    return state_dict
