@@ -50,6 +50,7 @@ DEBUG_EXPORTS = (
     'b2e_debug_set_pair_flags',
     'b2e_debug_set_clock_buffer',
     'b2e_debug_set_layers',
+    'b2e_debug_set_att3_variant',
 )
 
 

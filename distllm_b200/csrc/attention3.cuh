@@ -46,24 +46,36 @@ constexpr float AT3_RESCALE_THRESHOLD = 8.0f;
 
 // bias[b, j] for j < S_pad (multiple of 64) and kv_chunks[b] = chunks holding an attended key
 // (all chunks when nothing is attended, so that such a row degenerates to HF's uniform softmax).
+// plain_chunks[b] (nullable) = number of LEADING chunks whose 64 keys are all attended: on those the softmax
+// needs neither the bias row nor a vote over it (right-padded batches: every chunk but the last one or two).
 __global__ void attn_prep_kernel(const int64_t* __restrict__ mask, float* __restrict__ bias,
-                                 int* __restrict__ kv_chunks, int B, int S, int S_pad) {
+                                 int* __restrict__ kv_chunks, int* __restrict__ plain_chunks, int B, int S,
+                                 int S_pad) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
   int last = 0;
+  int first_off = S_pad;   // first key position that is NOT attended (padding beyond S counts)
   for (int j = lane; j < S_pad; j += 32) {
     float v = -INFINITY;
+    bool on = false;
     if (j < S) {
-      const bool on = mask[static_cast<size_t>(b) * S + j] != 0;
+      on = mask[static_cast<size_t>(b) * S + j] != 0;
       v = on ? 0.0f : AT3_MASKED;
       if (on) last = j + 1;
     }
+    if (!on) first_off = min(first_off, j);
     bias[static_cast<size_t>(b) * S_pad + j] = v;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-  if (lane == 0) kv_chunks[b] = last > 0 ? (last + AT3_KC - 1) / AT3_KC : S_pad / AT3_KC;
+  for (int o = 16; o > 0; o >>= 1) {
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    first_off = min(first_off, __shfl_xor_sync(0xffffffffu, first_off, o));
+  }
+  if (lane == 0) {
+    kv_chunks[b] = last > 0 ? (last + AT3_KC - 1) / AT3_KC : S_pad / AT3_KC;
+    if (plain_chunks != nullptr) plain_chunks[b] = first_off / AT3_KC;
+  }
 }
 
 // ---- softmax helpers over 32 register-resident scores (x = scale*s + bias formed on the fly)
@@ -109,15 +121,37 @@ __device__ __forceinline__ float at3_smax_plain(const uint32_t (&s)[32], float m
   for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(s[i]));
   return m;
 }
+// 2^x on the FMA / ALU pipes instead of the MUFU pipe (16 ex2 per clock and SM is what bounds head_dim-64
+// attention): Cody-Waite range reduction n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax
+// polynomial (relative error ~1e-4, the result is rounded to bf16 = 4e-3 anyway), n added to the exponent
+// field as an integer.  x is clamped at -126 (no denormal / wrap-around for very negative scores).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;   // 1.5 * 2^23: round-to-nearest integer part in the low mantissa bits
+  const float n = t - 12582912.0f;
+  const float f = x - n;
+  float p = 0.0555054f;
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// POLY = how many of every four exponentials run on the FMA pipe (0, 1 or 2)
+template <int POLY>
 __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], float scale, float neg_m,
                                                     uint32_t* pk) {
   float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    const float p0 = fast_exp2(fmaf(__uint_as_float(s[i + 0]), scale, neg_m));
-    const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale, neg_m));
-    const float p2 = fast_exp2(fmaf(__uint_as_float(s[i + 2]), scale, neg_m));
-    const float p3 = fast_exp2(fmaf(__uint_as_float(s[i + 3]), scale, neg_m));
+    const float x0 = fmaf(__uint_as_float(s[i + 0]), scale, neg_m);
+    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale, neg_m);
+    const float x2 = fmaf(__uint_as_float(s[i + 2]), scale, neg_m);
+    const float x3 = fmaf(__uint_as_float(s[i + 3]), scale, neg_m);
+    const float p0 = fast_exp2(x0);
+    const float p1 = POLY >= 2 ? poly_exp2(x1) : fast_exp2(x1);
+    const float p2 = fast_exp2(x2);
+    const float p3 = POLY >= 1 ? poly_exp2(x3) : fast_exp2(x3);
     sum0 += p0 + p1;
     sum1 += p2 + p3;
     pk[i / 2] = pack_bf16x2(p0, p1);
@@ -128,17 +162,19 @@ __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], flo
 
 // One work item = (sequence b, head h, pair of query tiles pr); n = key chunks to visit.
 struct At3Item {
-  int b, h, pr, n;
+  int b, h, pr, n, np;   // np: leading chunks whose 64 keys are all attended
 };
 __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
-                                              const int* __restrict__ kv_chunks, int n_items) {
-  At3Item it{0, 0, 0, 0};
+                                              const int* __restrict__ kv_chunks,
+                                              const int* __restrict__ plain_chunks, int n_items) {
+  At3Item it{0, 0, 0, 0, 0};
   if (item < n_items) {
     it.pr = item % npairs;
     const int bh = item / npairs;
     it.h = bh % heads;
     it.b = bh / heads;
     it.n = __ldg(kv_chunks + it.b);
+    it.np = plain_chunks != nullptr ? __ldg(plain_chunks + it.b) : 0;
   }
   return it;
 }
@@ -147,11 +183,18 @@ __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
 __device__ long long* g_att3_clock = nullptr;
 __device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the exp phase, 2 (default) de-phase once per item
 
+// V (softmax variant, measured side by side in tools/att_bench.py):
+//   bit 0  plain chunks come from plain_chunks[b]: no wait for / vote over the bias row on them
+//   bit 1  S_{j+1} is fetched from TMEM right behind the store of P_j, so that tcgen05.ld's latency runs
+//          under the publish (st wait, fence, arrive) instead of in front of the next chunk's exponentials
+//   bits 2-3  exponentials per four that run on the FMA pipe (plain chunks only): 0, 1 or 2
+template <int V>
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
                       const __grid_constant__ CUtensorMap tm_kv,  // [T, 3H] bf16, box 64 x 64
                       const float* __restrict__ bias,             // [B, S_pad]
                       const int* __restrict__ kv_chunks,          // [B]
+                      const int* __restrict__ plain_chunks,       // [B] or nullptr
                       const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] bf16, box 64 x 128 x 1
                       int B, int S, int S_pad, int heads, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -226,9 +269,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
           const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = b * S;
           const int buf = it & 1;
@@ -278,9 +321,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
           const int n = cur.n;
           const int buf = it & 1;
           const bool active = 2 * cur.pr + slot < nq;
@@ -363,7 +406,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
-    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, n_items);
+    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
     // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
     // is ordered (A before B), which merely de-phases the two warpgroups
@@ -373,7 +416,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
-      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, n_items);
+      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
       const int pr = cur.pr, h = cur.h, b = cur.b, n = cur.n;
       const int t = 2 * pr + slot;
       if (t >= nq && pingpong) {
@@ -384,23 +427,49 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         }
       }
       if (t < nq) {
+        constexpr bool kPlainCount = (V & 1) != 0;
+        constexpr bool kPrefetch = (V & 2) != 0;
+        constexpr int kPoly = (V >> 2) & 3;
+        const int n_plain = cur.np;
         float m_used = 0.0f, l = 0.0f;
+        uint32_t s0[32], s1[32];
+        // wait for S_j = Q K_j^T and start moving it from TMEM into registers (completed by tmem_ld_wait)
+        auto fetch_scores = [&](int j) {
+          const int sbuf = j & 1;
+          mbar_wait(s_ready + 8u * (slot * 2 + sbuf), (s_par >> sbuf) & 1u);
+          s_par ^= 1u << sbuf;
+          tc_fence_after();
+          const uint32_t t_s = t_slot + static_cast<uint32_t>(sbuf * 64);
+          tmem_ld32(t_s, s0);
+          tmem_ld32(t_s + 32u, s1);
+        };
+        if (kPrefetch) {
+          fetch_scores(0);
+          tmem_ld_wait();
+        }
         for (int j = 0; j < n; ++j) {
           const int sbuf = j & 1;
           const uint32_t c = chunk_base + j;
           const int st = c % AT3_NST;
           if (r == 0) AT3_STAMP(slot, j * 10 + 0);
-          mbar_wait(s_ready + 8u * (slot * 2 + sbuf), (s_par >> sbuf) & 1u);
-          s_par ^= 1u << sbuf;
+          if (!kPrefetch) {
+            fetch_scores(j);
+            tmem_ld_wait();
+          }
           if (r == 0) AT3_STAMP(slot, j * 10 + 1);
-          mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);  // already complete: acquires the bias bytes
-          tc_fence_after();
           const float* bias_j = reinterpret_cast<const float*>(smem + AT3_SMEM_BIAS + st * AT3_KC * 4);
           const uint32_t t_s = t_slot + static_cast<uint32_t>(sbuf * 64);
-          uint32_t s0[32], s1[32];
-          tmem_ld32(t_s, s0);
-          tmem_ld32(t_s + 32u, s1);
-          tmem_ld_wait();
+          // all 64 keys of the chunk attended?  Either known from the prepared per-sequence count (no
+          // shared-memory traffic at all on such chunks), or by a warp vote over the chunk's bias row
+          bool plain;
+          if (kPlainCount) {
+            plain = j < n_plain;
+            if (!plain) mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);  // complete: acquires the bias bytes
+          } else {
+            mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);  // already complete: acquires the bias bytes
+            const float2 bz = *reinterpret_cast<const float2*>(bias_j + 2 * (threadIdx.x & 31));
+            plain = !__any_sync(0xffffffffu, bz.x != 0.0f || bz.y != 0.0f);
+          }
           // Optional ping-pong (experiment, b2e_debug_set_att3_flags bit 0): the exp-heavy part of a chunk
           // runs in ONE warpgroup at a time.  Measured: a warpgroup alone still needs ~950 clk for the 64
           // exponentials per thread (issue/latency bound, MUFU alone would be 512), so strict alternation
@@ -408,29 +477,25 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           const bool turn = (pp_mode & 1) || (pp_mode == 2 && j == 0);
           if (turn) asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           uint32_t pk[32];
-          // all 64 keys of the chunk attended?  (warp vote over the chunk's bias row in shared memory)
-          bool plain;
-          {
-            const float2 bz = *reinterpret_cast<const float2*>(bias_j + 2 * (threadIdx.x & 31));
-            plain = !__any_sync(0xffffffffu, bz.x != 0.0f || bz.y != 0.0f);
-          }
           bool done = false;
           if (plain) {
             if (j == 0) {
               // exact maximum of the raw scores first (scale > 0: max commutes with the scaling)
               m_used = scale_log2e * at3_smax_plain(s1, at3_smax_plain(s0, -INFINITY));
-              l = at3_exp_pack_plain(s0, scale_log2e, -m_used, pk);
-              l += at3_exp_pack_plain(s1, scale_log2e, -m_used, pk + 16);
+              l = at3_exp_pack_plain<kPoly>(s0, scale_log2e, -m_used, pk);
+              l += at3_exp_pack_plain<kPoly>(s1, scale_log2e, -m_used, pk + 16);
               done = true;
             } else {
-              float sum = at3_exp_pack_plain(s0, scale_log2e, -m_used, pk);
-              sum += at3_exp_pack_plain(s1, scale_log2e, -m_used, pk + 16);
+              float sum = at3_exp_pack_plain<kPoly>(s0, scale_log2e, -m_used, pk);
+              sum += at3_exp_pack_plain<kPoly>(s1, scale_log2e, -m_used, pk + 16);
               // every p <= row sum: a sum within 2^threshold proves that no score ran away
               // (a NaN sum -- inf - inf cannot occur here -- would fail the test and take the general path)
               const bool calm = sum <= 256.0f;   // 2^AT3_RESCALE_THRESHOLD
               if (__all_sync(0xffffffffu, calm)) {
                 l += sum;
                 done = true;
+              } else if (kPlainCount) {
+                mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);   // the general path reads the bias row
               }
             }
           }
@@ -478,9 +543,13 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           if (turn) asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
           if (r == 0) AT3_STAMP(slot, j * 10 + 2);
           tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
+          // S_{j+1} (the other buffer; its Q K^T was issued before P_{j-1} V_{j-1}) starts to move into the
+          // score registers now: the load runs under the store's wait, the fence and the arrive
+          if (kPrefetch && j + 1 < n) fetch_scores(j + 1);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(p_ready + 8u * (slot * 2 + sbuf));
+          if (kPrefetch && j + 1 < n) tmem_ld_wait();
           if (r == 0) AT3_STAMP(slot, j * 10 + 3);
         }
         // ---- epilogue: O / l -> bf16 -> swizzled staging tile -> one TMA store per tile

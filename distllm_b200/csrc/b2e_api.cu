@@ -285,6 +285,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
 struct AttnScratch {
   float* bias = nullptr;   // [B, S_pad]
   int* kv_chunks = nullptr;  // [B]
+  int* plain_chunks = nullptr;  // [B]  leading fully-attended chunks
   size_t cap_bias = 0, cap_b = 0;
   uint64_t gen = 0;   // bumped on every reallocation
   int device = -1;    // the buffers live on this device; a call from another one starts over
@@ -307,17 +308,18 @@ struct AttnScratch {
       cap_bias = (size_t)B * S_pad;
     }
     if ((size_t)B > cap_b) {
-      cudaFree(kv_chunks);
-      kv_chunks = nullptr;
+      cudaFree(kv_chunks); cudaFree(plain_chunks);
+      kv_chunks = plain_chunks = nullptr;
       cap_b = 0;
       CUDA_TRY(cudaMalloc(&kv_chunks, sizeof(int) * B));
+      CUDA_TRY(cudaMalloc(&plain_chunks, sizeof(int) * B));
       cap_b = B;
     }
     return B2E_OK;
   }
   void release() {
-    cudaFree(bias); cudaFree(kv_chunks);
-    bias = nullptr; kv_chunks = nullptr; cap_bias = cap_b = 0;
+    cudaFree(bias); cudaFree(kv_chunks); cudaFree(plain_chunks);
+    bias = nullptr; kv_chunks = plain_chunks = nullptr; cap_bias = cap_b = 0;
   }
 };
 
@@ -327,7 +329,32 @@ int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaSt
   int rc;
   const int S_pad = attn_s_pad(S);
   if ((rc = sc.ensure(B, S_pad))) return rc;
-  attn_prep_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, sc.bias, sc.kv_chunks, B, S, S_pad);
+  attn_prep_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, sc.bias, sc.kv_chunks, sc.plain_chunks, B, S, S_pad);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+// Softmax variant of the head_dim-64 attention kernel (template parameter V of attention3_d64_kernel);
+// B2E_ATT3=<n> or b2e_debug_set_att3_variant picks one of the instantiated ones for A/B measurements.
+constexpr int AT3_DEFAULT_VARIANT = 0;
+int g_att3_variant = -1;
+inline int att3_variant() {
+  if (g_att3_variant < 0) {
+    const char* e = getenv("B2E_ATT3");
+    g_att3_variant = e ? atoi(e) : AT3_DEFAULT_VARIANT;
+  }
+  return g_att3_variant;
+}
+
+template <int V>
+int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
+                       const CUtensorMap& tctx, int B, int S, int heads, int grid, float scale_log2e,
+                       cudaStream_t st) {
+  auto kern = attention3_d64_kernel<V>;
+  const int arc = ensure_smem_attr(kern, AT3_SMEM_BYTES);
+  if (arc) return arc;
+  kern<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
+                                                  attn_s_pad(S), heads, scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -336,20 +363,22 @@ int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaSt
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc, void* ctx,
                      int B, int S, int heads, int sms, cudaStream_t st) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  {
-    const int arc = ensure_smem_attr(attention3_d64_kernel, AT3_SMEM_BYTES);
-    if (arc) return arc;
-  }
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
   const int grid = items < sms ? (int)items : sms;
   CUtensorMap tctx;  // [B, S, H]: the output store clips rows >= S per sequence
   int rc;
   if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
-  attention3_d64_kernel<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(
-      tq, tkv, sc.bias, sc.kv_chunks, tctx, B, S, attn_s_pad(S), heads, scale_log2e);
-  CUDA_TRY(cudaGetLastError());
-  return B2E_OK;
+  switch (att3_variant()) {
+    case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 2: return launch_attention_v<2>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 3: return launch_attention_v<3>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 7: return launch_attention_v<7>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 11: return launch_attention_v<11>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 5: return launch_attention_v<5>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+  }
+  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11)", att3_variant());
 }
 
 // Causal grouped-query attention, head_dim 128 (attention4.cuh).  qkv is [B*S, (heads + 2 kv_heads)*128]
@@ -807,6 +836,11 @@ int b2e_debug_set_att3_flags(int flags) {
   return B2E_OK;
 }
 
+int b2e_debug_set_att3_variant(int variant) {
+  g_att3_variant = variant;
+  return B2E_OK;
+}
+
 // Experiment knob for the CTA-pair GEMM: bit 0 = skip the epilogue's math and stores.
 int b2e_debug_set_pair_flags(int flags) {
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_flags, &flags, sizeof(flags)));
@@ -1071,7 +1105,6 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
   PoolScratch& ps = e->pool;
   if (d.arch == B2E_ARCH_MISTRAL) {
     if ((rc = run_mistral_trunk(e, ids, mask, B, S, st))) return rc;
-    const int M = B * S;
     if (pool_kind == B2E_POOL_LAST_TOKEN) {
       // only the B selected rows go through the final norm (fp32 end to end)
       seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
@@ -1082,38 +1115,37 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
       CUDA_TRY(cudaGetLastError());
       return B2E_OK;
     }
-    DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, (const float*)e->w[1], e->hidden, M, d.eps)));
+    // mean poolers: final RMSNorm fused with the masked sum, fp32 end to end, [B,S,H] never written
     if ((rc = launch_pool_weights(ps, const_cast<int64_t*>(mask), B, S, pool_kind, 0, st))) return rc;
     const int nsplit = pool_nsplit(S);
     const int rows_per = (S + nsplit - 1) / nsplit;
     dim3 grid(B, nsplit);
-    DISPATCH_NV(H, (pool_sum_kernel<NV, bf16><<<grid, ROW_THREADS, 0, st>>>(e->hidden, ps.w, ps.part, S,
-                                                                          rows_per)));
+    DISPATCH_NV(H, (addnorm_pool_kernel<NV, true><<<grid, ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->w[1], nullptr, ps.w, ps.part, S, rows_per, d.eps)));
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
   if (d.arch == B2E_ARCH_ESM2) {
     if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
-    const int M = B * S;
-    // final LayerNorm into the bf16 hidden buffer, then the standalone pooling kernels over it
-    DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], e->hidden, M,
-                       d.eps)));
     if (pool_kind == B2E_POOL_LAST_TOKEN) {
+      // only the B selected rows go through emb_layer_norm_after (fp32 end to end)
       seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
       last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
-      gather_rows_kernel<bf16><<<B, 128, 0, st>>>(e->hidden, ps.idx, out, B, S, H);
+      DISPATCH_NV(H, (addnorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], ps.idx, out, B, S,
+                         d.eps)));
       if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
       CUDA_TRY(cudaGetLastError());
       return B2E_OK;
     }
+    // mean poolers: final LayerNorm fused with the masked sum, fp32 end to end, [B,S,H] never written
     if ((rc = launch_pool_weights(ps, const_cast<int64_t*>(mask), B, S, pool_kind, 0, st))) return rc;
     const int nsplit = pool_nsplit(S);
     const int rows_per = (S + nsplit - 1) / nsplit;
     dim3 grid(B, nsplit);
-    DISPATCH_NV(H, (pool_sum_kernel<NV, bf16><<<grid, ROW_THREADS, 0, st>>>(e->hidden, ps.w, ps.part, S,
-                                                                          rows_per)));
+    DISPATCH_NV(H, (addnorm_pool_kernel<NV, false><<<grid, ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], ps.w, ps.part, S,
+                       rows_per, d.eps)));
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }

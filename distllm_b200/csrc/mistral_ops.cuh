@@ -104,6 +104,75 @@ rmsnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ a
   for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(b) * H + v * 256 + lane * 8, x[v]);
 }
 
+// ESM-2 last-token pooling: out[b] = LayerNorm(xres[row] + add[row]) for the B selected rows (fp32 [B,H]).
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS)
+addnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const int* __restrict__ idx, float* __restrict__ out, int B, int S, float eps) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const size_t row = static_cast<size_t>(b) * S + idx[b];
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = row * H + v * 256 + lane * 8;
+    float a[8];
+    load8(xres + off, x[v]);
+    load8(add + off, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[v][e] += a[e];
+  }
+  warp_layernorm<NV>(x, gamma, beta, lane, eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(b) * H + v * 256 + lane * 8, x[v]);
+}
+
+// Final norm of the pre-norm families fused with the masked-sum pooling (the [B,S,H] final hidden state is
+// never written): x = xres + add, then LayerNorm (RMS == false: ESM-2's emb_layer_norm_after) or RMSNorm
+// (RMS == true: Mistral's final norm), weighted by the pooling weights and summed per block.
+// grid = (B, nsplit); each warp walks rows s = split*rows_per + warp, += ROW_WARPS (as layernorm_pool_kernel).
+template <int NV, bool RMS>
+__global__ void __launch_bounds__(ROW_THREADS)
+addnorm_pool_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ w, float* __restrict__ part, int S, int rows_per, float eps) {
+  constexpr int H = NV * 256;
+  __shared__ float red[H];
+  const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[v][e] = 0.0f;
+  const int s_end = min(S, (split + 1) * rows_per);
+  for (int s = split * rows_per + warp; s < s_end; s += ROW_WARPS) {
+    const float wv = w[static_cast<size_t>(b) * S + s];
+    if (wv == 0.0f) continue;  // warp-uniform
+    float x[NV][8];
+    const size_t row = static_cast<size_t>(b) * S + s;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const size_t off = row * H + v * 256 + lane * 8;
+      float a[8];
+      load8(xres + off, x[v]);
+      load8(add + off, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[v][e] += a[e];
+    }
+    if (RMS) warp_rmsnorm<NV>(x, gamma, lane, eps);
+    else warp_layernorm<NV>(x, gamma, beta, lane, eps);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[v][e] = fmaf(x[v][e], wv, acc[v][e]);
+  }
+  block_store_partial<NV>(acc, red, part + (static_cast<size_t>(b) * nsplit + split) * H, warp, lane);
+}
+
 // cos/sin tables [max_pos, half]: angle(p, i) = p * theta^(-2i / (2*half))
 __global__ void rope_table_theta_kernel(float* __restrict__ cos_t, float* __restrict__ sin_t,
                                         int max_pos, int half, float theta) {

@@ -22,6 +22,8 @@ int b2e_debug_set_layers(struct B2EEncoder* enc, int n_layers);
 int b2e_debug_set_att3_clock(void* device_buffer);
 /* softmax scheduling experiments of the attention kernels (see attention3.cuh g_att3_flags) */
 int b2e_debug_set_att3_flags(int flags);
+/* which instantiated softmax variant of attention3_d64_kernel<V> the next launches use (also B2E_ATT3) */
+int b2e_debug_set_att3_variant(int variant);
 /* CTA-pair GEMM: bit 0 = skip the epilogue's math and stores (experiment) */
 int b2e_debug_set_pair_flags(int flags);
 /* device buffer of 4 x 256 int64 filled with clock64() stamps by CTAs 0/1 of the CTA-pair GEMM */

@@ -130,7 +130,7 @@ def write_tiny_bert_checkpoint(ckpt_dir: Path) -> None:
     ckpt_dir = Path(ckpt_dir)
     ckpt_dir.mkdir(parents=True, exist_ok=True)
     (ckpt_dir / 'vocab.txt').write_text('\n'.join(tiny_bert_vocab()) + '\n')
-    tok = BertTokenizerFast(vocab_file=str(ckpt_dir / 'vocab.txt'), do_lower_case=False)
+    tok = BertTokenizerFast(vocab=str(ckpt_dir / 'vocab.txt'), do_lower_case=False)
     model.eval().save_pretrained(ckpt_dir)
     tok.save_pretrained(ckpt_dir)
 

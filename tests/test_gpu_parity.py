@@ -223,7 +223,7 @@ def test_semantic_chunk_embedder_end_to_end(tmp_path, tiny_bert, tiny_native):
     cfg, sd = tiny_bert
     words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
     (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
-    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok = BertTokenizerFast(vocab=str(tmp_path / 'vocab.txt'), do_lower_case=False)
     tok.model_max_length = cfg.max_position_embeddings
     rng = np.random.default_rng(0)
     docs = []
@@ -462,7 +462,7 @@ def test_retriever_query_path_end_to_end(tmp_path, tiny_bert, tiny_native):
     cfg, sd = tiny_bert
     words = [f'w{i:03d}' for i in range(TINY['vocab_size'] - 5)]
     (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
-    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok = BertTokenizerFast(vocab=str(tmp_path / 'vocab.txt'), do_lower_case=False)
     tok.model_max_length = cfg.max_position_embeddings
     encoder = AutoEncoder.from_native(tiny_native, tokenizer=tok)
     pooler = get_pooler({'name': 'mean'})

@@ -259,7 +259,7 @@ def _bert_tokenizer(tmp_path, max_len=32):
 
     words = [f'w{i:03d}' for i in range(300)]
     (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
-    tok = BertTokenizerFast(vocab_file=str(tmp_path / 'vocab.txt'), do_lower_case=False)
+    tok = BertTokenizerFast(vocab=str(tmp_path / 'vocab.txt'), do_lower_case=False)
     tok.model_max_length = max_len
     return tok, words
 

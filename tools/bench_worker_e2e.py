@@ -26,7 +26,7 @@ with tempfile.TemporaryDirectory() as tmp:
     model.load_state_dict(random_bert_state_dict(cfg, seed=0), strict=False)
     (tmp / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
     model.save_pretrained(tmp / 'ckpt')
-    BertTokenizerFast(vocab_file=str(tmp / 'vocab.txt'), do_lower_case=False).save_pretrained(tmp / 'ckpt')
+    BertTokenizerFast(vocab=str(tmp / 'vocab.txt'), do_lower_case=False).save_pretrained(tmp / 'ckpt')
     del model
     docs = []
     for d in range(n_docs):

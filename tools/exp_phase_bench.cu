@@ -1,0 +1,124 @@
+// Micro-benchmark of the softmax "exp phase" of the attention kernels, one SM at a time.
+//
+// Question (profiles/r01_notes.md): a softmax warp ALONE on its SMSP needs ~950 clk for the 64 exponentials
+// of a 64-key chunk although the MUFU pipe (16 ex2/clk/SM = one warp instruction per 8 clk per SMSP) would
+// allow 512.  Which instruction class costs the rest, and what does moving part of the exponentials to the
+// FMA pipe (Cody-Waite range reduction + degree-3 polynomial) buy?
+//
+// Each warp keeps 64 values per thread in registers and repeats the chunk body ITER times; results feed back
+// into the next iteration (64 independent chains, so the ILP of the real loop is kept).  Reported: clk per
+// chunk body (64 elements per thread) for 1 warp per SMSP (4 warps) and 2 warps per SMSP (8 warps).
+//
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/bin/exp_phase_bench tools/exp_phase_bench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 2^x for x in [-126, 126] on the FMA / ALU pipes: n = round(x), f = x - n in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (rel. error ~1e-4, far below bf16's 4e-3), exponent added as integer.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float n = t - 12582912.0f;
+  const float f = x - n;
+  float p = 0.0555054f;                      // minimax coefficients of 2^f on [-0.5, 0.5]
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) bench(const float* __restrict__ in, float* __restrict__ out,
+                                               long long* __restrict__ clk, int iters, float scale, float negm) {
+  float s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = in[(threadIdx.x * 64 + i) & 4095];
+  float sum0 = 0.0f, sum1 = 0.0f;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+      float p0, p1, p2, p3;
+      if constexpr (MODE == 0) {            // MUFU only
+        p0 = ex2(s[i]); p1 = ex2(s[i + 1]); p2 = ex2(s[i + 2]); p3 = ex2(s[i + 3]);
+      } else if constexpr (MODE <= 3) {     // FFMA + MUFU (+ FADD, + pack below)
+        p0 = ex2(fmaf(s[i], scale, negm)); p1 = ex2(fmaf(s[i + 1], scale, negm));
+        p2 = ex2(fmaf(s[i + 2], scale, negm)); p3 = ex2(fmaf(s[i + 3], scale, negm));
+      } else if constexpr (MODE == 4) {     // 1 of 4 on the FMA pipe
+        p0 = ex2(fmaf(s[i], scale, negm)); p1 = ex2(fmaf(s[i + 1], scale, negm));
+        p2 = ex2(fmaf(s[i + 2], scale, negm)); p3 = ex2_poly(fmaf(s[i + 3], scale, negm));
+      } else if constexpr (MODE == 5) {     // 2 of 4 on the FMA pipe
+        p0 = ex2(fmaf(s[i], scale, negm)); p1 = ex2_poly(fmaf(s[i + 1], scale, negm));
+        p2 = ex2(fmaf(s[i + 2], scale, negm)); p3 = ex2_poly(fmaf(s[i + 3], scale, negm));
+      } else {                              // MODE 6: all on the FMA pipe
+        p0 = ex2_poly(fmaf(s[i], scale, negm)); p1 = ex2_poly(fmaf(s[i + 1], scale, negm));
+        p2 = ex2_poly(fmaf(s[i + 2], scale, negm)); p3 = ex2_poly(fmaf(s[i + 3], scale, negm));
+      }
+      if constexpr (MODE >= 2) {
+        sum0 += p0 + p1;
+        sum1 += p2 + p3;
+      }
+      if constexpr (MODE >= 3) {
+        acc ^= pack2(p0, p1);
+        acc += pack2(p2, p3);
+      }
+      s[i] = p0; s[i + 1] = p1; s[i + 2] = p2; s[i + 3] = p3;
+    }
+  }
+  const long long t1 = clock64();
+  float r = sum0 + sum1 + __uint_as_float(acc & 0x3fffffffu);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) r += s[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if ((threadIdx.x & 31) == 0) clk[blockIdx.x * 8 + (threadIdx.x >> 5)] = t1 - t0;
+}
+
+template <int MODE>
+void run(const char* name, const float* in, float* out, long long* clk, int warps) {
+  const int iters = 2000;
+  long long h[8];
+  bench<MODE><<<1, warps * 32>>>(in, out, clk, 10, 0.18f, -0.5f);
+  bench<MODE><<<1, warps * 32>>>(in, out, clk, iters, 0.18f, -0.5f);
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (int w = 0; w < warps; ++w) mx = h[w] > mx ? h[w] : mx;
+  printf("%-44s warps/SM=%d (%d per SMSP): %7.1f clk per 64-element chunk per warp\n", name, warps, warps / 4,
+         (double)mx / iters);
+}
+
+int main() {
+  float *in, *out;
+  long long* clk;
+  cudaMalloc(&in, 4096 * 4);
+  cudaMalloc(&out, 256 * 4);
+  cudaMalloc(&clk, 64 * 8);
+  float h[4096];
+  for (int i = 0; i < 4096; ++i) h[i] = -3.0f + 6.0f * (float)((i * 2654435761u) % 1000) / 1000.0f;
+  cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+  for (int warps = 4; warps <= 8; warps += 4) {
+    run<0>("MUFU.EX2 only", in, out, clk, warps);
+    run<1>("FFMA + MUFU", in, out, clk, warps);
+    run<2>("FFMA + MUFU + FADD (row sum)", in, out, clk, warps);
+    run<3>("FFMA + MUFU + FADD + bf16 pack (as shipped)", in, out, clk, warps);
+    run<4>("same, 1 of 4 exponentials on the FMA pipe", in, out, clk, warps);
+    run<5>("same, 2 of 4 exponentials on the FMA pipe", in, out, clk, warps);
+    run<6>("same, all exponentials on the FMA pipe", in, out, clk, warps);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+  return 0;
+}

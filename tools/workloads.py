@@ -50,7 +50,11 @@ def write_bert_checkpoint(ckpt_dir: Path, cfg: dict | None = None, seed: int = 0
     model.save_pretrained(ckpt_dir)
     vocab = ['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *vocab_words(cfg['vocab_size'])]
     (ckpt_dir / 'vocab.txt').write_text('\n'.join(vocab) + '\n')
-    BertTokenizerFast(vocab_file=str(ckpt_dir / 'vocab.txt'), do_lower_case=False).save_pretrained(ckpt_dir)
+    tok = BertTokenizerFast(vocab=str(ckpt_dir / 'vocab.txt'), do_lower_case=False)
+    probe = tok('w00000 w00001')['input_ids']
+    if tok.unk_token_id in probe or len(probe) != 4:   # transformers >= 5 ignores the old `vocab_file=` keyword
+        raise RuntimeError(f'synthetic vocabulary not loaded: {probe}')
+    tok.save_pretrained(ckpt_dir)
     return ckpt_dir
 
 
@@ -100,23 +104,36 @@ _OUT_ROWS = {
 }
 
 
-def add_outliers(state_dict: dict, family: str, seed: int = 0, n_channels: int = 4, scale: float = 50.0,
-                 gain_range: tuple[float, float] = (0.1, 10.0)) -> dict:
-    """In place: (i) the rows of every block-output projection that write ``n_channels`` fixed hidden
-    channels are multiplied by ``scale`` (those channels of the residual stream become massive), (ii) every
-    norm gain is redrawn log-uniformly from ``gain_range`` and every norm bias from N(0, 0.5).  Works on HF
-    state-dict names of BertModel / EsmModel / MistralModel (any device / dtype); returns the dict."""
+def add_outliers(state_dict: dict, family: str, seed: int = 0, n_massive: int = 4, scale: float = 50.0,
+                 n_loud: int = 8, loud_gain: float = 10.0, gain_range: tuple[float, float] = (0.5, 2.0),
+                 massive_gain: float = 0.05) -> dict:
+    """In place, on HF state-dict names of BertModel / EsmModel / MistralModel (any device / dtype):
+
+      * MASSIVE channels: the rows of every block-output projection (attention output and FFN-down) that write
+        ``n_massive`` fixed hidden channels are multiplied by ``scale``, so those channels of the residual
+        stream are ~50x the rest and dominate every norm statistic; like trained checkpoints, the norm gains
+        of those channels are small (``massive_gain``);
+      * LOUD channels: ``n_loud`` other channels get a norm gain of ``loud_gain`` (= 10);
+      * every other norm gain is log-uniform in ``gain_range``, every norm bias N(0, 0.5).
+
+    (A first version drew EVERY gain from [0.1, 10]: with all q/k inputs up to 10x larger the attention
+    logits grow ~100x, softmax turns into an arg-max, and the fp32 network itself becomes discontinuous in
+    its inputs -- any 16-bit implementation then flips keys at random tokens.  profiles/r02_drift_report.md
+    keeps that run as the documented stress case.)"""
     g = torch.Generator().manual_seed(seed)
     out_names = _OUT_ROWS[family]
     hidden = next(v.shape[0] for k, v in state_dict.items() if k.endswith(out_names[0]))
-    channels = torch.randperm(hidden, generator=g)[:n_channels]
+    perm = torch.randperm(hidden, generator=g)
+    massive, loud = perm[:n_massive], perm[n_massive:n_massive + n_loud]
     lo, hi = float(np.log(gain_range[0])), float(np.log(gain_range[1]))
     for name, t in state_dict.items():
         if name.endswith(out_names):
-            t[channels.to(t.device)] *= scale
+            t[massive.to(t.device)] *= scale
         elif t.dim() == 1 and ('LayerNorm.weight' in name or 'layer_norm_after.weight' in name
                                or name.endswith('layernorm.weight') or name == 'norm.weight'):
             gain = torch.exp(torch.rand(t.shape, generator=g) * (hi - lo) + lo)
+            gain[massive] = massive_gain
+            gain[loud] = loud_gain
             t.copy_(gain.to(device=t.device, dtype=t.dtype))
         elif t.dim() == 1 and ('LayerNorm.bias' in name or 'layer_norm_after.bias' in name):
             t.copy_((0.5 * torch.randn(t.shape, generator=g)).to(device=t.device, dtype=t.dtype))
