@@ -41,6 +41,8 @@ EXPORTS = (
     'b2e_attention_d64',
     'b2e_attention_causal_d128',
     'b2e_topk_ip',
+    'b2e_pack_ubinary',
+    'b2e_search_ubinary',
     'b2e_layernorm',
 )
 # profiling hooks declared in include/b2e_debug.h (tools/ only; nothing in the package calls them)
@@ -120,6 +122,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_attention_causal_d128.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b2e_topk_ip.restype = i32
     lib.b2e_topk_ip.argtypes = [vp, i32, vp, i32, i64, i32, i32, vp, vp, vp]
+    lib.b2e_pack_ubinary.restype = i32
+    lib.b2e_pack_ubinary.argtypes = [vp, i64, i32, vp, vp]
+    lib.b2e_search_ubinary.restype = i32
+    lib.b2e_search_ubinary.argtypes = [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp]
     lib.b2e_layernorm.restype = i32
     lib.b2e_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
 
@@ -249,6 +255,39 @@ def topk_ip(queries: torch.Tensor, corpus: torch.Tensor, k: int) -> tuple[torch.
     with torch.cuda.device(queries.device):
         check(lib.b2e_topk_ip(queries.data_ptr(), q, corpus.data_ptr(), dtype_code(corpus.dtype), n, h, k,
                               scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
+    return scores, indices
+
+
+def pack_ubinary(embeddings: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,H] (CUDA) -> uint8 [N,H/8]: bit = value > 0, first dimension in the most significant bit."""
+    lib = load()
+    _cuda_contig(embeddings, 'embeddings')
+    if embeddings.dtype != torch.float32:
+        raise NativeError('pack_ubinary expects float32')
+    n, h = embeddings.shape
+    out = torch.empty((n, h // 8), dtype=torch.uint8, device=embeddings.device)
+    with torch.cuda.device(embeddings.device):
+        check(lib.b2e_pack_ubinary(embeddings.data_ptr(), n, h, out.data_ptr(), stream_ptr(embeddings.device)))
+    return out
+
+
+def search_ubinary(queries: torch.Tensor, corpus_bits: torch.Tensor, k: int,
+                   rescore_multiplier: int = 2) -> tuple[torch.Tensor, torch.Tensor]:
+    """Hamming top-(k * rescore_multiplier) over packed bits + float rescoring: (scores [Q,k] f32,
+    indices [Q,k] i64), descending score."""
+    lib = load()
+    _cuda_contig(queries, 'queries'), _cuda_contig(corpus_bits, 'corpus_bits')
+    if queries.dtype != torch.float32 or corpus_bits.dtype != torch.uint8:
+        raise NativeError('search_ubinary expects float32 queries and a uint8 packed corpus')
+    q, h = queries.shape
+    n = corpus_bits.shape[0]
+    if corpus_bits.shape[1] * 8 != h:
+        raise NativeError(f'corpus has {corpus_bits.shape[1] * 8} bits per row, queries have {h} dimensions')
+    scores = torch.empty((q, k), dtype=torch.float32, device=queries.device)
+    indices = torch.empty((q, k), dtype=torch.int64, device=queries.device)
+    with torch.cuda.device(queries.device):
+        check(lib.b2e_search_ubinary(queries.data_ptr(), q, corpus_bits.data_ptr(), n, h, k, rescore_multiplier,
+                                     scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
     return scores, indices
 
 

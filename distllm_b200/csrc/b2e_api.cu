@@ -17,6 +17,7 @@
 
 #include "attention3.cuh"
 #include "attention4.cuh"
+#include "binsearch.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -1512,6 +1513,130 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
       return launch_topk<bf16, 3, 2>(queries, Q, (const bf16*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
   }
   return fail(B2E_ERR_INVALID, "topk: corpus dtype %d (F32 or BF16)", corpus_dtype);
+}
+
+// ---- ubinary retrieval: packed bits, Hamming top-K, float rescoring (binsearch.cuh)
+extern "C++" {
+namespace {
+struct BinScratch {
+  uint32_t* qbits = nullptr;            // [Q, W]
+  unsigned* hist = nullptr;             // [Q, H+1]
+  int* thr = nullptr;                   // [Q, 2]
+  unsigned long long* cand = nullptr;   // [Q, BIN_MAX_CAND]
+  unsigned* n_cand = nullptr;           // [Q]
+  size_t cap_q = 0, cap_h = 0;
+  int device = -1;
+  void release() {
+    cudaFree(qbits); cudaFree(hist); cudaFree(thr); cudaFree(cand); cudaFree(n_cand);
+    qbits = nullptr; hist = nullptr; thr = nullptr; cand = nullptr; n_cand = nullptr;
+    cap_q = cap_h = 0;
+  }
+  int ensure(int Q, int H) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != device) {
+      release();
+      device = dev;
+    }
+    if ((size_t)Q <= cap_q && (size_t)H <= cap_h) return B2E_OK;
+    release();
+    const size_t q = (size_t)Q > 8 ? Q : 8, h = (size_t)H > 1024 ? H : 1024;
+    CUDA_TRY(cudaMalloc(&qbits, q * (h / 32) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&hist, q * (h + 1) * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&thr, q * 2 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&cand, q * BIN_MAX_CAND * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&n_cand, q * sizeof(unsigned)));
+    cap_q = q;
+    cap_h = h;
+    return B2E_OK;
+  }
+};
+thread_local BinScratch g_bin_scratch;
+
+template <int Q>
+int launch_bin_pass(const uint32_t* corpus, const uint32_t* qbits, int64_t N, int W, int H, long long K,
+                    BinScratch& sc, int q0, int grid, cudaStream_t st) {
+  const size_t smem_hist = (size_t)Q * W * 4 + (size_t)Q * (H + 1) * 4;
+  const size_t smem_sel = (size_t)Q * W * 4;
+  auto hist_k = hamming_hist_kernel<Q>;
+  auto sel_k = hamming_select_kernel<Q>;
+  int rc;
+  if (smem_hist > 48 * 1024 && (rc = ensure_smem_attr(hist_k, (int)smem_hist))) return rc;
+  hist_k<<<grid, BIN_THREADS, smem_hist, st>>>(corpus, qbits + (size_t)q0 * W, N, W, H,
+                                               sc.hist + (size_t)q0 * (H + 1));
+  hamming_threshold_kernel<<<1, 32, 0, st>>>(sc.hist + (size_t)q0 * (H + 1), H, K, Q, sc.thr + 2 * q0);
+  sel_k<<<grid, BIN_THREADS, smem_sel, st>>>(corpus, qbits + (size_t)q0 * W, N, W, sc.thr + 2 * q0,
+                                             sc.cand + (size_t)q0 * BIN_MAX_CAND, sc.n_cand + q0, BIN_MAX_CAND);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int b2e_pack_ubinary(const float* emb, int64_t n_rows, int H, uint8_t* out, void* stream) {
+  if (n_rows <= 0) return B2E_OK;
+  if (!emb || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (H <= 0 || H % 8 != 0) return fail(B2E_ERR_INVALID, "pack_ubinary: H=%d must be a positive multiple of 8", H);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  const long long total = (long long)n_rows * (H / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)info.sms * 16) blocks = (long long)info.sms * 16;
+  pack_ubinary_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(emb, out, n_rows, H);
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
+int b2e_search_ubinary(const float* queries, int Q, const uint8_t* corpus_bits, int64_t N, int H, int k,
+                       int rescore_multiplier, float* out_scores, int64_t* out_indices, void* stream) {
+  if (!queries || !corpus_bits || !out_scores || !out_indices) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (Q <= 0 || N <= 0) return fail(B2E_ERR_INVALID, "search_ubinary: empty problem Q=%d N=%lld", Q, (long long)N);
+  if (H <= 0 || H % 32 != 0 || H / 32 > BIN_MAX_WORDS)
+    return fail(B2E_ERR_INVALID, "search_ubinary: H=%d must be a multiple of 32 (<= %d)", H, 32 * BIN_MAX_WORDS);
+  if (N >= (1ll << 40)) return fail(B2E_ERR_INVALID, "search_ubinary: N=%lld too large", (long long)N);
+  if (k <= 0 || rescore_multiplier <= 0) return fail(B2E_ERR_INVALID, "search_ubinary: k and rescore_multiplier must be positive");
+  const long long K = (long long)k * rescore_multiplier;
+  if (2 * K > BIN_MAX_CAND)
+    return fail(B2E_ERR_INVALID, "search_ubinary: k * rescore_multiplier = %lld exceeds %d", K, BIN_MAX_CAND / 2);
+  if ((reinterpret_cast<uintptr_t>(corpus_bits) & 15u) != 0)
+    return fail(B2E_ERR_INVALID, "search_ubinary: corpus_bits must be 16-byte aligned");
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  BinScratch& sc = g_bin_scratch;
+  if ((rc = sc.ensure(Q, H))) return rc;
+  const int W = H / 32;
+  const uint32_t* corpus = reinterpret_cast<const uint32_t*>(corpus_bits);
+  if ((rc = b2e_pack_ubinary(queries, Q, H, reinterpret_cast<uint8_t*>(sc.qbits), stream))) return rc;
+  CUDA_TRY(cudaMemsetAsync(sc.hist, 0, (size_t)Q * (H + 1) * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(sc.n_cand, 0, (size_t)Q * sizeof(unsigned), st));
+  long long want = (N + BIN_THREADS - 1) / BIN_THREADS;
+  const int grid = (int)(want < (long long)info.sms * 8 ? want : (long long)info.sms * 8);
+  // queries per pass over the corpus: as many as the shared-memory histogram allows (<= 8)
+  int qp = 8;
+  while (qp > 1 && (size_t)qp * (W + H + 1) * 4 > 160 * 1024) qp >>= 1;
+  for (int q0 = 0; q0 < Q;) {
+    int n = Q - q0 < qp ? Q - q0 : qp;
+    if (n >= 8) { n = 8; rc = launch_bin_pass<8>(corpus, sc.qbits, N, W, H, K, sc, q0, grid, st); }
+    else if (n >= 4) { n = 4; rc = launch_bin_pass<4>(corpus, sc.qbits, N, W, H, K, sc, q0, grid, st); }
+    else if (n >= 2) { n = 2; rc = launch_bin_pass<2>(corpus, sc.qbits, N, W, H, K, sc, q0, grid, st); }
+    else { n = 1; rc = launch_bin_pass<1>(corpus, sc.qbits, N, W, H, K, sc, q0, grid, st); }
+    if (rc) return rc;
+    q0 += n;
+  }
+  // candidates: the K nearest plus every row tied with the K-th; sort width = next power of two >= 2K
+  int n_pow2 = 2;
+  while (n_pow2 < 2 * K || n_pow2 < 64) n_pow2 <<= 1;
+  if (n_pow2 < BIN_MAX_CAND) n_pow2 = BIN_MAX_CAND;   // ties beyond 2K still fit up to the buffer size
+  const size_t smem = (size_t)n_pow2 * 8 + (size_t)H * 4;
+  if ((rc = ensure_smem_attr(binary_rescore_kernel, (int)smem))) return rc;
+  binary_rescore_kernel<<<Q, BIN_THREADS, smem, st>>>(sc.cand, sc.n_cand, BIN_MAX_CAND, n_pow2, corpus, W, H,
+                                                      queries, K, k, out_scores,
+                                                      reinterpret_cast<long long*>(out_indices));
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
 }
 
 int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* out, int rows, int H,

@@ -10,9 +10,11 @@ Mirrors the float32 / exact branch of distllm/rag/search.py:
     Retriever.get_pooled_embeddings / _get_pooled_embeddings   :800-881 (sort by length, batches of `batch_size`,
                                             tokenizer(padding=True, truncation=True), encode, pool, fp32)
 
-The index itself is the matrix: no faiss file, no quantisation (the ``uint8`` / ``ubinary`` precisions and
-the HNSW branch of the reference are not built).  There is no CPU fallback: the search runs in
-``b2e_topk_ip``.
+The index itself is the device-resident matrix: no faiss file.  ``precision='float32'`` is the exact
+IndexFlatIP search (``b2e_topk_ip``); ``precision='ubinary'`` is the reference's binary branch
+(search.py:34-56, :202-260, :280-336: packbits(x > 0) corpus, Hamming top-(k * rescore_multiplier), float
+rescoring) on ``b2e_pack_ubinary`` / ``b2e_search_ubinary``, 1/32 of the HBM traffic per query.  The HNSW
+(approximate) branch is not built -- ``search_algorithm='hnsw'`` raises.  There is no CPU fallback.
 """
 
 from __future__ import annotations
@@ -34,15 +36,22 @@ MAX_TOP_K = 256
 
 
 class ExactIndexConfig(BaseConfig):
-    """Subset of the reference's ``FaissIndexV2Config`` that the exact float32 search uses."""
+    """The reference's ``FaissIndexV2Config`` (search.py:59-95) for the exact branches: same field names and
+    defaults, so a reference YAML validates; the faiss file fields are accepted and unused."""
 
-    name: Literal['exact_index'] = 'exact_index'  # type: ignore[assignment]
+    name: Literal['exact_index', 'faiss_index_v2'] = 'exact_index'  # type: ignore[assignment]
     # HF dataset directory with the document text and the fp32 ``embeddings`` column
     dataset_dir: Optional[Path] = None  # noqa: UP007
-    # storage of the matrix on the device: 'float32' (exact) or 'bfloat16' (half the HBM traffic; scores
-    # are exact fp32 dot products of the ROUNDED corpus)
-    corpus_dtype: Literal['float32', 'bfloat16'] = 'float32'
+    faiss_index_path: Optional[Path] = None  # noqa: UP007  (no index file: the matrix lives in HBM)
+    dataset_chunk_paths: Optional[list[Path]] = None  # noqa: UP007
+    precision: Literal['float32', 'ubinary'] = Field(
+        'float32', description='The desired precision for the embeddings [float32, ubinary].')
     search_algorithm: Literal['exact'] = Field('exact', description='only the exact search is built')
+    rescore_multiplier: int = Field(2, description='Oversampling factor for rescoring (ubinary).')
+    num_quantization_workers: int = 1   # accepted for compatibility: packing is one kernel launch
+    # not in the reference: storage of the float32-precision matrix on the device: 'float32' (exact) or
+    # 'bfloat16' (half the HBM traffic; scores are exact fp32 dot products of the ROUNDED corpus)
+    corpus_dtype: Literal['float32', 'bfloat16'] = 'float32'
 
 
 class ExactIndex:
@@ -66,8 +75,22 @@ class ExactIndex:
         matrix = torch.as_tensor(embeddings)
         if matrix.ndim != 2:
             raise ValueError(f'embeddings must be [N, H], got {tuple(matrix.shape)}')
+        self.precision = self.config.precision
+        if self.precision == 'ubinary':
+            # quantize_embeddings(..., 'ubinary') (search.py:34-56): packed on the device, chunk by chunk so that
+            # the fp32 matrix never has to sit in HBM next to its 32x smaller packed form
+            if matrix.shape[1] % 32:
+                raise ValueError(f'ubinary needs an embedding size that is a multiple of 32, got {matrix.shape[1]}')
+            self.corpus = torch.empty((matrix.shape[0], matrix.shape[1] // 8), dtype=torch.uint8, device=dev)
+            step = 1 << 20
+            for lo in range(0, matrix.shape[0], step):
+                rows = matrix[lo:lo + step].to(device=dev, dtype=torch.float32).contiguous()
+                self.corpus[lo:lo + step] = _native.pack_ubinary(rows)
+            self.embedding_size = matrix.shape[1]
+            return
         dtype = torch.float32 if self.config.corpus_dtype == 'float32' else torch.bfloat16
         self.corpus = matrix.to(device=dev, dtype=dtype).contiguous()
+        self.embedding_size = matrix.shape[1]
 
     def __len__(self) -> int:
         return self.corpus.shape[0]
@@ -87,7 +110,13 @@ class ExactIndex:
         queries = torch.as_tensor(query_embedding, dtype=torch.float32).to(self.corpus.device).contiguous()
         if queries.ndim == 1:
             queries = queries[None]
-        scores, indices = _native.topk_ip(queries, self.corpus, top_k)
+        if self.precision == 'ubinary':
+            scores, indices = _native.search_ubinary(queries, self.corpus, top_k, self.config.rescore_multiplier)
+            if bool((indices == -2).any()):
+                raise _native.NativeError('ubinary search: more rows tie at the threshold Hamming distance than '
+                                          'the candidate buffer holds (duplicate corpus rows?)')
+        else:
+            scores, indices = _native.topk_ip(queries, self.corpus, top_k)
         scores, indices = scores.cpu(), indices.cpu()
         total_scores, total_indices = [], []
         for s_row, i_row in zip(scores.tolist(), indices.tolist()):

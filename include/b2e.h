@@ -150,6 +150,19 @@ int b2e_attention_causal_d128(const void* qkv, const int64_t* attention_mask, vo
  * index); when N < k the tail is filled with -inf / -1. */
 int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtype, int64_t N, int H,
                 int k, float* out_scores, int64_t* out_indices, void* stream);
+/* Binary retrieval (distllm/rag/search.py, precision='ubinary', search_algorithm='exact'):
+ * b2e_pack_ubinary = sentence_transformers quantize_embeddings(x, 'ubinary') as called from search.py:34-56
+ * (np.packbits(x > 0): eight dimensions per byte, first dimension in the most significant bit), fp32
+ * [n_rows,H] -> uint8 [n_rows,H/8] on the device.
+ * b2e_search_ubinary = faiss.IndexBinaryFlat.search + the rescoring of semantic_search_faiss(rescore=True)
+ * as called from search.py:202-260 and :280-336: the k*rescore_multiplier rows nearest in Hamming distance to
+ * the packed query (ties: smaller row ids), rescored as sum_j q[j]*bit[j] with the float query, top k by
+ * descending score into out_scores / out_indices [Q,k] (-inf / -1 past the end of a small corpus; NaN / -2
+ * when more rows tie at the threshold distance than the 4096-entry candidate buffer holds).
+ * H % 32 == 0, k*rescore_multiplier <= 2048, corpus_bits 16-byte aligned. */
+int b2e_pack_ubinary(const float* emb, int64_t n_rows, int H, uint8_t* out_bits, void* stream);
+int b2e_search_ubinary(const float* queries, int Q, const uint8_t* corpus_bits, int64_t N, int H, int k,
+                       int rescore_multiplier, float* out_scores, int64_t* out_indices, void* stream);
 int b2e_layernorm(const void* in_bf16, const float* gamma, const float* beta, void* out, int rows,
                   int H, float eps, int out_dtype, void* stream);
 

@@ -353,3 +353,56 @@ def test_topk_rejects_bad_arguments(dev):
         nv.topk_ip(qq, c, 300)
     with pytest.raises(nv.NativeError, match='H=100'):
         nv.topk_ip(torch.zeros(2, 100, device=dev), torch.zeros(10, 100, device=dev), 3)
+
+
+# ---------------------------------------------------------------------------------- binary retrieval
+@pytest.mark.parametrize('n,h,q,k,mult', [(5000, 768, 3, 10, 2), (20000, 1280, 9, 5, 4), (40, 256, 2, 8, 2),
+                                          (3000, 64 * 3, 1, 100, 2)])
+def test_ubinary_search_matches_oracle(n, h, q, k, mult):
+    """b2e_pack_ubinary / b2e_search_ubinary vs the CPU restatement of packbits + IndexBinaryFlat + rescoring
+    (oracle/search.py): packed bits and result indices bit-exact (integer / index work), scores to fp32 rounding."""
+    from oracle import search as osearch
+
+    rng = np.random.default_rng(n + h)
+    corpus = rng.standard_normal((n, h)).astype(np.float32)
+    corpus[rng.integers(0, n, 50)] = 0.0          # zero rows pack to all-zero bits
+    if n > 100:
+        corpus[100:110] = corpus[7]                # exact duplicates: Hamming ties resolved by row id
+    queries = rng.standard_normal((q, h)).astype(np.float32)
+    queries[0] = corpus[7] + 0.05 * rng.standard_normal(h).astype(np.float32)
+    bits = nv.pack_ubinary(torch.from_numpy(corpus).cuda())
+    ref_bits = osearch.quantize_ubinary(corpus)
+    assert np.array_equal(bits.cpu().numpy(), ref_bits)
+    scores, indices = nv.search_ubinary(torch.from_numpy(queries).cuda(), bits, k, mult)
+    ref_s, ref_i = osearch.search_ubinary(queries, ref_bits, k, mult)
+    kk = ref_i.shape[1]
+    got_i, got_s = indices.cpu().numpy(), scores.cpu().numpy()
+    # rescored scores are sums of up to h floats: order of summation differs -> compare with a tolerance, and
+    # indices wherever the reference scores are not tied within that tolerance
+    np.testing.assert_allclose(got_s[:, :kk], ref_s, rtol=1e-5, atol=1e-4)
+    for r in range(q):
+        gap = np.abs(np.diff(ref_s[r])) > 1e-3
+        stable = np.concatenate(([True], gap)) & np.concatenate((gap, [True]))
+        assert np.array_equal(got_i[r, :kk][stable], ref_i[r][stable]), (r, got_i[r], ref_i[r])
+        assert set(got_i[r, :kk]) == set(ref_i[r])
+    if kk < k:
+        assert (got_i[:, kk:] == -1).all() and np.isinf(got_s[:, kk:]).all()
+
+
+def test_exact_index_ubinary_through_the_retriever_surface():
+    from distllm_b200.rag.search import ExactIndex
+    from distllm_b200.rag.search import ExactIndexConfig
+    from oracle import search as osearch
+
+    rng = np.random.default_rng(9)
+    corpus = rng.standard_normal((4000, 768)).astype(np.float32)
+    index = ExactIndex(corpus, config=ExactIndexConfig(precision='ubinary', rescore_multiplier=3))
+    assert index.corpus.dtype == torch.uint8 and index.corpus.shape == (4000, 96) and len(index) == 4000
+    q = ExactIndex.transform(corpus[[5, 77]] + 0.1 * rng.standard_normal((2, 768)).astype(np.float32))
+    res = index.search(q, top_k=4)
+    ref_s, ref_i = osearch.search_ubinary(q, osearch.quantize_ubinary(corpus), 4, 3)
+    assert [r[0] for r in res.total_indices] == [5, 77]
+    assert res.total_indices == ref_i.tolist()
+    np.testing.assert_allclose(np.array(res.total_scores), ref_s, rtol=1e-5, atol=1e-4)
+    kept = index.search(q, top_k=4, score_threshold=float(ref_s[0, 1]))
+    assert kept.total_indices[0] == ref_i[0, :2].tolist()

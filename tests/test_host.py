@@ -579,3 +579,43 @@ def test_sentence_splitter_choice_is_explicit():
         assert ''.join(split_by_sentence_tokenizer('regex')('One. Two.')) == 'One. Two.'
     with pytest.raises(ValueError):
         split_by_sentence_tokenizer('other')
+
+
+def test_ubinary_search_oracle_properties():
+    """oracle/search.py's restatement of the reference's binary branch (quantize -> IndexBinaryFlat -> rescore):
+    known-answer checks of every piece (no faiss / sentence_transformers here: parity unpinned, see its header)."""
+    from oracle import search as osearch
+
+    x = np.array([[0.5, -1.0, 0.0, 2.0, -0.1, 3.0, 1e-9, -7.0,     1.0, 1.0, 1.0, 1.0, -1.0, -1.0, -1.0, -1.0]],
+                 dtype=np.float32)
+    bits = osearch.quantize_ubinary(x)
+    assert bits.dtype == np.uint8 and bits.tolist() == [[0b10010110, 0b11110000]]   # first dimension = MSB; 0 -> 0
+    rng = np.random.default_rng(3)
+    corpus = rng.standard_normal((300, 64)).astype(np.float32)
+    corpus[17] = corpus[5]                       # identical rows: a Hamming tie, the smaller id first
+    cb = osearch.quantize_ubinary(corpus)
+    q = corpus[5:6] + 0.01 * rng.standard_normal((1, 64)).astype(np.float32)
+    d, i = osearch.hamming_topk(osearch.quantize_ubinary(q), cb, 4)
+    assert i[0, 0] == 5 and i[0, 1] == 17 and d[0, 0] == d[0, 1] and list(d[0]) == sorted(d[0])
+    brute = (np.unpackbits(cb, axis=1) != np.unpackbits(osearch.quantize_ubinary(q), axis=1)).sum(1)
+    assert sorted(brute)[:4] == list(d[0])
+    s, idx = osearch.search_ubinary(q, cb, top_k=3, rescore_multiplier=4)
+    cand = osearch.hamming_topk(osearch.quantize_ubinary(q), cb, 12)[1][0]
+    resc = (np.unpackbits(cb[cand], axis=1) * q[0]).sum(1)
+    assert np.allclose(s[0], np.sort(resc)[::-1][:3], rtol=1e-6) and set(idx[0]) <= set(cand)
+    assert list(s[0]) == sorted(s[0], reverse=True)
+    s2, idx2 = osearch.search_ubinary(q, cb[:2], top_k=3, rescore_multiplier=2)   # corpus smaller than k
+    assert s2.shape == (1, 2)
+
+
+def test_exact_index_config_accepts_the_reference_fields(tmp_path):
+    from distllm_b200.rag.search import ExactIndexConfig
+
+    cfg = ExactIndexConfig(name='faiss_index_v2', dataset_dir=tmp_path, faiss_index_path=tmp_path / 'x.index',
+                           precision='ubinary', rescore_multiplier=4, num_quantization_workers=8)
+    assert (cfg.precision, cfg.search_algorithm, cfg.rescore_multiplier) == ('ubinary', 'exact', 4)
+    assert ExactIndexConfig().precision == 'float32' and ExactIndexConfig().rescore_multiplier == 2
+    with pytest.raises(Exception):
+        ExactIndexConfig(search_algorithm='hnsw')      # the approximate branch is not built
+    with pytest.raises(Exception):
+        ExactIndexConfig(precision='uint8')            # the reference itself only accepts float32 / ubinary
