@@ -338,17 +338,17 @@ def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
     from distllm_b200 import _native as nv
 
     m, n, k = BATCH * SEQ, BERT_BASE['intermediate_size'], BERT_BASE['hidden_size']
-    a = torch.randn(m, k, device=device).bfloat16()
-    w = (torch.randn(n, k, device=device) * 0.02).bfloat16()
+    a = torch.randn(m, k, device=device).half()
+    w = (torch.randn(n, k, device=device) * 0.02).half()
     bias = torch.zeros(n, device=device)
     for _ in range(3):
-        nv.gemm_bf16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        nv.gemm_f16(a, w, bias, None, nv.EPI_BIAS_GELU)
     reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(device)
     e0.record()
     for _ in range(reps):
-        nv.gemm_bf16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        nv.gemm_f16(a, w, bias, None, nv.EPI_BIAS_GELU)
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / reps
@@ -358,7 +358,7 @@ def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
             'unit': 'TFLOP/s', 'peak_kind': 'burst (kernel timed alone)'}
 
 
-DOMINANT_KERNEL = 'gemm2_bf16_pair<5,GELU> (FFN up, M=262144 N=3072 K=768; CTA-pair tcgen05 kernel)'
+DOMINANT_KERNEL = 'gemm2_h16_pair<5,GELU> (FFN up, M=262144 N=3072 K=768; CTA-pair tcgen05 kernel)'
 
 
 def ncu_traffic_bytes() -> float | None:
@@ -426,7 +426,7 @@ def extra_mistral(device, peaks: dict, reduce_max) -> dict:
 
     cfg = MistralConfig(**MISTRAL_7B)
     b, s = 16, 4096
-    sd = random_mistral_state_dict(cfg, seed=0, device=device, dtype=torch.bfloat16)
+    sd = random_mistral_state_dict(cfg, seed=0, device=device, dtype=torch.float16)
     enc = NativeMistralEncoder(cfg, sd, device=device)
     del sd
     torch.cuda.empty_cache()
@@ -442,7 +442,7 @@ def extra_mistral(device, peaks: dict, reduce_max) -> dict:
     seqs = b / (ms * 1e-3)
     tf = seqs * mistral_flops_per_seq(MISTRAL_7B, s) / 1e12
     return {'workload': 'C3: SFR-Embedding-Mistral shape (Mistral-7B: L32 H4096 32q/8kv x128 I14336), '
-                        'last_token pooler, batch_size=16, S=4096, synthetic ids, random-init bf16 weights',
+                        'last_token pooler, batch_size=16, S=4096, synthetic ids, random-init fp16 weights',
             'value_per_gpu': seqs, 'unit': 'sequences/s', 'ms_per_step': ms, 'steps': 3,
             'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
                          'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
@@ -691,18 +691,18 @@ def run_native(args) -> None:
         roof = {'bound': 'tensor', 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s',
                 'frac': dom['frac'], 'traffic': ncu_traffic_bytes(), 'kernel': dom['name'],
                 'flops_per_launch': dom['flops_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
-                'peak_source': f'{peak_src} burst bf16 (kernel timed alone)',
+                'peak_source': f'{peak_src} burst 16-bit (bf16 cuBLAS) tensor peak (kernel timed alone)',
                 'whole_step': {'achieved': step_tf, 'peak': peaks['bf16_tflops_sustained'],
                                'frac': step_tf / peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                                'flops_per_chunk': fpc,
-                               'peak_source': f'{peak_src} sustained bf16 (whole step, per GPU)'}}
+                               'peak_source': f'{peak_src} sustained 16-bit (bf16 cuBLAS) tensor peak (whole step, per GPU)'}}
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_leg(device)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world,
             'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * elapsed_s / steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'seq_len': SEQ,
                        'parallelism': f'dp{world}: chunks sharded by rank, one all-gather of the pooled matrix',
                        'l2': 'per-step activations (~4 GB) exceed the 126 MB L2; no explicit flush needed'},

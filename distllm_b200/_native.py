@@ -37,7 +37,7 @@ EXPORTS = (
     'b2e_pool_last_token',
     'b2e_l2_normalize',
     'b2e_adjacent_cosine_dist',
-    'b2e_gemm_bf16',
+    'b2e_gemm_f16',
     'b2e_attention_d64',
     'b2e_attention_causal_d128',
     'b2e_topk_ip',
@@ -114,8 +114,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_l2_normalize.argtypes = [vp, i64, i32, vp]
     lib.b2e_adjacent_cosine_dist.restype = i32
     lib.b2e_adjacent_cosine_dist.argtypes = [vp, i32, i64, i32, vp, vp, vp]
-    lib.b2e_gemm_bf16.restype = i32
-    lib.b2e_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b2e_gemm_f16.restype = i32
+    lib.b2e_gemm_f16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b2e_attention_d64.restype = i32
     lib.b2e_attention_d64.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.b2e_attention_causal_d128.restype = i32
@@ -180,14 +180,14 @@ def _cuda_contig(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- thin op wrappers
-def gemm_bf16(
+def gemm_f16(
     a: torch.Tensor,
     w: torch.Tensor,
     bias: torch.Tensor | None,
     resid: torch.Tensor | None = None,
     epilogue: int = EPI_BIAS,
 ) -> torch.Tensor:
-    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; bf16 in/out.
+    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; fp16 in/out, fp32 accumulation.
 
     ``EPI_SWIGLU``: ``w`` holds gate/up rows interleaved in blocks of 64 (weights.interleave_gate_up)
     and the result is ``silu(gate) * up`` of shape [M, N/2]."""
@@ -198,9 +198,11 @@ def gemm_bf16(
     m, k = a.shape
     n = w.shape[0]
     n_out = n // 2 if epilogue == EPI_SWIGLU else n
-    out = torch.empty((m, n_out), dtype=torch.bfloat16, device=a.device)
+    if a.dtype != torch.float16 or w.dtype != torch.float16:
+        raise NativeError('gemm_f16 expects float16 operands')
+    out = torch.empty((m, n_out), dtype=torch.float16, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib.b2e_gemm_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid),
+        check(lib.b2e_gemm_f16(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid),
                                 out.data_ptr(), m, n, k, epilogue, stream_ptr(a.device)))
     return out
 
@@ -212,10 +214,10 @@ def attention_d64(
     seq: int,
     heads: int,
 ) -> torch.Tensor:
-    """qkv [B*S, 3*heads*64] bf16 -> context [B*S, heads*64] bf16."""
+    """qkv [B*S, 3*heads*64] fp16 -> context [B*S, heads*64] fp16."""
     lib = load()
     _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
-    ctx = torch.zeros((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    ctx = torch.zeros((batch * seq, heads * 64), dtype=torch.float16, device=qkv.device)
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_d64(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch,
                                     seq, heads, None, stream_ptr(qkv.device)))
@@ -231,10 +233,10 @@ def attention_causal_d128(
     kv_heads: int,
     window: int = 0,
 ) -> torch.Tensor:
-    """qkv [B*S, (heads + 2*kv_heads)*128] bf16 (q | k | v, rotary applied) -> [B*S, heads*128] bf16."""
+    """qkv [B*S, (heads + 2*kv_heads)*128] fp16 (q | k | v, rotary applied) -> [B*S, heads*128] fp16."""
     lib = load()
     _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
-    ctx = torch.zeros((batch * seq, heads * 128), dtype=torch.bfloat16, device=qkv.device)
+    ctx = torch.zeros((batch * seq, heads * 128), dtype=torch.float16, device=qkv.device)
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_causal_d128(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(),
                                             batch, seq, heads, kv_heads, window, stream_ptr(qkv.device)))
@@ -296,7 +298,7 @@ def layernorm(
     gamma: torch.Tensor,
     beta: torch.Tensor,
     eps: float,
-    out_dtype: torch.dtype = torch.bfloat16,
+    out_dtype: torch.dtype = torch.float16,
 ) -> torch.Tensor:
     lib = load()
     _cuda_contig(x, 'x')

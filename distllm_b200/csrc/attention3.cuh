@@ -13,7 +13,7 @@
 //                           leaves the softmax critical path
 //   warps 0-3   softmax for query tile A (slot 0)    one row per thread; scores of a chunk live in
 //   warps 4-7   softmax for query tile B (slot 1)    registers; online softmax with lazy rescale;
-//                                                    bf16 P written over S's own TMEM columns
+//                                                    h16 P written over S's own TMEM columns
 //
 // TMEM: slot s at column 256*s: S/P buffer 0 [0,64), S/P buffer 1 [64,128), O [128,192).
 // Semantics: HF SDPA with an additive key-padding mask (transformers/models/bert/
@@ -91,7 +91,7 @@ __device__ __forceinline__ float at3_max(const uint32_t (&s)[32], const float* _
   }
   return m;
 }
-// p = exp2(x - m) -> bf16 pairs; returns the fp32 row-sum contribution and tracks max(x)
+// p = exp2(x - m) -> h16 pairs; returns the fp32 row-sum contribution and tracks max(x)
 __device__ __forceinline__ float at3_exp_pack(const uint32_t (&s)[32], const float* __restrict__ bias,
                                               float scale, float m, uint32_t* pk, float& xmax) {
   float sum = 0.0f;
@@ -106,8 +106,8 @@ __device__ __forceinline__ float at3_exp_pack(const uint32_t (&s)[32], const flo
     const float p0 = fast_exp2(x0 - m), p1 = fast_exp2(x1 - m);
     const float p2 = fast_exp2(x2 - m), p3 = fast_exp2(x3 - m);
     sum += (p0 + p1) + (p2 + p3);
-    pk[i / 2] = pack_bf16x2(p0, p1);
-    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+    pk[i / 2] = pack_h16x2(p0, p1);
+    pk[i / 2 + 1] = pack_h16x2(p2, p3);
   }
   return sum;
 }
@@ -122,18 +122,20 @@ __device__ __forceinline__ float at3_smax_plain(const uint32_t (&s)[32], float m
   return m;
 }
 // 2^x on the FMA / ALU pipes instead of the MUFU pipe (16 ex2 per clock and SM is what bounds head_dim-64
-// attention): Cody-Waite range reduction n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax
-// polynomial (relative error ~1e-4, the result is rounded to bf16 = 4e-3 anyway), n added to the exponent
-// field as an integer.  x is clamped at -126 (no denormal / wrap-around for very negative scores).
+// attention): Cody-Waite range reduction n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-4 least-squares
+// polynomial (max relative error 2.7e-6 on the interval, the level of ex2.approx itself and far below the
+// 2^-11 rounding of P to half), n added to the exponent field as an integer.  x is clamped at -126 (no
+// denormal / wrap-around for very negative scores).
 __device__ __forceinline__ float poly_exp2(float x) {
   x = fmaxf(x, -126.0f);
   const float t = x + 12582912.0f;   // 1.5 * 2^23: round-to-nearest integer part in the low mantissa bits
   const float n = t - 12582912.0f;
   const float f = x - n;
-  float p = 0.0555054f;
-  p = fmaf(p, f, 0.2402265f);
-  p = fmaf(p, f, 0.6931472f);
-  p = fmaf(p, f, 1.0f);
+  float p = 0.009560510f;
+  p = fmaf(p, f, 0.055917039f);
+  p = fmaf(p, f, 0.240249811f);
+  p = fmaf(p, f, 0.693121968f);
+  p = fmaf(p, f, 0.999999191f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
@@ -154,8 +156,8 @@ __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], flo
     const float p3 = POLY >= 1 ? poly_exp2(x3) : fast_exp2(x3);
     sum0 += p0 + p1;
     sum1 += p2 + p3;
-    pk[i / 2] = pack_bf16x2(p0, p1);
-    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+    pk[i / 2] = pack_h16x2(p0, p1);
+    pk[i / 2 + 1] = pack_h16x2(p2, p3);
   }
   return sum0 + sum1;
 }
@@ -190,12 +192,12 @@ __device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the 
 //   bits 2-3  exponentials per four that run on the FMA pipe (plain chunks only): 0, 1 or 2
 template <int V>
 __global__ void __launch_bounds__(AT3_THREADS, 1)
-attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf16, box 64 x 128
-                      const __grid_constant__ CUtensorMap tm_kv,  // [T, 3H] bf16, box 64 x 64
+attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16, box 64 x 128
+                      const __grid_constant__ CUtensorMap tm_kv,  // [T, 3H] h16, box 64 x 64
                       const float* __restrict__ bias,             // [B, S_pad]
                       const int* __restrict__ kv_chunks,          // [B]
                       const int* __restrict__ plain_chunks,       // [B] or nullptr
-                      const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] bf16, box 64 x 128 x 1
+                      const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] h16, box 64 x 128 x 1
                       int B, int S, int S_pad, int heads, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -312,8 +314,8 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
         // per QK or PV event (polls + 4 MMAs + commits), four events per pair of chunks: 1800 clk,
         // more than the softmax itself.  Two threads run their slots side by side with blocking waits.
         const int slot = (warp == 8) ? 0 : 1;
-        constexpr uint32_t idesc_s = make_idesc_bf16(128, AT3_KC, 0, 0);
-        constexpr uint32_t idesc_o = make_idesc_bf16(128, AT3_D, 0, 1);  // B (= V) is MN-major
+        constexpr uint32_t idesc_s = make_idesc_h16(128, AT3_KC, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc_h16(128, AT3_D, 0, 1);  // B (= V) is MN-major
         const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
         uint32_t chunk_base = 0;   // ring position of this item's chunk 0
         uint32_t q_cnt[2] = {0, 0};   // Q tiles consumed per item buffer (parity of q_full)
@@ -542,7 +544,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           }
           if (turn) asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
           if (r == 0) AT3_STAMP(slot, j * 10 + 2);
-          tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
+          tmem_st32(t_s, pk);  // h16 P over the first 32 columns of S's own buffer
           // S_{j+1} (the other buffer; its Q K^T was issued before P_{j-1} V_{j-1}) starts to move into the
           // score registers now: the load runs under the store's wait, the fence and the arrive
           if (kPrefetch && j + 1 < n) fetch_scores(j + 1);
@@ -552,7 +554,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
           if (kPrefetch && j + 1 < n) tmem_ld_wait();
           if (r == 0) AT3_STAMP(slot, j * 10 + 3);
         }
-        // ---- epilogue: O / l -> bf16 -> swizzled staging tile -> one TMA store per tile
+        // ---- epilogue: O / l -> h16 -> swizzled staging tile -> one TMA store per tile
         if (r == 0) AT3_STAMP(slot, 900);
         if (r == 0) tma_store_wait_read<0>();   // the previous tile's store has read the staging
         asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
@@ -569,10 +571,10 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] bf1
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            w.x = pack_h16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_h16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_h16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_h16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
             const int unit = cc * 4 + (i >> 3);
             *reinterpret_cast<uint4*>(ostage + r * 128 + ((unit ^ (r & 7)) << 4)) = w;
           }

@@ -12,7 +12,7 @@
 //                           over two 64-wide slabs) and O += P_j V_j (TS: P from TMEM, V_j as MN-major
 //                           smem operand, N = 128)
 //   warps 0-3   softmax for query tile A (slot 0)   one row per thread, online softmax in the exp2
-//   warps 4-7   softmax for query tile B (slot 1)   domain with lazy rescale; bf16 P over S's columns
+//   warps 4-7   softmax for query tile B (slot 1)   domain with lazy rescale; h16 P over S's columns
 //
 // TMEM: slot s at column 256*s: S/P buffer 0 [0,64), S/P buffer 1 [64,128), O [128,256).
 // Masking: a key j is visible to query i iff j <= i, (window == 0 or i - j < window) and the key is
@@ -82,8 +82,8 @@ __device__ __forceinline__ float at4_exp_pack(const uint32_t (&s)[32], const flo
     const float p0 = fast_exp2(x0 - m), p1 = fast_exp2(x1 - m);
     const float p2 = fast_exp2(x2 - m), p3 = fast_exp2(x3 - m);
     sum += (p0 + p1) + (p2 + p3);
-    pk[i / 2] = pack_bf16x2(p0, p1);
-    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+    pk[i / 2] = pack_h16x2(p0, p1);
+    pk[i / 2 + 1] = pack_h16x2(p2, p3);
   }
   return sum;
 }
@@ -119,8 +119,8 @@ __device__ __forceinline__ At4Item at4_decode(int item, int npairs, int heads, i
 }
 
 __global__ void __launch_bounds__(AT4_THREADS, 1)
-attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, ld] bf16, box 64 x 128
-                              const __grid_constant__ CUtensorMap tm_kv,  // [T, ld] bf16, box 64 x 64
+attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, ld] h16, box 64 x 128
+                              const __grid_constant__ CUtensorMap tm_kv,  // [T, ld] h16, box 64 x 64
                               const float* __restrict__ bias,             // [B, S_pad]
                               const int* __restrict__ kv_chunks,          // [B]
                               const __grid_constant__ CUtensorMap tm_ctx, // [B, S, heads*128], box 64 x 128 x 1
@@ -247,8 +247,8 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         // of chunks -- more than the softmax it feeds.  Each slot's thread walks the item's ring chunks in
         // order: chunks outside its tile's range only get their ring arrival, the others Q K^T / P V.
         const int slot = (warp == 8) ? 0 : 1;
-        constexpr uint32_t idesc_s = make_idesc_bf16(128, AT4_KC, 0, 0);
-        constexpr uint32_t idesc_o = make_idesc_bf16(128, AT4_D, 0, 1);  // B (= V) is MN-major
+        constexpr uint32_t idesc_s = make_idesc_h16(128, AT4_KC, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc_h16(128, AT4_D, 0, 1);  // B (= V) is MN-major
         const uint32_t t_slot = tmem_base + static_cast<uint32_t>(slot * 256);
         const uint32_t q_addr = sb + AT4_SMEM_Q + slot * AT4_QTILE;
         uint32_t chunk_base = 0;   // ring position of this item's first chunk (lo[0])
@@ -433,12 +433,12 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
             }
           }
           l += sum;
-          tmem_st32(t_s, pk);  // bf16 P over the first 32 columns of S's own buffer
+          tmem_st32(t_s, pk);  // h16 P over the first 32 columns of S's own buffer
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(p_ready + 8u * (slot * 2 + sbuf));
         }
-        // ---- epilogue: O / l -> bf16 -> swizzled 128 x 64 staging tile -> TMA store, twice
+        // ---- epilogue: O / l -> h16 -> swizzled 128 x 64 staging tile -> TMA store, twice
         mbar_wait(o_ready + 8u * slot, o_cnt & 1u);
         ++o_cnt;
         tc_fence_after();
@@ -455,10 +455,10 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-              w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-              w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-              w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+              w.x = pack_h16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+              w.y = pack_h16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+              w.z = pack_h16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+              w.w = pack_h16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
               const int unit = cc * 4 + (i >> 3);
               *reinterpret_cast<uint4*>(ostage + r * 128 + ((unit ^ (r & 7)) << 4)) = w;
             }

@@ -67,8 +67,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = 64 columns (128 B, swizzle-128B) x box_rows.
-int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+// 2-D half row-major [rows, cols] tensor, box = 64 columns (128 B, swizzle-128B) x box_rows.
+int make_tmap_h16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
                    uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -76,7 +76,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -85,9 +85,9 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
   return B2E_OK;
 }
 
-// 3-D bf16 [batch, rows, cols] tensor (contiguous), box = 64 columns x box_rows x 1: used for
+// 3-D half [batch, rows, cols] tensor (contiguous), box = 64 columns x box_rows x 1: used for
 // per-sequence TMA stores that must clip at the end of EACH sequence, not only at the tensor end.
-int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows,
+int make_tmap_h16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows,
                       uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -95,7 +95,7 @@ int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_
   cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -163,10 +163,10 @@ int ensure_smem_attr(Kern kern, int bytes) {
 // ---------------------------------------------------------------- launches
 template <int BN, int STAGES, int EPI>
 int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                    const float* bias, const bf16* resid, int M, int N, int K, int sms,
+                    const float* bias, const h16* resid, int M, int N, int K, int sms,
                     cudaStream_t st) {
   using Cfg = GemmCfg<BN, STAGES>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, EPI>;
+  auto kern = gemm_h16_tcgen05_kernel<BN, STAGES, EPI>;
   {
     const int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES);
     if (arc) return arc;
@@ -201,7 +201,7 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
 
 template <int BN, int STAGES>
 int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                   const float* bias, const bf16* resid, int M, int N, int K, int epi, int sms,
+                   const float* bias, const h16* resid, int M, int N, int K, int epi, int sms,
                    cudaStream_t st) {
   switch (epi) {
     case B2E_EPI_BIAS:
@@ -242,10 +242,10 @@ int check_gemm_shape(int M, int N, int K) {
 
 template <int STAGES, int EPI>
 int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                     const float* bias, const bf16* resid, int M, int N, int K, int sms,
+                     const float* bias, const h16* resid, int M, int N, int K, int sms,
                      cudaStream_t st) {
   using Cfg = Gemm2Cfg<STAGES>;
-  auto kern = gemm2_bf16_pair_kernel<STAGES, EPI>;
+  auto kern = gemm2_h16_pair_kernel<STAGES, EPI>;
   {
     const int arc = ensure_smem_attr(kern, Cfg::SMEM_BYTES);
     if (arc) return arc;
@@ -261,12 +261,12 @@ int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 // A map: [M,K] box 128 rows; W map: [N,K] box gemm_bn_for(N) rows.
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const float* bias,
                 const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
-  const bf16* r = static_cast<const bf16*>(resid);
+  const h16* r = static_cast<const h16*>(resid);
   // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
   CUtensorMap tout;
   int rc;
   const int n_out = (epi == B2E_EPI_SWIGLU) ? N / 2 : N;   // SwiGLU writes silu(gate)*up: [M, N/2]
-  if ((rc = make_tmap_bf16(&tout, out, M, n_out, GEMM_OUT_BOX_ROWS))) return rc;
+  if ((rc = make_tmap_h16(&tout, out, M, n_out, GEMM_OUT_BOX_ROWS))) return rc;
   if (N % 256 == 0 && gemm_use_pair()) {
     constexpr int PS = 5;   // 5 x 32 KiB stages + two staging tiles per epilogue warp
     switch (epi) {
@@ -337,7 +337,7 @@ int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaSt
 
 // Softmax variant of the head_dim-64 attention kernel (template parameter V of attention3_d64_kernel);
 // B2E_ATT3=<n> or b2e_debug_set_att3_variant picks one of the instantiated ones for A/B measurements.
-constexpr int AT3_DEFAULT_VARIANT = 0;
+constexpr int AT3_DEFAULT_VARIANT = 5;   // plain-chunk count + one exponential in four on the FMA pipe (profiles/r02_att_bench_variants_v1.log)
 int g_att3_variant = -1;
 inline int att3_variant() {
   if (g_att3_variant < 0) {
@@ -369,7 +369,7 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   const int grid = items < sms ? (int)items : sms;
   CUtensorMap tctx;  // [B, S, H]: the output store clips rows >= S per sequence
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
+  if ((rc = make_tmap_h16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
   switch (att3_variant()) {
     case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
     case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
@@ -393,9 +393,9 @@ int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, in
   const uint64_t ld = (uint64_t)(heads + 2 * kv_heads) * AT4_D;
   CUtensorMap tq, tkv, tctx;
   int rc;
-  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, ld, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, ld, AT4_KC))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT4_D, 128))) return rc;
+  if ((rc = make_tmap_h16(&tq, qkv, (uint64_t)B * S, ld, 128))) return rc;
+  if ((rc = make_tmap_h16(&tkv, qkv, (uint64_t)B * S, ld, AT4_KC))) return rc;
+  if ((rc = make_tmap_h16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT4_D, 128))) return rc;
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
   const int grid = items < sms ? (int)items : sms;
@@ -545,9 +545,9 @@ struct B2EEncoder {
   std::vector<const void*> w;
   int device = 0;
   int sms = 0;
-  // activations (bf16)
+  // activations (h16)
   size_t cap_tokens = 0;
-  bf16 *hidden = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
+  h16 *hidden = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
   PoolScratch pool;
   AttnScratch attn;
   // weight tensor maps, one per layer
@@ -670,11 +670,11 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
 
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
-  if ((rc = make_tmap_bf16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
-  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
+  if ((rc = make_tmap_h16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ctx, e->ctx, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
 
   for (int l = 0; l < d.num_layers; ++l) {
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->L(l, 1), nullptr, M,
@@ -686,7 +686,7 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), nullptr, M, H, H,
                           B2E_EPI_BIAS, e->sms, st)))
       return rc;
-    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+    DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->tmp, e->hidden, (const float*)e->L(l, 4), (const float*)e->L(l, 5),
                        e->hidden, M, d.eps)));
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->L(l, 7), nullptr, M, I,
@@ -696,7 +696,7 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
                           B2E_EPI_BIAS, e->sms, st)))
       return rc;
     if (l + 1 < d.num_layers) {
-      DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+      DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
                          e->hidden, M, d.eps)));
     }
@@ -708,7 +708,7 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
 // ESM-2 (pre-LayerNorm, rotary): transformers/models/esm/modeling_esm.py:189-234 (embeddings with
 // token dropout), :318-362 (attention, rotary on q/k), :386-404 / :446-483 (pre-LN blocks).  The
 // residual stream e->xres stays fp32; each add_layernorm call folds the previous GEMM output into it
-// and emits the next GEMM's bf16 input.  Leaves xres (before the last FFN output is added) and e->tmp
+// and emits the next GEMM's h16 input.  Leaves xres (before the last FFN output is added) and e->tmp
 // (that FFN-down output): the caller applies emb_layer_norm_after to xres + tmp.
 int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
                   cudaStream_t st) {
@@ -722,13 +722,13 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
-  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
+  if ((rc = make_tmap_h16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ctx, e->ctx, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
 
-  DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+  DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      e->xres, nullptr, (const float*)e->E(0, 0), (const float*)e->E(0, 1), e->hidden,
                      M, d.eps)));
   const long long rope_work = (long long)M * d.heads * 2;
@@ -743,7 +743,7 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->E(l, 5), nullptr, M, H, H,
                           B2E_EPI_BIAS, e->sms, st)))
       return rc;
-    DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+    DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->xres, e->tmp, (const float*)e->E(l, 6), (const float*)e->E(l, 7), e->hidden,
                        M, d.eps)));
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->E(l, 9), nullptr, M, I, H,
@@ -753,7 +753,7 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
                           B2E_EPI_BIAS, e->sms, st)))
       return rc;
     if (l + 1 < L) {
-      DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->E(l + 1, 0), (const float*)e->E(l + 1, 1),
                          e->hidden, M, d.eps)));
     }
@@ -777,11 +777,11 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn;
-  if ((rc = make_tmap_bf16(&tm_hidden, e->hidden, M, H, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ctx, e->ctx, M, CC, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ctx, e->ctx, M, CC, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ffn, e->ffn, M, I, 128))) return rc;
 
-  DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+  DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      e->xres, nullptr, (const float*)e->Mi(0, 0), e->hidden, M, d.eps)));
   const int n_rot = d.heads + d.kv_heads;   // q heads and k heads are adjacent columns of qkv
   const long long rope_work = (long long)M * n_rot;
@@ -797,7 +797,7 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, CC, B2E_EPI_BIAS,
                           e->sms, st)))
       return rc;
-    DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+    DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->xres, e->tmp, (const float*)e->Mi(l, 3), e->hidden, M, d.eps)));
     // gate and up in one GEMM (interleaved rows), silu(gate) * up in its epilogue: [M, I]
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, nullptr, nullptr, M, 2 * I, H,
@@ -807,7 +807,7 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
                           e->sms, st)))
       return rc;
     if (l + 1 < L) {
-      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->Mi(l + 1, 0), e->hidden, M, d.eps)));
     }
   }
@@ -934,10 +934,10 @@ int create_mistral(const B2EModelDesc* desc, const void* const* weights, int n_w
   e->sms = info.sms;
   e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
   for (int l = 0; l < L; ++l) {
-    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], e->Mi(l, 1), QC, H, gemm_bn_for(QC))) ||
-        (rc = make_tmap_bf16(&e->tm_wo[l], e->Mi(l, 2), H, CC, gemm_bn_for(H))) ||
-        (rc = make_tmap_bf16(&e->tm_w1[l], e->Mi(l, 4), 2 * I, H, gemm_bn_for(2 * I))) ||
-        (rc = make_tmap_bf16(&e->tm_w2[l], e->Mi(l, 5), H, I, gemm_bn_for(H)))) {
+    if ((rc = make_tmap_h16(&e->tm_wqkv[l], e->Mi(l, 1), QC, H, gemm_bn_for(QC))) ||
+        (rc = make_tmap_h16(&e->tm_wo[l], e->Mi(l, 2), H, CC, gemm_bn_for(H))) ||
+        (rc = make_tmap_h16(&e->tm_w1[l], e->Mi(l, 4), 2 * I, H, gemm_bn_for(2 * I))) ||
+        (rc = make_tmap_h16(&e->tm_w2[l], e->Mi(l, 5), H, I, gemm_bn_for(H)))) {
       delete e;
       return rc;
     }
@@ -990,10 +990,10 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
     const void* wo = esm ? e->E(l, 4) : e->L(l, 2);
     const void* w1 = esm ? e->E(l, 8) : e->L(l, 6);
     const void* w2 = esm ? e->E(l, 10) : e->L(l, 8);
-    if ((rc = make_tmap_bf16(&e->tm_wqkv[l], wqkv, 3 * H, H, gemm_bn_for(3 * H))) ||
-        (rc = make_tmap_bf16(&e->tm_wo[l], wo, H, H, gemm_bn_for(H))) ||
-        (rc = make_tmap_bf16(&e->tm_w1[l], w1, I, H, gemm_bn_for(I))) ||
-        (rc = make_tmap_bf16(&e->tm_w2[l], w2, H, I, gemm_bn_for(H)))) {
+    if ((rc = make_tmap_h16(&e->tm_wqkv[l], wqkv, 3 * H, H, gemm_bn_for(3 * H))) ||
+        (rc = make_tmap_h16(&e->tm_wo[l], wo, H, H, gemm_bn_for(H))) ||
+        (rc = make_tmap_h16(&e->tm_w1[l], w1, I, H, gemm_bn_for(I))) ||
+        (rc = make_tmap_h16(&e->tm_w2[l], w2, H, I, gemm_bn_for(H)))) {
       delete e;
       return rc;
     }
@@ -1044,8 +1044,8 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
   int rc;
   if ((rc = validate_batch(e, B, S))) return rc;
   if (!ids || !mask || !out_hidden) return fail(B2E_ERR_INVALID, "null tensor pointer");
-  if (out_dtype != B2E_DTYPE_F32 && out_dtype != B2E_DTYPE_BF16)
-    return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or BF16");
+  if (out_dtype != B2E_DTYPE_F32 && out_dtype != B2E_DTYPE_F16)
+    return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or F16");
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_workspace(e, B, S))) return rc;
   const B2EModelDesc& d = e->desc;
@@ -1057,8 +1057,8 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
       DISPATCH_NV(H, (add_rmsnorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->w[1], (float*)out_hidden, M, d.eps)));
     } else {
-      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->w[1], (bf16*)out_hidden, M, d.eps)));
+      DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->w[1], (h16*)out_hidden, M, d.eps)));
     }
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
@@ -1071,9 +1071,9 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
                          e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
                          (float*)out_hidden, M, d.eps)));
     } else {
-      DISPATCH_NV(H, (add_layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
-                         (bf16*)out_hidden, M, d.eps)));
+                         (h16*)out_hidden, M, d.eps)));
     }
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
@@ -1084,9 +1084,9 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
                        e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
                        (float*)out_hidden, M, d.eps)));
   } else {
-    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+    DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
-                       (bf16*)out_hidden, M, d.eps)));
+                       (h16*)out_hidden, M, d.eps)));
   }
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
@@ -1380,7 +1380,7 @@ int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
   return B2E_OK;
 }
 
-int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+int b2e_gemm_f16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epi, void* stream) {
   if (!A || !W || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");  // bias may be null
   if (epi == B2E_EPI_BIAS_RESID && !resid) return fail(B2E_ERR_INVALID, "resid epilogue needs resid");
@@ -1391,8 +1391,8 @@ int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* r
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;
   CUtensorMap ta, tb;
-  if ((rc = make_tmap_bf16(&ta, A, M, K, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tb, W, N, K, gemm_bn_for(N)))) return rc;
+  if ((rc = make_tmap_h16(&ta, A, M, K, 128))) return rc;
+  if ((rc = make_tmap_h16(&tb, W, N, K, gemm_bn_for(N)))) return rc;
   return launch_gemm(ta, tb, out, bias, resid, M, N, K, epi, info.sms, (cudaStream_t)stream);
 }
 
@@ -1406,8 +1406,8 @@ int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, in
   if ((rc = current_device_info(&info))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tq, tkv;
-  if ((rc = make_tmap_bf16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, AT3_KC))) return rc;
+  if ((rc = make_tmap_h16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, 128))) return rc;
+  if ((rc = make_tmap_h16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, AT3_KC))) return rc;
   if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
   return launch_attention(tq, tkv, g_attn_scratch, ctx, B, S, heads, info.sms, st);
 }
@@ -1650,12 +1650,12 @@ int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* o
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == B2E_DTYPE_F32) {
     DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
-                       (const bf16*)in, nullptr, gamma, beta, (float*)out, rows, eps)));
-  } else if (out_dtype == B2E_DTYPE_BF16) {
-    DISPATCH_NV(H, (layernorm_kernel<NV, bf16><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
-                       (const bf16*)in, nullptr, gamma, beta, (bf16*)out, rows, eps)));
+                       (const h16*)in, nullptr, gamma, beta, (float*)out, rows, eps)));
+  } else if (out_dtype == B2E_DTYPE_F16) {
+    DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
+                       (const h16*)in, nullptr, gamma, beta, (h16*)out, rows, eps)));
   } else {
-    return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or BF16");
+    return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or F16");
   }
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;

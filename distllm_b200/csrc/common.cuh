@@ -7,12 +7,20 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b2e {
 
-using bf16 = __nv_bfloat16;
+using bf16 = __nv_bfloat16;   // only at the API surface (hidden states / corpora a caller hands in as bf16)
+// The 16-bit storage type of every weight matrix and every activation between kernels.  IEEE half, not
+// bfloat16: both feed the tensor cores at the same rate, but half keeps 11 significand bits against 8, and
+// with bfloat16 the per-operator rounding alone (1.7e-3 relative, profiles/r02_stage_errors_bf16.log) drifts
+// a 32-layer Mistral-shaped model 1.6e-3 in cosine away from the fp32 reference (tolerance 1e-3;
+// profiles/r02_drift_report_bf16.md).  The reference's own reduced-precision mode is half as well
+// (half_precision -> model.half(), distllm/embed/encoders/auto.py:77-79).  Conversions saturate at +-65504.
+using h16 = __half;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -327,25 +335,38 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
-//   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
+// Instruction descriptor for kind::f16 with half A/B and fp32 accumulation.
+//   [4,6) D format (1 = f32)  [7,10) A format (0 = f16, 1 = bf16)  [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major (0 = K)      [16] B major (0 = K, 1 = MN)
 //   [17,23) N >> 3            [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
-                                                       int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_h16(int M, int N, int a_mn_major,
+                                                      int b_mn_major) {
+  // A / B format fields [7,10) / [10,13): 0 = f16 (h16 operands), 1 = bf16
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ small math / packing
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// two floats -> packed half2 (lo in the low 16 bits), round to nearest, saturating to +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+__device__ __forceinline__ float2 unpack_h16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// bf16 pairs of a caller-provided bf16 corpus (top-k scan)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+__device__ __forceinline__ h16 to_h16(float x) {
+  h16 r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(*reinterpret_cast<unsigned short*>(&r)) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

@@ -1,9 +1,9 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias)
+// Persistent warp-specialised h16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias)
 //
 //   warp 0      TMA producer   (one elected lane): A/W tiles -> 128B-swizzled smem ring
 //   warp 1      MMA issuer     (one elected lane): tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld -> +bias (-> erf-GELU | +residual) -> bf16 -> per-warp
+//   warps 4-11  epilogue: tcgen05.ld -> +bias (-> erf-GELU | +residual) -> h16 -> per-warp
 //               swizzled smem tile (32 rows x 64 cols) -> TMA store (cp.async.bulk.tensor)
 //
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
@@ -27,7 +27,7 @@ namespace b2e {
 enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_SWIGLU = 3 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_BK = 64;  // 64 h16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_OUT_BOX_ROWS = 32;   // TMA store box: 64 columns x 32 rows (one warp's chunk)
@@ -49,11 +49,11 @@ struct GemmCfg {
 // erf-GELU, x * Phi(x), with Phi from the Abramowitz-Stegun 7.1.26 erfc polynomial
 // (|erf error| <= 1.5e-7): gelu(x) = max(x,0) - 0.5*|x|*poly(t)*exp(-x^2/2), t = 1/(1 + p*|x|/sqrt2).
 // ~14 FP instructions + 2 MUFU per element instead of libdevice erff's ~35: the FFN-up epilogue
-// is issue-bound, and the output is rounded to bf16 (2^-9) anyway.
+// is issue-bound, and the output is rounded to h16 (2^-9) anyway.
 // Cheaper variant used by the FFN-up epilogue: erf(x/sqrt2) ~= tanh(x * Q(x^2)) with a cubic Q fitted
 // to erf itself (max |erf error| 1.4e-5 before the hardware tanh), one MUFU (tanh.approx.f32, abs error
 // ~5e-4) instead of two.  gelu(x) = 0.5 x (1 + erf(x/sqrt2)).  Total absolute error <= ~3e-4 |x|,
-// i.e. below the bf16 rounding (2^-9 relative) the output goes through anyway.
+// i.e. below the h16 rounding (2^-9 relative) the output goes through anyway.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float xc = fminf(fmaxf(x, -5.65685f), 5.65685f);  // |x|/sqrt2 <= 4: the fit's range
   const float v = xc * xc;
@@ -80,12 +80,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // Epilogue of one 32-row x 64-column chunk held as two 32-column TMEM reads: bias (+GELU / +resid),
-// bf16, into the warp's swizzled staging tile (row = lane).  `resid_row` points at this lane's
+// h16, into the warp's swizzled staging tile (row = lane).  `resid_row` points at this lane's
 // row, first column of the chunk (only read when EPI == EPI_BIAS_RESID and the row exists).
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32],
                                                     const float* __restrict__ bias_smem,
-                                                    const bf16* __restrict__ resid_row, bool row_ok,
+                                                    const h16* __restrict__ resid_row, bool row_ok,
                                                     uint8_t* staging, int lane) {
 #pragma unroll
   for (int u = 0; u < 8; ++u) {  // 16-byte unit = 8 columns
@@ -114,17 +114,17 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32]
     if (EPI == EPI_BIAS_RESID) {
       if (row_ok) {
         const uint4 rr = *reinterpret_cast<const uint4*>(resid_row + u * 8);
-        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                     r3 = unpack_bf16x2(rr.w);
+        const float2 r0 = unpack_h16x2(rr.x), r1 = unpack_h16x2(rr.y), r2 = unpack_h16x2(rr.z),
+                     r3 = unpack_h16x2(rr.w);
         v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
         v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack_h16x2(v[0], v[1]);
+    o.y = pack_h16x2(v[2], v[3]);
+    o.z = pack_h16x2(v[4], v[5]);
+    o.w = pack_h16x2(v[6], v[7]);
     // 128B-swizzle: unit index XOR (row & 7) -- conflict-free for "one row per lane" writes and
     // exactly the layout the SWIZZLE_128B tensor map expects
     *reinterpret_cast<uint4*>(staging + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[2][32]
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_chunk_gbias(const uint32_t (&acc)[2][32],
                                                           const float* __restrict__ bias,
-                                                          const bf16* __restrict__ resid_row,
+                                                          const h16* __restrict__ resid_row,
                                                           bool row_ok, uint8_t* staging, int lane) {
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -162,23 +162,23 @@ __device__ __forceinline__ void gemm_epilogue_chunk_gbias(const uint32_t (&acc)[
     if (EPI == EPI_BIAS_RESID) {
       if (row_ok) {
         const uint4 rr = *reinterpret_cast<const uint4*>(resid_row + u * 8);
-        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                     r3 = unpack_bf16x2(rr.w);
+        const float2 r0 = unpack_h16x2(rr.x), r1 = unpack_h16x2(rr.y), r2 = unpack_h16x2(rr.z),
+                     r3 = unpack_h16x2(rr.w);
         v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
         v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack_h16x2(v[0], v[1]);
+    o.y = pack_h16x2(v[2], v[3]);
+    o.z = pack_h16x2(v[4], v[5]);
+    o.w = pack_h16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(staging + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
   }
 }
 
 // SwiGLU epilogue of one 32-row x 64-output chunk: g, u = the gate / up accumulators (two 32-column
-// TMEM reads each); silu(g) * u -> bf16 -> the warp's swizzled staging tile.
+// TMEM reads each); silu(g) * u -> h16 -> the warp's swizzled staging tile.
 // silu(g) = g / (1 + 2^(-g log2 e)): one ex2 + one rcp per element (hidden under the K loop's MMAs).
 __device__ __forceinline__ void gemm_swiglu_chunk(const uint32_t (&g)[2][32],
                                                   const uint32_t (&u)[2][32], uint8_t* staging,
@@ -196,20 +196,20 @@ __device__ __forceinline__ void gemm_swiglu_chunk(const uint32_t (&g)[2][32],
       v[e] = x * r * __uint_as_float(uu[e]);
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack_h16x2(v[0], v[1]);
+    o.y = pack_h16x2(v[2], v[3]);
+    o.z = pack_h16x2(v[4], v[5]);
+    o.w = pack_h16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(staging + lane * 128 + ((un ^ (lane & 7)) << 4)) = o;
   }
 }
 
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] box 64 x 128
+gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] box 64 x 128
                          const __grid_constant__ CUtensorMap tm_b,    // [N,K] box 64 x BN
                          const __grid_constant__ CUtensorMap tm_out,  // [M,N] box 64 x 32
-                         const float* __restrict__ bias, const bf16* __restrict__ resid, int M,
+                         const float* __restrict__ bias, const h16* __restrict__ resid, int M,
                          int N, int K) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -274,7 +274,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] b
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_h16(GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -321,7 +321,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] b
       const bool row_ok = row < M;
       const int col0 = half * COLS_PER_WARP;       // first column of this warp inside the tile
       const int gcol0 = n_blk * BN + col0;
-      const bf16* resid_row =
+      const h16* resid_row =
           (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       // the tile's bias slice goes to smem before the accumulator wait (double-buffered by `as`)

@@ -1,4 +1,4 @@
-// CTA-pair bf16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias),  N % 256 == 0.
+// CTA-pair h16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias),  N % 256 == 0.
 //
 // Two CTAs of one cluster (the two SMs of a TPC) cooperate on a 256 x 256 output tile with
 // tcgen05.mma.cta_group::2 (256 x 256 x 16): each CTA stages its own 128 rows of A and only HALF of
@@ -47,10 +47,10 @@ __device__ int g_gemm2_flags = 0;                // 1 skip epilogue math+stores,
 
 template <int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box 64 x 128
+gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box 64 x 128
                        const __grid_constant__ CUtensorMap tm_b,    // [N,K], box 64 x 128
                        const __grid_constant__ CUtensorMap tm_out,  // [M,N] (SwiGLU: [M,N/2]), box 64 x 32
-                       const float* __restrict__ bias, const bf16* __restrict__ resid, int M, int N,
+                       const float* __restrict__ bias, const h16* __restrict__ resid, int M, int N,
                        int K) {
   using Cfg = Gemm2Cfg<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,7 +135,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, G2_BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_h16(256, G2_BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -186,7 +186,7 @@ gemm2_bf16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], bo
       const bool row_ok = row < M;
       const int col0 = half * COLS_PER_WARP;
       const int gcol0 = n_blk * G2_BN + col0;
-      const bf16* resid_row =
+      const h16* resid_row =
           (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       if (stamp) G2_STAMP(1);

@@ -50,10 +50,10 @@ __device__ __forceinline__ void warp_rmsnorm(float (&x)[NV][8], const float* __r
 }
 
 // Residual stream update fused with the next RMSNorm:
-//   xres += add (bf16 GEMM output; nullptr on the very first call);  out = RMSNorm(xres) * gamma
+//   xres += add (h16 GEMM output; nullptr on the very first call);  out = RMSNorm(xres) * gamma
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
-add_rmsnorm_kernel(float* __restrict__ xres, const bf16* __restrict__ add,
+add_rmsnorm_kernel(float* __restrict__ xres, const h16* __restrict__ add,
                    const float* __restrict__ gamma, OutT* __restrict__ out, int rows, float eps) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
@@ -81,7 +81,7 @@ add_rmsnorm_kernel(float* __restrict__ xres, const bf16* __restrict__ add,
 //   out[b] = RMSNorm(xres[b*S + idx[b]] + add[b*S + idx[b]]) * gamma        (fp32 [B,H])
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-rmsnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+rmsnorm_gather_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                       const float* __restrict__ gamma, const int* __restrict__ idx,
                       float* __restrict__ out, int B, int S, float eps) {
   constexpr int H = NV * 256;
@@ -107,7 +107,7 @@ rmsnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ a
 // ESM-2 last-token pooling: out[b] = LayerNorm(xres[row] + add[row]) for the B selected rows (fp32 [B,H]).
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-addnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+addnorm_gather_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const int* __restrict__ idx, float* __restrict__ out, int B, int S, float eps) {
   constexpr int H = NV * 256;
@@ -136,7 +136,7 @@ addnorm_gather_kernel(const float* __restrict__ xres, const bf16* __restrict__ a
 // grid = (B, nsplit); each warp walks rows s = split*rows_per + warp, += ROW_WARPS (as layernorm_pool_kernel).
 template <int NV, bool RMS>
 __global__ void __launch_bounds__(ROW_THREADS)
-addnorm_pool_kernel(const float* __restrict__ xres, const bf16* __restrict__ add,
+addnorm_pool_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ w, float* __restrict__ part, int S, int rows_per, float eps) {
   constexpr int H = NV * 256;
@@ -190,22 +190,22 @@ __global__ void rope_table_theta_kernel(float* __restrict__ cos_t, float* __rest
 // halves of 64; q heads are followed directly by the k heads, so one pass rotates both):
 //   out[i] = x[i] cos_i - x[i+64] sin_i ;  out[i+64] = x[i+64] cos_i + x[i] sin_i   (position = t % S)
 // One warp per (token, head); a lane owns frequencies lane and lane + 32.
-__global__ void rope_d128_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_t,
+__global__ void rope_d128_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t,
                                  const float* __restrict__ sin_t, int T, int S, int n_rot, int ld) {
   const int lane = threadIdx.x & 31;
   const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= static_cast<long long>(T) * n_rot) return;
   const int t = static_cast<int>(w / n_rot);
   const int hd = static_cast<int>(w % n_rot);
-  bf16* p = qkv + static_cast<size_t>(t) * ld + hd * 128;
+  h16* p = qkv + static_cast<size_t>(t) * ld + hd * 128;
   const int pos = t % S;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int i = lane + 32 * k;
     const float c = cos_t[pos * 64 + i], s = sin_t[pos * 64 + i];
-    const float x1 = __bfloat162float(p[i]), x2 = __bfloat162float(p[i + 64]);
-    p[i] = __float2bfloat16_rn(x1 * c - x2 * s);
-    p[i + 64] = __float2bfloat16_rn(x2 * c + x1 * s);
+    const float x1 = __half2float(p[i]), x2 = __half2float(p[i + 64]);
+    p[i] = to_h16(x1 * c - x2 * s);
+    p[i + 64] = to_h16(x2 * c + x1 * s);
   }
 }
 

@@ -14,11 +14,15 @@ constexpr int ROW_WARPS = 8;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 
 // ---- 8-element vector load/store helpers (lane owns columns v*256 + lane*8 .. +8)
-__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {   // bf16 hidden states at the API
   const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
-               d = unpack_bf16x2(u.w);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
 }
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -35,13 +39,19 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+__device__ __forceinline__ void store8(h16* p, const float (&v)[8]) {
   uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
+  u.x = pack_h16x2(v[0], v[1]);
+  u.y = pack_h16x2(v[2], v[3]);
+  u.z = pack_h16x2(v[4], v[5]);
+  u.w = pack_h16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {   // b2e_encode(out_dtype = BF16)
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h);
 }
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -78,14 +88,14 @@ __device__ __forceinline__ void warp_layernorm(float (&x)[NV][8], const float* _
   }
 }
 
-// BERT embeddings: word[ids] + position[t % S] + type[type_ids] -> LayerNorm -> bf16 hidden.
+// BERT embeddings: word[ids] + position[t % S] + type[type_ids] -> LayerNorm -> h16 hidden.
 // (transformers/models/bert/modeling_bert.py:72-112)
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 embed_layernorm_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
                        const float* __restrict__ word, const float* __restrict__ pos,
                        const float* __restrict__ type, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, bf16* __restrict__ out, int rows, int S,
+                       const float* __restrict__ beta, h16* __restrict__ out, int rows, int S,
                        float eps) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
@@ -112,7 +122,7 @@ embed_layernorm_kernel(const int64_t* __restrict__ ids, const int64_t* __restric
 
 // x = in (+ resid when given): the residual add of the transformer block rides on the LayerNorm's
 // coalesced row reads instead of the GEMM epilogue's one-row-per-lane accesses.
-__device__ __forceinline__ void load8_residual(const bf16* in, const bf16* resid, float (&x)[8]) {
+__device__ __forceinline__ void load8_residual(const h16* in, const h16* resid, float (&x)[8]) {
   load8(in, x);
   if (resid != nullptr) {
     float r[8];
@@ -122,11 +132,11 @@ __device__ __forceinline__ void load8_residual(const bf16* in, const bf16* resid
   }
 }
 
-// LayerNorm over rows of a bf16 matrix, optionally of (in + resid).  `out` may alias `resid`
+// LayerNorm over rows of a h16 matrix, optionally of (in + resid).  `out` may alias `resid`
 // (each warp reads its whole row before writing it).
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_kernel(const bf16* __restrict__ in, const bf16* resid, const float* __restrict__ gamma,
+layernorm_kernel(const h16* __restrict__ in, const h16* resid, const float* __restrict__ gamma,
                  const float* __restrict__ beta, OutT* out, int rows, float eps) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
@@ -146,7 +156,7 @@ layernorm_kernel(const bf16* __restrict__ in, const bf16* resid, const float* __
 // LayerNorm of selected rows only: out[b] = LN(in[b*S + idx[b]])  (last-token pooling).
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_gather_kernel(const bf16* __restrict__ in, const bf16* __restrict__ resid,
+layernorm_gather_kernel(const h16* __restrict__ in, const h16* __restrict__ resid,
                         const int* __restrict__ idx, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float* __restrict__ out, int B, int S,
                         float eps) {
@@ -266,7 +276,7 @@ __device__ __forceinline__ void block_store_partial(float (&acc)[NV][8], float* 
 // written.  grid = (B, nsplit); each warp walks rows s = split*rows_per + warp, += ROW_WARPS.
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_pool_kernel(const bf16* __restrict__ in, const bf16* __restrict__ resid,
+layernorm_pool_kernel(const h16* __restrict__ in, const h16* __restrict__ resid,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ w,
                       float* __restrict__ part, int S, int rows_per, float eps) {
@@ -481,11 +491,11 @@ esm_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ ma
 }
 
 // Residual stream update fused with the next LayerNorm (pre-LN blocks):
-//   xres += add (bf16 GEMM output; nullptr on the very first call);  out = LayerNorm(xres)
-// The fp32 residual stream keeps 33 layers of accumulation out of bf16.
+//   xres += add (h16 GEMM output; nullptr on the very first call);  out = LayerNorm(xres)
+// The fp32 residual stream keeps 33 layers of accumulation out of h16.
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
-add_layernorm_kernel(float* __restrict__ xres, const bf16* __restrict__ add,
+add_layernorm_kernel(float* __restrict__ xres, const h16* __restrict__ add,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      OutT* __restrict__ out, int rows, float eps) {
   constexpr int H = NV * 256;
@@ -526,7 +536,7 @@ __global__ void rope_table_kernel(float* __restrict__ cos_t, float* __restrict__
 // In-place rotary embedding of the Q and K thirds of qkv [T, 3H] (head_dim 64, halves of 32):
 //   out[i] = x[i] cos - x[i+32] sin ;  out[i+32] = x[i+32] cos + x[i] sin     (position = t % S)
 // One warp per (token, head pair of Q|K); lane = frequency index i.
-__global__ void rope_qk_kernel(bf16* __restrict__ qkv, const float* __restrict__ cos_t,
+__global__ void rope_qk_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t,
                                const float* __restrict__ sin_t, int T, int S, int heads) {
   const int H = heads * 64;
   const int lane = threadIdx.x & 31;
@@ -535,12 +545,12 @@ __global__ void rope_qk_kernel(bf16* __restrict__ qkv, const float* __restrict__
   if (w >= n_work) return;
   const int t = static_cast<int>(w / (heads * 2));
   const int hk = static_cast<int>(w % (heads * 2));  // [0, heads): q head, [heads, 2*heads): k head
-  bf16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
+  h16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
   const int pos = t % S;
   const float c = cos_t[pos * 32 + lane], s = sin_t[pos * 32 + lane];
-  const float x1 = __bfloat162float(p[lane]), x2 = __bfloat162float(p[lane + 32]);
-  p[lane] = __float2bfloat16_rn(x1 * c - x2 * s);
-  p[lane + 32] = __float2bfloat16_rn(x2 * c + x1 * s);
+  const float x1 = __half2float(p[lane]), x2 = __half2float(p[lane + 32]);
+  p[lane] = to_h16(x1 * c - x2 * s);
+  p[lane + 32] = to_h16(x2 * c + x1 * s);
 }
 
 }  // namespace b2e

@@ -2,7 +2,7 @@
 
 Drop-in for distllm/embed/encoders/auto.py:15-138 -- same config fields and defaults, same
 properties, ``encode`` returns the last hidden state ``[B,S,H]``.  transformers is used only to read
-the checkpoint and to build the tokenizer; the forward pass is libb2e (bf16 tensor-core GEMMs with
+the checkpoint and to build the tokenizer; the forward pass is libb2e (fp16 tensor-core GEMMs with
 fp32 accumulation, fp32 LayerNorm/softmax statistics).  There is no eager/CPU fallback: an
 architecture that is not built raises.
 """
@@ -41,7 +41,7 @@ class AutoEncoderConfig(BaseConfig):
     eval_mode: bool = True
     # Kept for compatibility: there is no tracing compiler in this path
     compile_model: bool = False
-    # Kept for compatibility: NF4 is not reproduced, weights run as bf16 on the tensor cores
+    # Kept for compatibility: NF4 is not reproduced, weights run as fp16 on the tensor cores
     quantization: bool = True
 
 
@@ -63,7 +63,7 @@ class AutoEncoder:
         if config.quantization:
             warnings.warn(
                 'quantization=True (bitsandbytes NF4) is not reproduced by the native encoder; '
-                'running bf16 tensor-core weights instead.',
+                'running fp16 tensor-core weights instead.',
                 stacklevel=2,
             )
         model = AutoModel.from_pretrained(config.pretrained_model_name_or_path)

@@ -90,7 +90,7 @@ class NativeBertEncoder:
     def encode(self, input_ids: torch.Tensor, attention_mask: torch.Tensor,
                token_type_ids: torch.Tensor | None = None,
                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-        """Final hidden state ``[B,S,H]`` (post final LayerNorm) as fp32 or bf16."""
+        """Final hidden state ``[B,S,H]`` (post final LayerNorm) as fp32 or fp16."""
         ids = self._prep(input_ids, 'input_ids')
         mask = self._prep(attention_mask, 'attention_mask')
         types = self._prep(token_type_ids, 'token_type_ids')

@@ -5,11 +5,11 @@ BERT (``B2E_ARCH_BERT``), 5 + 12*L device tensors:
     0 word_embeddings [V,H] f32      1 position_embeddings [P,H] f32   2 token_type_embeddings [T,H] f32
     3 embeddings.LayerNorm.weight    4 embeddings.LayerNorm.bias       (f32 [H])
     per layer l, base = 5 + 12*l:
-      +0 Wqkv [3H,H] bf16 (rows: query | key | value)   +1 bqkv [3H] f32
-      +2 Wo   [H,H]  bf16                               +3 bo   [H]  f32
+      +0 Wqkv [3H,H] f16 (rows: query | key | value)   +1 bqkv [3H] f32
+      +2 Wo   [H,H]  f16                               +3 bo   [H]  f32
       +4 attention.output.LayerNorm.weight  +5 .bias    (f32)
-      +6 W1   [I,H]  bf16 (intermediate.dense)          +7 b1   [I]  f32
-      +8 W2   [H,I]  bf16 (output.dense)                +9 b2   [H]  f32
+      +6 W1   [I,H]  f16 (intermediate.dense)          +7 b1   [I]  f32
+      +8 W2   [H,I]  f16 (output.dense)                +9 b2   [H]  f32
       +10 output.LayerNorm.weight           +11 .bias   (f32)
 
 Names on the right are HF ``BertModel`` state-dict keys (transformers/models/bert/modeling_bert.py).
@@ -24,6 +24,15 @@ from typing import Mapping
 import torch
 
 from distllm_b200 import _native
+
+
+HALF_MAX = 65504.0
+
+
+def to_half(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """Checkpoint matrix (fp32 / f16 / fp16) -> contiguous fp16 device tensor, saturating at +-65504 (weights
+    never get near it; the clamp only keeps a broken checkpoint from turning into inf)."""
+    return t.detach().to(device=device, dtype=torch.float32).clamp_(-HALF_MAX, HALF_MAX).to(torch.float16).contiguous()
 
 
 def bert_desc(hf_config) -> _native.ModelDesc:
@@ -64,7 +73,7 @@ def bert_weight_list(
         return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
 
     def b16(t: torch.Tensor) -> torch.Tensor:
-        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+        return to_half(t, device)
 
     out = [
         f32('embeddings.word_embeddings.weight'),
@@ -143,11 +152,11 @@ def random_bert_state_dict(hf_config, seed: int = 0, device: torch.device | str 
 #     1 encoder.emb_layer_norm_after.weight   2 .bias                         (f32 [H])
 #     per layer l, base = 3 + 12*l (pre-LayerNorm blocks):
 #       +0 attention.LayerNorm.weight  +1 .bias                 (LN before self-attention)
-#       +2 Wqkv [3H,H] bf16 (query | key | value)               +3 bqkv [3H] f32
-#       +4 attention.output.dense.weight [H,H] bf16             +5 .bias
+#       +2 Wqkv [3H,H] f16 (query | key | value)               +3 bqkv [3H] f32
+#       +4 attention.output.dense.weight [H,H] f16             +5 .bias
 #       +6 LayerNorm.weight            +7 .bias                 (LN before the feed-forward)
-#       +8 intermediate.dense.weight [I,H] bf16                 +9 .bias
-#       +10 output.dense.weight [H,I] bf16                      +11 .bias
+#       +8 intermediate.dense.weight [I,H] f16                 +9 .bias
+#       +10 output.dense.weight [H,I] f16                      +11 .bias
 #
 # ``B2EModelDesc.reserved`` carries ``mask_token_id + 1`` when ``token_dropout`` is on (0 = off).
 
@@ -190,7 +199,7 @@ def esm_weight_list(
         return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
 
     def b16(t: torch.Tensor) -> torch.Tensor:
-        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+        return to_half(t, device)
 
     out = [
         f32('embeddings.word_embeddings.weight'),
@@ -259,14 +268,14 @@ def random_esm_state_dict(hf_config, seed: int = 0, device: torch.device | str =
 #     0 embed_tokens [V,H] f32          1 norm.weight [H] f32 (final RMSNorm)
 #     per layer l, base = 2 + 6*l:
 #       +0 input_layernorm.weight [H] f32
-#       +1 Wqkv [(heads + 2*kv_heads)*d, H] bf16 (rows: q_proj | k_proj | v_proj)
-#       +2 Wo   [H, heads*d] bf16
+#       +1 Wqkv [(heads + 2*kv_heads)*d, H] f16 (rows: q_proj | k_proj | v_proj)
+#       +2 Wo   [H, heads*d] f16
 #       +3 post_attention_layernorm.weight [H] f32
-#       +4 Wgu  [2I, H] bf16: gate_proj and up_proj interleaved in blocks of 64 rows
+#       +4 Wgu  [2I, H] f16: gate_proj and up_proj interleaved in blocks of 64 rows
 #               (rows [128t, 128t+64) = gate rows [64t, 64t+64); rows [128t+64, 128t+128) = up rows
 #               [64t, 64t+64)), so that one GEMM tile holds gate and up of the same 64 outputs and
 #               the SwiGLU product is taken in the epilogue
-#       +5 Wd   [H, I] bf16 (down_proj)
+#       +5 Wd   [H, I] f16 (down_proj)
 #
 # Names are HF ``MistralModel`` state-dict keys (transformers/models/mistral/modeling_mistral.py).
 
@@ -327,7 +336,7 @@ def mistral_weight_list(
         return sd[key].detach().to(device=device, dtype=torch.float32).contiguous()
 
     def b16(t: torch.Tensor) -> torch.Tensor:
-        return t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+        return to_half(t, device)
 
     out = [f32('embed_tokens.weight'), f32('norm.weight')]
     for layer in range(num_layers):

@@ -21,7 +21,7 @@
  *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
  *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
  *   b2e_topk_ip             distllm/rag/search.py:280-336 (exact float32 search of the query path)
- *   b2e_gemm_bf16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
+ *   b2e_gemm_f16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
  *                           blocks, exported so the parity tests can pin each kernel separately.
  */
 #ifndef B2E_H_
@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2E_ABI_VERSION 1
+#define B2E_ABI_VERSION 2   /* 2: 16-bit weights / activations are IEEE half (were bfloat16); b2e_gemm_f16 */
 
 enum {
   B2E_OK = 0,
@@ -81,7 +81,9 @@ const char* b2e_last_error(void);
 
 /* Number of device weight pointers b2e_encoder_create expects for `desc` (BERT: 5 + 12*L, ESM-2:
  * 3 + 12*L, Mistral: 2 + 6*L; order documented in distllm_b200/embed/encoders/weights.py).  Matrices
- * are bf16 [out,in] row-major, vectors and embedding tables fp32.  The pointers stay owned by the
+ * are IEEE half (fp16) [out,in] row-major, vectors and embedding tables fp32.  (fp16, not bf16: the
+ * tensor cores run both at the same rate and fp16 keeps 11 significand bits; the reference's own reduced
+ * precision is fp16 too, distllm/embed/encoders/auto.py:77-79.  Values outside +-65504 saturate.)  The pointers stay owned by the
  * caller and must outlive the handle.  For B2E_ARCH_ESM2, desc.reserved = mask_token_id + 1 enables
  * ESM's token dropout rescaling (0 = off) and token_type_ids are ignored.  For B2E_ARCH_MISTRAL
  * (head_dim 128, heads % kv_heads == 0, intermediate % 128 == 0) the gate/up projection is ONE matrix
@@ -100,7 +102,7 @@ void b2e_encoder_destroy(B2EEncoder* enc);
 /* Bytes of device workspace the handle holds for a [B,S] batch (grown lazily, never shrunk). */
 int64_t b2e_workspace_bytes(const B2EEncoder* enc, int B, int S);
 
-/* Full forward pass; writes the final hidden state [B,S,H] as out_dtype (F32 or BF16). */
+/* Full forward pass; writes the final hidden state [B,S,H] as out_dtype (F32 or F16). */
 int b2e_encode(B2EEncoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
                const int64_t* token_type_ids /* nullable */, int B, int S, void* out_hidden,
                int out_dtype, void* stream);
@@ -131,8 +133,8 @@ int b2e_l2_normalize(float* x, int64_t n_rows, int H, void* stream);
 int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
                              const int32_t* doc_id, float* out, void* stream);
 
-/* Building blocks (bf16 row-major): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
-int b2e_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+/* Building blocks (fp16 row-major, fp32 accumulation): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
+int b2e_gemm_f16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epilogue, void* stream);
 /* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; `reserved` must be NULL (it was a debug score dump). */
 int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
@@ -163,7 +165,7 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
 int b2e_pack_ubinary(const float* emb, int64_t n_rows, int H, uint8_t* out_bits, void* stream);
 int b2e_search_ubinary(const float* queries, int Q, const uint8_t* corpus_bits, int64_t N, int H, int k,
                        int rescore_multiplier, float* out_scores, int64_t* out_indices, void* stream);
-int b2e_layernorm(const void* in_bf16, const float* gamma, const float* beta, void* out, int rows,
+int b2e_layernorm(const void* in_f16, const float* gamma, const float* beta, void* out, int rows,
                   int H, float eps, int out_dtype, void* stream);
 
 #ifdef __cplusplus

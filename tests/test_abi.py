@@ -73,7 +73,7 @@ def test_header_symbols_all_exported():
 
 def test_version_and_error_string():
     lib = _native.load()
-    assert lib.b2e_version() == 1
+    assert lib.b2e_version() == 2
     assert isinstance(lib.b2e_last_error(), bytes)
 
 
@@ -97,7 +97,7 @@ def test_num_weights_bert():
 def test_argument_validation_without_touching_the_gpu():
     lib = _native.load()
     # null pointers / bad shapes are rejected before any CUDA call
-    assert lib.b2e_gemm_bf16(None, None, None, None, None, 128, 128, 64, 0, None) == 1
+    assert lib.b2e_gemm_f16(None, None, None, None, None, 128, 128, 64, 0, None) == 1
     assert b'null' in lib.b2e_last_error()
     assert lib.b2e_adjacent_cosine_dist(None, 0, 1, 768, None, None, None) == 0  # <2 rows: no-op
     assert lib.b2e_encode(None, None, None, None, 1, 1, None, 0, None) == 1

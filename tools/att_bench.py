@@ -30,7 +30,7 @@ def reference(qkv, mask, b, s, heads):
 # ---- correctness of every variant on a ragged small problem
 b, s, heads = 5, 333, 4
 g = torch.Generator(device='cpu').manual_seed(0)
-qkv = (torch.randn(b * s, 3 * heads * 64, generator=g) * 1.5).to(dev).bfloat16()
+qkv = (torch.randn(b * s, 3 * heads * 64, generator=g) * 1.5).to(dev).half()
 lens = torch.tensor([333, 64, 200, 1, 129])
 mask = (torch.arange(s)[None] < lens[:, None]).long().to(dev)
 ref = reference(qkv, mask, b, s, heads)
@@ -43,7 +43,7 @@ for v in variants:
     assert err < 0.05, (v, err)
 
 for b, s, heads in [(512, 512, 12), (128, 512, 12), (64, 1026, 20)]:
-    qkv = torch.randn(b * s, 3 * heads * 64, device=dev).bfloat16()
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev).half()
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     base = None
     for v in variants:

@@ -20,7 +20,7 @@ cfg = MistralConfig(vocab_size=32000, hidden_size=H, num_hidden_layers=L, num_at
                     num_key_value_heads=KV, head_dim=128, intermediate_size=I, max_position_embeddings=32768,
                     rms_norm_eps=1e-5, sliding_window=4096, initializer_range=0.02)
 dev = torch.device('cuda:0')
-sd = random_mistral_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
+sd = random_mistral_state_dict(cfg, seed=0, device=dev, dtype=torch.float16)
 enc = NativeMistralEncoder(cfg, sd, device=dev)
 del sd
 torch.cuda.empty_cache()
@@ -62,20 +62,20 @@ def timeit(fn, reps=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 M = B * S
-x = torch.randn(M, H, device=dev).bfloat16()
-wqkv = (torch.randn(QC, H, device=dev) * 0.02).bfloat16()
-wo = (torch.randn(H, H, device=dev) * 0.02).bfloat16()
-wgu = (torch.randn(2 * I, H, device=dev) * 0.02).bfloat16()
-wd = (torch.randn(H, I, device=dev) * 0.02).bfloat16()
-qkv = nv.gemm_bf16(x, wqkv, None)
-ffn = nv.gemm_bf16(x, wgu, None, None, nv.EPI_SWIGLU)
+x = torch.randn(M, H, device=dev).half()
+wqkv = (torch.randn(QC, H, device=dev) * 0.02).half()
+wo = (torch.randn(H, H, device=dev) * 0.02).half()
+wgu = (torch.randn(2 * I, H, device=dev) * 0.02).half()
+wd = (torch.randn(H, I, device=dev) * 0.02).half()
+qkv = nv.gemm_f16(x, wqkv, None)
+ffn = nv.gemm_f16(x, wgu, None, None, nv.EPI_SWIGLU)
 parts = {
-    'gemm_qkv': (timeit(lambda: nv.gemm_bf16(x, wqkv, None)), 2.0 * M * H * QC),
+    'gemm_qkv': (timeit(lambda: nv.gemm_f16(x, wqkv, None)), 2.0 * M * H * QC),
     'attention_causal': (timeit(lambda: nv.attention_causal_d128(qkv, mask, B, S, HEADS, KV, 4096)),
                          2.0 * B * S * (S + 128) * H),
-    'gemm_o': (timeit(lambda: nv.gemm_bf16(x, wo, None)), 2.0 * M * H * H),
-    'gemm_gate_up_swiglu': (timeit(lambda: nv.gemm_bf16(x, wgu, None, None, nv.EPI_SWIGLU)), 4.0 * M * H * I),
-    'gemm_down': (timeit(lambda: nv.gemm_bf16(ffn, wd, None)), 2.0 * M * H * I),
+    'gemm_o': (timeit(lambda: nv.gemm_f16(x, wo, None)), 2.0 * M * H * H),
+    'gemm_gate_up_swiglu': (timeit(lambda: nv.gemm_f16(x, wgu, None, None, nv.EPI_SWIGLU)), 4.0 * M * H * I),
+    'gemm_down': (timeit(lambda: nv.gemm_f16(ffn, wd, None)), 2.0 * M * H * I),
 }
 res['layer_kernels'] = {k: {'ms': round(t, 3), 'tflops': round(f / t / 1e9, 1)} for k, (t, f) in parts.items()}
 res['layer_kernels_sum_ms'] = round(sum(t for t, _ in parts.values()), 3)

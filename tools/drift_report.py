@@ -127,7 +127,7 @@ def run_mistral(lines):
     lens = torch.tensor([1024, 700])
     mask = (torch.arange(s)[None] < lens[:, None]).long()
     for w in ('normal', 'outliers'):
-        sd = random_mistral_state_dict(cfg, seed=5, device=dev, dtype=torch.bfloat16)
+        sd = random_mistral_state_dict(cfg, seed=5, device=dev, dtype=torch.float16)
         if w == 'outliers':
             add_outliers(sd, 'mistral', seed=3)
         t0 = time.time()

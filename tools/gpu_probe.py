@@ -33,14 +33,14 @@ def probe_gemm():
     torch.manual_seed(0)
     for (m, n, k) in [(300, 768, 768), (128, 256, 64), (1000, 2304, 768), (517, 3072, 768),
                       (517, 768, 3072), (200, 384, 128)]:
-        a = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
-        w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+        a = (torch.randn(m, k, device=dev) * 0.5).half()
+        w = (torch.randn(n, k, device=dev) * 0.05).half()
         bias = torch.randn(n, device=dev) * 0.1
-        resid = torch.randn(m, n, device=dev).bfloat16()
+        resid = torch.randn(m, n, device=dev).half()
         base = a.float() @ w.float().T + bias
         for epi, name in [(nv.EPI_BIAS, 'bias'), (nv.EPI_BIAS_GELU, 'gelu'), (nv.EPI_BIAS_RESID, 'resid')]:
             try:
-                out = nv.gemm_bf16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
+                out = nv.gemm_f16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
                 torch.cuda.synchronize()
             except Exception as exc:  # noqa: BLE001
                 print(f'gemm {m}x{n}x{k} {name}: EXC {exc}', flush=True)
@@ -74,7 +74,7 @@ def probe_attn():
     torch.manual_seed(1)
     for (b, s, heads, ragged) in [(2, 128, 2, False), (2, 512, 12, False), (3, 200, 12, True),
                                   (2, 512, 12, True), (4, 37, 4, True)]:
-        qkv = (torch.randn(b * s, 3 * heads * 64, device=dev)).bfloat16()
+        qkv = (torch.randn(b * s, 3 * heads * 64, device=dev)).half()
         mask = torch.ones(b, s, dtype=torch.int64, device=dev)
         if ragged:
             for i in range(b):
@@ -107,13 +107,13 @@ def ref_average_pool(emb, mask):
 def probe_rows():
     torch.manual_seed(2)
     rows, h = 1000, 768
-    x = torch.randn(rows, h, device=dev).bfloat16()
+    x = torch.randn(rows, h, device=dev).half()
     g = torch.randn(h, device=dev)
     bt = torch.randn(h, device=dev)
     ref = torch.nn.functional.layer_norm(x.float(), (h,), g, bt, 1e-12)
-    stats('layernorm bf16 out', nv.layernorm(x, g, bt, 1e-12, torch.bfloat16), ref)
+    stats('layernorm bf16 out', nv.layernorm(x, g, bt, 1e-12, torch.float16), ref)
     stats('layernorm f32 out', nv.layernorm(x, g, bt, 1e-12, torch.float32), ref)
-    for dt in (torch.float32, torch.bfloat16, torch.float16):
+    for dt in (torch.float32, torch.float16, torch.float16):
         b, s = 9, 77
         emb = torch.randn(b, s, h, device=dev).to(dt)
         lens = torch.tensor([77, 5, 1, 2, 40, 40, 76, 3, 0], device=dev)
@@ -140,18 +140,18 @@ def probe_time():
     for (m, n, k, epi) in [(65536, 2304, 768, nv.EPI_BIAS), (65536, 768, 768, nv.EPI_BIAS_RESID),
                            (65536, 3072, 768, nv.EPI_BIAS_GELU), (65536, 768, 3072, nv.EPI_BIAS_RESID),
                            (262144, 3072, 768, nv.EPI_BIAS_GELU)]:
-        a = torch.randn(m, k, device=dev).bfloat16()
-        w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+        a = torch.randn(m, k, device=dev).half()
+        w = (torch.randn(n, k, device=dev) * 0.05).half()
         bias = torch.randn(n, device=dev)
-        resid = torch.randn(m, n, device=dev).bfloat16()
+        resid = torch.randn(m, n, device=dev).half()
         r = resid if epi == nv.EPI_BIAS_RESID else None
         for _ in range(3):
-            nv.gemm_bf16(a, w, bias, r, epi)
+            nv.gemm_f16(a, w, bias, r, epi)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            nv.gemm_bf16(a, w, bias, r, epi)
+            nv.gemm_f16(a, w, bias, r, epi)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
@@ -164,7 +164,7 @@ def probe_time():
         ms = e0.elapsed_time(e1) / 10
         print(f'   cublas (no epilogue): {ms:.3f} ms  {2 * m * n * k / ms / 1e9:.1f} TFLOP/s', flush=True)
     b, s, heads = 128, 512, 12
-    qkv = torch.randn(b * s, 3 * heads * 64, device=dev).bfloat16()
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev).half()
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     for _ in range(3):
         nv.attention_d64(qkv, mask, b, s, heads)

@@ -6,6 +6,6 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from distllm_b200 import _native as nv
 dev = torch.device('cuda:0')
 m, n, k = 65536, 4096, 14336
-a = torch.randn(m, k, device=dev).bfloat16(); w = (torch.randn(n, k, device=dev) * 0.02).bfloat16()
-for _ in range(4): nv.gemm_bf16(a, w, None)
+a = torch.randn(m, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * 0.02).half()
+for _ in range(4): nv.gemm_f16(a, w, None)
 torch.cuda.synchronize(); print('done')
