@@ -333,22 +333,23 @@ def run_reference_port(args) -> None:
 
 
 # ======================================================================================== native arm
-def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
-    """FFN-up GEMM (M=B*S, N=3072, K=768, bias+GELU epilogue) timed alone with CUDA events."""
+def time_dominant_kernel(device: torch.device, peaks: dict, dtype: torch.dtype = torch.bfloat16) -> dict:
+    """FFN-up GEMM (M=B*S, N=3072, K=768, bias+GELU epilogue) timed alone with CUDA events, in the build of the
+    library whose 16-bit storage type is ``dtype`` (the BERT family runs the bfloat16 build)."""
     from distllm_b200 import _native as nv
 
     m, n, k = BATCH * SEQ, BERT_BASE['intermediate_size'], BERT_BASE['hidden_size']
-    a = torch.randn(m, k, device=device).half()
-    w = (torch.randn(n, k, device=device) * 0.02).half()
+    a = torch.randn(m, k, device=device).to(dtype)
+    w = (torch.randn(n, k, device=device) * 0.02).to(dtype)
     bias = torch.zeros(n, device=device)
     for _ in range(3):
-        nv.gemm_f16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        nv.gemm_h16(a, w, bias, None, nv.EPI_BIAS_GELU)
     reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(device)
     e0.record()
     for _ in range(reps):
-        nv.gemm_f16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        nv.gemm_h16(a, w, bias, None, nv.EPI_BIAS_GELU)
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / reps
@@ -358,7 +359,34 @@ def time_dominant_kernel(device: torch.device, peaks: dict) -> dict:
             'unit': 'TFLOP/s', 'peak_kind': 'burst (kernel timed alone)'}
 
 
-DOMINANT_KERNEL = 'gemm2_h16_pair<5,GELU> (FFN up, M=262144 N=3072 K=768; CTA-pair tcgen05 kernel)'
+def storage_ab(device: torch.device) -> dict:
+    """The same FFN-up GEMM in the two builds of the library, long enough (about 1.5 s each) to reach the
+    power-capped clock: what the 16-bit storage type costs in sustained tensor throughput."""
+    from distllm_b200 import _native as nv
+
+    m, n, k = BATCH * SEQ, BERT_BASE['intermediate_size'], BERT_BASE['hidden_size']
+    out = {}
+    for name, dtype in (('bf16', torch.bfloat16), ('f16', torch.float16), ('bf16_again', torch.bfloat16)):
+        a = torch.randn(m, k, device=device).to(dtype)
+        w = (torch.randn(n, k, device=device) * 0.02).to(dtype)
+        bias = torch.zeros(n, device=device)
+        for _ in range(300):   # ~0.3 s to settle the clock
+            nv.gemm_h16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        reps = 1200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(reps):
+            nv.gemm_h16(a, w, bias, None, nv.EPI_BIAS_GELU)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {'ms_per_launch': ms, 'tflops': 2.0 * m * n * k / (ms * 1e-3) / 1e12}
+    out['what'] = 'FFN-up GEMM (M=262144 N=3072 K=768, bias + GELU), 1200 back-to-back launches per storage type'
+    return out
+
+
+DOMINANT_KERNEL = 'gemm2_h16_pair<5,GELU> (FFN up, M=262144 N=3072 K=768; CTA-pair tcgen05 kernel, bfloat16 build)'
 
 
 def ncu_traffic_bytes() -> float | None:
@@ -409,7 +437,7 @@ def extra_esm2(device, peaks: dict, reduce_max) -> dict:
     seqs = b / (ms * 1e-3)
     tf = seqs * flops_per_chunk(ESM2_650M, s) / 1e12
     return {'workload': 'C5: ESM2-650M shape (L33 H1280 I5120), 1024 residues -> S=1026, mean pooler, '
-                        'batch 64 per GPU, synthetic residues, random-init weights',
+                        'batch 64 per GPU, synthetic residues, random-init weights; bfloat16-storage build',
             'value_per_gpu': seqs, 'unit': 'sequences/s', 'ms_per_step': ms, 'steps': 5,
             'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
                          'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
@@ -442,7 +470,7 @@ def extra_mistral(device, peaks: dict, reduce_max) -> dict:
     seqs = b / (ms * 1e-3)
     tf = seqs * mistral_flops_per_seq(MISTRAL_7B, s) / 1e12
     return {'workload': 'C3: SFR-Embedding-Mistral shape (Mistral-7B: L32 H4096 32q/8kv x128 I14336), '
-                        'last_token pooler, batch_size=16, S=4096, synthetic ids, random-init fp16 weights',
+                        'last_token pooler, batch_size=16, S=4096, synthetic ids, random-init weights; half-storage build (f16)',
             'value_per_gpu': seqs, 'unit': 'sequences/s', 'ms_per_step': ms, 'steps': 3,
             'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
                          'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
@@ -577,6 +605,7 @@ def run_native(args) -> None:
     cfg = BertConfig(**BERT_BASE)
     sd = random_bert_state_dict(cfg, seed=0, device=device)
     enc = NativeBertEncoder(cfg, sd, device=device)
+    enc_storage = enc.storage   # 'bf16': the BERT family runs the bfloat16 build (fp32 accumulate / statistics)
     del sd
     hidden = BERT_BASE['hidden_size']
     steps, warm = args.steps, max(args.warmup, 3)
@@ -654,6 +683,8 @@ def run_native(args) -> None:
     del r_ids, r_mask, r_types, r_out
 
     dom = time_dominant_kernel(device, peaks) if rank == 0 else None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra['storage_ab'] = storage_ab(device)
 
     if world > 1:
         # ---- C4-sized tail: >= 2 M pooled rows per rank through the one all-gather (30.7 GB at 10 M x 768 fp32)
@@ -702,7 +733,7 @@ def run_native(args) -> None:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world,
             'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * elapsed_s / steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': enc_storage, 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'seq_len': SEQ,
                        'parallelism': f'dp{world}: chunks sharded by rank, one all-gather of the pooled matrix',
                        'l2': 'per-step activations (~4 GB) exceed the 126 MB L2; no explicit flush needed'},

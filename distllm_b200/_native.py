@@ -12,18 +12,47 @@ from pathlib import Path
 
 import torch
 
+# Two builds of the same sources (distllm_b200/build.py): they differ only in the 16-bit storage type of
+# weights and activations.  libb2e.so = IEEE half, libb2e_bf16.so = bfloat16 (b2e_storage_dtype()).
 LIB_PATH = Path(__file__).resolve().parent / 'libb2e.so'
+LIB_PATHS = {'f16': LIB_PATH, 'bf16': LIB_PATH.with_name('libb2e_bf16.so')}
+STORAGE_TORCH_DTYPE = {'f16': torch.float16, 'bf16': torch.bfloat16}
+# Which build an encoder family runs on.  Measured (profiles/r02_drift_report_*.md, r02_storage_ab.md): with
+# bfloat16 the 12-layer BERT and 33-layer ESM-2 shapes stay within 5e-5 cosine of the fp32 reference and the
+# GEMMs hold a ~13 % higher clock under the 1 kW power cap; the 32-layer Mistral-7B shape needs half (3.3e-5
+# against 1.6e-3 with bfloat16; tolerance 1e-3).  B2E_STORAGE=f16|bf16 overrides for every family.
+_STORAGE_BY_ARCH = {'bert': 'bf16', 'esm': 'bf16', 'modernbert': 'bf16', 'mistral': 'f16'}
 
-ARCH_BERT, ARCH_ESM2, ARCH_MISTRAL = 0, 1, 2
+
+def storage_for_arch(arch: str) -> str:
+    import os
+
+    forced = os.environ.get('B2E_STORAGE')
+    if forced:
+        if forced not in LIB_PATHS:
+            raise NativeError(f'B2E_STORAGE={forced!r}: expected one of {sorted(LIB_PATHS)}')
+        return forced
+    return _STORAGE_BY_ARCH[arch]
+
+
+def storage_of(dtype: torch.dtype) -> str:
+    """The build whose storage type is ``dtype`` (operands of the building-block entry points)."""
+    for name, dt in STORAGE_TORCH_DTYPE.items():
+        if dt == dtype:
+            return name
+    raise NativeError(f'no libb2e build stores {dtype}: expected float16 or bfloat16 operands')
+
+ARCH_BERT, ARCH_ESM2, ARCH_MISTRAL, ARCH_MODERNBERT = 0, 1, 2, 3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 POOL_MEAN_REF, POOL_MEAN_PER_ROW, POOL_LAST_TOKEN = 0, 1, 2
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_SWIGLU = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_SWIGLU, EPI_GEGLU = 0, 1, 2, 3, 4
 
 _DTYPE_CODES = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
 
 # every symbol include/b2e.h declares (checked by the CPU test-suite)
 EXPORTS = (
     'b2e_version',
+    'b2e_storage_dtype',
     'b2e_last_error',
     'b2e_num_weights',
     'b2e_check_model',
@@ -37,8 +66,9 @@ EXPORTS = (
     'b2e_pool_last_token',
     'b2e_l2_normalize',
     'b2e_adjacent_cosine_dist',
-    'b2e_gemm_f16',
+    'b2e_gemm_h16',
     'b2e_attention_d64',
+    'b2e_attention_d64_window',
     'b2e_attention_causal_d128',
     'b2e_topk_ip',
     'b2e_pack_ubinary',
@@ -78,16 +108,20 @@ class ModelDesc(C.Structure):
         ('rope_theta', C.c_float),
         ('sliding_window', C.c_int32),
         ('reserved', C.c_int32),
+        ('rope_theta_local', C.c_float),
+        ('global_every', C.c_int32),
     ]
 
 
-_lib: C.CDLL | None = None
+_libs: dict[str, C.CDLL] = {}
 
 
 def _declare(lib: C.CDLL) -> None:
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     lib.b2e_version.restype = i32
     lib.b2e_version.argtypes = []
+    lib.b2e_storage_dtype.restype = i32
+    lib.b2e_storage_dtype.argtypes = []
     lib.b2e_last_error.restype = C.c_char_p
     lib.b2e_last_error.argtypes = []
     lib.b2e_num_weights.restype = i32
@@ -114,10 +148,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_l2_normalize.argtypes = [vp, i64, i32, vp]
     lib.b2e_adjacent_cosine_dist.restype = i32
     lib.b2e_adjacent_cosine_dist.argtypes = [vp, i32, i64, i32, vp, vp, vp]
-    lib.b2e_gemm_f16.restype = i32
-    lib.b2e_gemm_f16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b2e_gemm_h16.restype = i32
+    lib.b2e_gemm_h16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b2e_attention_d64.restype = i32
     lib.b2e_attention_d64.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.b2e_attention_d64_window.restype = i32
+    lib.b2e_attention_d64_window.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b2e_attention_causal_d128.restype = i32
     lib.b2e_attention_causal_d128.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b2e_topk_ip.restype = i32
@@ -130,29 +166,33 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
 
 
-def load() -> C.CDLL:
-    """Load libb2e.so (once).  Raises ``NativeError`` when it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+def load(storage: str = 'f16') -> C.CDLL:
+    """Load libb2e.so ('f16') or libb2e_bf16.so ('bf16'), once each.  Raises ``NativeError`` when it has not
+    been built."""
+    if storage in _libs:
+        return _libs[storage]
+    path = LIB_PATHS[storage]
+    if not path.exists():
         raise NativeError(
-            f'{LIB_PATH} not found: build it with `python -m distllm_b200.build` '
+            f'{path} not found: build it with `python -m distllm_b200.build` '
             '(or __graft_entry__.build()). There is no CPU fallback.',
         )
     try:
-        lib = C.CDLL(str(LIB_PATH))
+        lib = C.CDLL(str(path))
     except OSError as exc:  # pragma: no cover - depends on the box
-        raise NativeError(f'cannot load {LIB_PATH}: {exc}') from exc
+        raise NativeError(f'cannot load {path}: {exc}') from exc
     _declare(lib)
-    _lib = lib
+    want = DTYPE_F16 if storage == 'f16' else DTYPE_BF16
+    if lib.b2e_storage_dtype() != want:
+        raise NativeError(f'{path} reports storage dtype {lib.b2e_storage_dtype()}, expected {want}')
+    _libs[storage] = lib
     return lib
 
 
-def check(rc: int) -> None:
-    """Turn a non-zero return code into a NativeError carrying b2e_last_error()."""
+def check(rc: int, lib: C.CDLL | None = None) -> None:
+    """Turn a non-zero return code into a NativeError carrying that library's b2e_last_error()."""
     if rc != 0:
-        msg = load().b2e_last_error()
+        msg = (lib or load()).b2e_last_error()
         raise NativeError(f'libb2e error {rc}: {msg.decode() if msg else "?"}')
 
 
@@ -180,30 +220,31 @@ def _cuda_contig(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- thin op wrappers
-def gemm_f16(
+def gemm_h16(
     a: torch.Tensor,
     w: torch.Tensor,
     bias: torch.Tensor | None,
     resid: torch.Tensor | None = None,
     epilogue: int = EPI_BIAS,
 ) -> torch.Tensor:
-    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; fp16 in/out, fp32 accumulation.
+    """out[M,N] = epi(a[M,K] @ w[N,K].T + bias (+ resid)) on the tcgen05 GEMM; float16 or bfloat16 in/out (the
+    matching build of the library is used), fp32 accumulation.
 
     ``EPI_SWIGLU``: ``w`` holds gate/up rows interleaved in blocks of 64 (weights.interleave_gate_up)
     and the result is ``silu(gate) * up`` of shape [M, N/2]."""
-    lib = load()
+    if a.dtype != w.dtype:
+        raise NativeError(f'gemm_h16: operands differ in dtype ({a.dtype} vs {w.dtype})')
+    lib = load(storage_of(a.dtype))
     _cuda_contig(a, 'a'), _cuda_contig(w, 'w')
     if bias is not None:
         _cuda_contig(bias, 'bias')
     m, k = a.shape
     n = w.shape[0]
-    n_out = n // 2 if epilogue == EPI_SWIGLU else n
-    if a.dtype != torch.float16 or w.dtype != torch.float16:
-        raise NativeError('gemm_f16 expects float16 operands')
-    out = torch.empty((m, n_out), dtype=torch.float16, device=a.device)
+    n_out = n // 2 if epilogue in (EPI_SWIGLU, EPI_GEGLU) else n
+    out = torch.empty((m, n_out), dtype=a.dtype, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib.b2e_gemm_f16(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid),
-                                out.data_ptr(), m, n, k, epilogue, stream_ptr(a.device)))
+        check(lib.b2e_gemm_h16(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid),
+                               out.data_ptr(), m, n, k, epilogue, stream_ptr(a.device)), lib)
     return out
 
 
@@ -215,12 +256,24 @@ def attention_d64(
     heads: int,
 ) -> torch.Tensor:
     """qkv [B*S, 3*heads*64] fp16 -> context [B*S, heads*64] fp16."""
-    lib = load()
+    lib = load(storage_of(qkv.dtype))
     _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
-    ctx = torch.zeros((batch * seq, heads * 64), dtype=torch.float16, device=qkv.device)
+    ctx = torch.zeros((batch * seq, heads * 64), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_d64(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch,
-                                    seq, heads, None, stream_ptr(qkv.device)))
+                                    seq, heads, None, stream_ptr(qkv.device)), lib)
+    return ctx
+
+
+def attention_d64_window(qkv: torch.Tensor, attention_mask: torch.Tensor, batch: int, seq: int, heads: int,
+                         window: int) -> torch.Tensor:
+    """Bidirectional sliding-window attention (|i - j| <= window): qkv [B*S, 3*heads*64] fp16 -> [B*S, heads*64]."""
+    lib = load(storage_of(qkv.dtype))
+    _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
+    ctx = torch.zeros((batch * seq, heads * 64), dtype=qkv.dtype, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.b2e_attention_d64_window(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(), batch, seq,
+                                           heads, window, stream_ptr(qkv.device)), lib)
     return ctx
 
 
@@ -234,12 +287,12 @@ def attention_causal_d128(
     window: int = 0,
 ) -> torch.Tensor:
     """qkv [B*S, (heads + 2*kv_heads)*128] fp16 (q | k | v, rotary applied) -> [B*S, heads*128] fp16."""
-    lib = load()
+    lib = load(storage_of(qkv.dtype))
     _cuda_contig(qkv, 'qkv'), _cuda_contig(attention_mask, 'attention_mask')
-    ctx = torch.zeros((batch * seq, heads * 128), dtype=torch.float16, device=qkv.device)
+    ctx = torch.zeros((batch * seq, heads * 128), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(qkv.device):
         check(lib.b2e_attention_causal_d128(qkv.data_ptr(), attention_mask.data_ptr(), ctx.data_ptr(),
-                                            batch, seq, heads, kv_heads, window, stream_ptr(qkv.device)))
+                                            batch, seq, heads, kv_heads, window, stream_ptr(qkv.device)), lib)
     return ctx
 
 
@@ -298,15 +351,17 @@ def layernorm(
     gamma: torch.Tensor,
     beta: torch.Tensor,
     eps: float,
-    out_dtype: torch.dtype = torch.float16,
+    out_dtype: torch.dtype | None = None,
 ) -> torch.Tensor:
-    lib = load()
+    """LayerNorm of a 16-bit matrix; ``out_dtype``: float32 or (default) the input's own 16-bit type."""
+    lib = load(storage_of(x.dtype))
+    out_dtype = out_dtype or x.dtype
     _cuda_contig(x, 'x')
     rows, h = x.shape
     out = torch.empty((rows, h), dtype=out_dtype, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.b2e_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
-                                h, eps, dtype_code(out_dtype), stream_ptr(x.device)))
+                                h, eps, dtype_code(out_dtype), stream_ptr(x.device)), lib)
     return out
 
 

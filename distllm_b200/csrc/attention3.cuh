@@ -164,12 +164,17 @@ __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], flo
 
 // One work item = (sequence b, head h, pair of query tiles pr); n = key chunks to visit.
 struct At3Item {
-  int b, h, pr, n, np;   // np: leading chunks whose 64 keys are all attended
+  int b, h, pr, n, np;   // n: key chunks to visit; np: leading chunks whose 64 keys are all attended
+  int j0;                // first key chunk (0 unless a sliding window narrows the range)
 };
+// window > 0 (bidirectional sliding window, |q - k| <= window): the pair of query tiles [256 pr, 256 pr + 255]
+// only needs the key chunks that overlap [256 pr - window, 256 pr + 255 + window]; BOTH tiles walk that same
+// range (the band is applied per element), so every role sees the same chunk list.  At least one chunk is
+// always visited: rows of padding tiles must still come out finite.
 __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
                                               const int* __restrict__ kv_chunks,
-                                              const int* __restrict__ plain_chunks, int n_items) {
-  At3Item it{0, 0, 0, 0, 0};
+                                              const int* __restrict__ plain_chunks, int n_items, int window) {
+  At3Item it{0, 0, 0, 0, 0, 0};
   if (item < n_items) {
     it.pr = item % npairs;
     const int bh = item / npairs;
@@ -177,6 +182,17 @@ __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
     it.b = bh / heads;
     it.n = __ldg(kv_chunks + it.b);
     it.np = plain_chunks != nullptr ? __ldg(plain_chunks + it.b) : 0;
+    if (window > 0) {
+      int lo = (256 * it.pr - window) / AT3_KC;
+      if (256 * it.pr - window < 0) lo = 0;
+      int hi = (256 * it.pr + 255 + window) / AT3_KC;
+      if (hi > it.n - 1) hi = it.n - 1;
+      if (lo > it.n - 1) lo = it.n - 1;
+      if (hi < lo) hi = lo;
+      it.j0 = lo;
+      it.n = hi - lo + 1;
+      it.np = 0;   // every chunk needs the band test
+    }
   }
   return it;
 }
@@ -190,6 +206,8 @@ __device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the 
 //   bit 1  S_{j+1} is fetched from TMEM right behind the store of P_j, so that tcgen05.ld's latency runs
 //          under the publish (st wait, fence, arrive) instead of in front of the next chunk's exponentials
 //   bits 2-3  exponentials per four that run on the FMA pipe (plain chunks only): 0, 1 or 2
+//   bit 4  bidirectional sliding window (`window` > 0: ModernBERT's local layers): chunk range per item narrowed
+//          to the band, scores outside |q - k| <= window masked per element
 template <int V>
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16, box 64 x 128
@@ -198,7 +216,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
                       const int* __restrict__ kv_chunks,          // [B]
                       const int* __restrict__ plain_chunks,       // [B] or nullptr
                       const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] h16, box 64 x 128 x 1
-                      int B, int S, int S_pad, int heads, float scale_log2e) {
+                      int B, int S, int S_pad, int heads, float scale_log2e, int window) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
@@ -271,9 +289,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
           const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = b * S;
           const int buf = it & 1;
@@ -298,10 +316,11 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             const uint32_t fb = kv_full + 8u * st;
             mbar_expect_tx(fb, 2 * AT3_KVTILE + AT3_KC * 4);
             const uint32_t dst = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE;
-            tma_load_2d(dst, &tm_kv, fb, H + h * AT3_D, row_base + j * AT3_KC);
-            tma_load_2d(dst + AT3_KVTILE, &tm_kv, fb, 2 * H + h * AT3_D, row_base + j * AT3_KC);
+            const int jk = (cur.j0 + j) * AT3_KC;   // first key of the chunk
+            tma_load_2d(dst, &tm_kv, fb, H + h * AT3_D, row_base + jk);
+            tma_load_2d(dst + AT3_KVTILE, &tm_kv, fb, 2 * H + h * AT3_D, row_base + jk);
             bulk_load_1d(sb + AT3_SMEM_BIAS + st * AT3_KC * 4,
-                         bias + static_cast<size_t>(b) * S_pad + j * AT3_KC, AT3_KC * 4, fb);
+                         bias + static_cast<size_t>(b) * S_pad + jk, AT3_KC * 4, fb);
             AT3_STAMP(3, it * 100 + j);
           }
           cur = nxt;
@@ -323,9 +342,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
           const int n = cur.n;
           const int buf = it & 1;
           const bool active = 2 * cur.pr + slot < nq;
@@ -408,7 +427,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
-    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items);
+    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
     // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
     // is ordered (A before B), which merely de-phases the two warpgroups
@@ -418,7 +437,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
-      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items);
+      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
       const int pr = cur.pr, h = cur.h, b = cur.b, n = cur.n;
       const int t = 2 * pr + slot;
       if (t >= nq && pingpong) {
@@ -479,6 +498,20 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
           const bool turn = (pp_mode & 1) || (pp_mode == 2 && j == 0);
           if (turn) asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           uint32_t pk[32];
+          if ((V & 16) != 0) {
+            // sliding window: key (j0 + j) * 64 + i is visible to query row q iff |q - key| <= window; scores
+            // outside the band become a large negative FINITE number (so that a chunk with no visible key
+            // degenerates to a uniform softmax that the next visible chunk's rescale wipes out)
+            const int q_abs = t * 128 + r;
+            const int ilo = q_abs - window - (cur.j0 + j) * AT3_KC;
+            const unsigned span = static_cast<unsigned>(2 * window);
+            constexpr uint32_t kOut = 0xfcf0bdc2u;   // -1e37f
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (static_cast<unsigned>(i - ilo) > span) s0[i] = kOut;
+              if (static_cast<unsigned>(i + 32 - ilo) > span) s1[i] = kOut;
+            }
+          }
           bool done = false;
           if (plain) {
             if (j == 0) {

@@ -27,6 +27,15 @@
 
 using namespace b2e;
 
+// the 16-bit storage type of this build (common.cuh): tensor-map element type and its ABI dtype code
+#ifdef B2E_STORAGE_BF16
+#define B2E_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+constexpr int kStorageDtype = B2E_DTYPE_BF16;
+#else
+#define B2E_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+constexpr int kStorageDtype = B2E_DTYPE_F16;
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -76,7 +85,7 @@ int make_tmap_h16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(tm, B2E_TMAP_DTYPE, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -95,7 +104,7 @@ int make_tmap_h16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t
   cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(tm, B2E_TMAP_DTYPE, 3, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -216,6 +225,11 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
         return launch_gemm_cfg<256, STAGES, EPI_SWIGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
       else
         return fail(B2E_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0");
+    case B2E_EPI_GEGLU:
+      if constexpr (BN == 256)
+        return launch_gemm_cfg<256, STAGES, EPI_GEGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+      else
+        return fail(B2E_ERR_INVALID, "GeGLU epilogue needs N %% 256 == 0");
   }
   return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -265,7 +279,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
   CUtensorMap tout;
   int rc;
-  const int n_out = (epi == B2E_EPI_SWIGLU) ? N / 2 : N;   // SwiGLU writes silu(gate)*up: [M, N/2]
+  const bool glu = epi == B2E_EPI_SWIGLU || epi == B2E_EPI_GEGLU;
+  const int n_out = glu ? N / 2 : N;   // the gated epilogues write act(first) * second: [M, N/2]
   if ((rc = make_tmap_h16(&tout, out, M, n_out, GEMM_OUT_BOX_ROWS))) return rc;
   if (N % 256 == 0 && gemm_use_pair()) {
     constexpr int PS = 5;   // 5 x 32 KiB stages + two staging tiles per epilogue warp
@@ -274,6 +289,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
       case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<PS, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
       case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<PS, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
       case B2E_EPI_SWIGLU: return launch_gemm2_cfg<PS, EPI_SWIGLU>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_GEGLU: return launch_gemm2_cfg<PS, EPI_GEGLU>(ta, tb, tout, bias, r, M, N, K, sms, st);
     }
     return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
   }
@@ -350,19 +366,20 @@ inline int att3_variant() {
 template <int V>
 int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
                        const CUtensorMap& tctx, int B, int S, int heads, int grid, float scale_log2e,
-                       cudaStream_t st) {
+                       cudaStream_t st, int window = 0) {
   auto kern = attention3_d64_kernel<V>;
   const int arc = ensure_smem_attr(kern, AT3_SMEM_BYTES);
   if (arc) return arc;
   kern<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
-                                                  attn_s_pad(S), heads, scale_log2e);
+                                                  attn_s_pad(S), heads, scale_log2e, window);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
 
 // tq: [T,3H] box 64x128, tkv: [T,3H] box 64x64.  `sc` must have been prepared for this batch's mask.
+// window > 0: bidirectional sliding window |q - k| <= window (ModernBERT's local layers), else full attention.
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc, void* ctx,
-                     int B, int S, int heads, int sms, cudaStream_t st) {
+                     int B, int S, int heads, int sms, cudaStream_t st, int window = 0) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
@@ -370,6 +387,7 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   CUtensorMap tctx;  // [B, S, H]: the output store clips rows >= S per sequence
   int rc;
   if ((rc = make_tmap_h16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
+  if (window > 0) return launch_attention_v<17>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st, window);
   switch (att3_variant()) {
     case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
     case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
@@ -580,6 +598,11 @@ struct B2EEncoder {
   //   0 embed_tokens, 1 final norm; per layer (2 + 6 l): input norm, Wqkv, Wo, post-attention norm,
   //   Wgu (gate/up interleaved), Wd
   const void* Mi(int l, int k) const { return w[2 + 6 * l + k]; }
+  // ModernBERT: weight slots (weights.py): 0 tok_embeddings, 1/2 embeddings.norm g/b, 3/4 final_norm g/b; per
+  // layer (5 + 8 l): attn_norm g/b, Wqkv, Wo, mlp_norm g/b, Wi (input/gate interleaved), mlp.Wo.  rope_cos/sin =
+  // full-attention layers' table, rope_cos2/sin2 = sliding-attention layers'
+  const void* Mb(int l, int k) const { return w[5 + 8 * l + k]; }
+  float *rope_cos2 = nullptr, *rope_sin2 = nullptr;
   // b2e_embed_host replays one CUDA graph per (batch shape, pooling, staging slot) instead of ~90
   // launches per batch; every graph is dropped when a buffer it points into is reallocated
   struct StepGraph {
@@ -815,12 +838,66 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
   return B2E_OK;
 }
 
+// ModernBERT (pre-LayerNorm blocks, rotary with one base per layer type, alternating full / sliding-window
+// bidirectional attention, GeGLU MLP, no Linear biases): transformers/models/modernbert/modeling_modernbert.py
+// :52-71 (embeddings), :232-310 (attention), :74-91 (MLP), :313-343 (block; layer 0 has no attn_norm),
+// :424-490 (model).  Leaves xres (before the last MLP output is added) and e->tmp (that output): the caller
+// applies final_norm to xres + tmp.
+int run_modernbert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
+                         cudaStream_t st) {
+  const B2EModelDesc& d = e->desc;
+  const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
+  int rc;
+  DISPATCH_NV(H, (modernbert_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                     ids, (const float*)e->w[0], (const float*)e->w[1], (const float*)e->w[2], e->xres,
+                     e->hidden, M, d.eps)));
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
+  CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
+  if ((rc = make_tmap_h16(&tm_hidden, e->hidden, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ctx, e->ctx, M, H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_ffn, e->ffn, M, I, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_qkv, e->qkv, M, 3 * H, 128))) return rc;
+  if ((rc = make_tmap_h16(&tm_kv64, e->qkv, M, 3 * H, AT3_KC))) return rc;
+  const long long rope_work = (long long)M * d.heads * 2;
+  for (int l = 0; l < L; ++l) {
+    const bool global = (l % d.global_every) == 0;
+    if (l > 0) {
+      DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                         e->xres, e->tmp, (const float*)e->Mb(l, 0), (const float*)e->Mb(l, 1), e->hidden, M,
+                         d.eps)));
+    }
+    if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, 3 * H, H, B2E_EPI_BIAS,
+                          e->sms, st)))
+      return rc;
+    rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(
+        e->qkv, global ? e->rope_cos : e->rope_cos2, global ? e->rope_sin : e->rope_sin2, M, S, d.heads);
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st,
+                               global ? 0 : d.sliding_window)))
+      return rc;
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, H, B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+    DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
+                       e->xres, e->tmp, (const float*)e->Mb(l, 4), (const float*)e->Mb(l, 5), e->hidden, M,
+                       d.eps)));
+    // Wi with its input / gate halves interleaved: gelu(input) * gate in the epilogue -> [M, I]
+    if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, nullptr, nullptr, M, 2 * I, H, B2E_EPI_GEGLU,
+                          e->sms, st)))
+      return rc;
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, nullptr, nullptr, M, H, I, B2E_EPI_BIAS, e->sms, st)))
+      return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2E_OK;
+}
+
 }  // namespace
 
 // ================================================================== C ABI
 extern "C" {
 
 int b2e_version(void) { return B2E_ABI_VERSION; }
+int b2e_storage_dtype(void) { return kStorageDtype; }
 
 // Profiling hooks (include/b2e_debug.h, not part of the reference-facing ABI): device buffer of
 // 4 x 256 int64 that CTAs 0 and 1 of the CTA-pair GEMM fill with clock64() stamps ([cta*2 + role][n],
@@ -872,6 +949,7 @@ int b2e_num_weights(const B2EModelDesc* desc) {
   if (desc->arch == B2E_ARCH_BERT) return 5 + 12 * desc->num_layers;
   if (desc->arch == B2E_ARCH_ESM2) return 3 + 12 * desc->num_layers;
   if (desc->arch == B2E_ARCH_MISTRAL) return 2 + 6 * desc->num_layers;
+  if (desc->arch == B2E_ARCH_MODERNBERT) return 5 + 8 * desc->num_layers;
   return -1;
 }
 
@@ -897,8 +975,15 @@ int b2e_check_model(const B2EModelDesc* desc) {
     if ((rc = check_gemm_shape(128, 2 * I, H))) return rc;
     return check_gemm_shape(128, H, I);
   }
-  if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2)
+  if (desc->arch != B2E_ARCH_BERT && desc->arch != B2E_ARCH_ESM2 && desc->arch != B2E_ARCH_MODERNBERT)
     return fail(B2E_ERR_UNSUPPORTED, "arch %d: unknown architecture", desc->arch);
+  if (desc->arch == B2E_ARCH_MODERNBERT) {
+    if (desc->global_every <= 0) return fail(B2E_ERR_INVALID, "ModernBERT: global_every must be positive");
+    if (desc->sliding_window <= 0) return fail(B2E_ERR_INVALID, "ModernBERT: sliding_window must be positive");
+    if ((2 * desc->intermediate) % 256 != 0)
+      return fail(B2E_ERR_UNSUPPORTED, "ModernBERT: 2 * intermediate_size = %d must be a multiple of 256 (the gated "
+                  "epilogue pairs 128 input with 128 gate columns)", 2 * desc->intermediate);
+  }
   if (desc->head_dim != 64 || desc->heads * desc->head_dim != desc->hidden)
     return fail(B2E_ERR_UNSUPPORTED,
                 "need head_dim 64 and heads*64 == hidden (got %d heads x %d, H=%d); of the ESM-2 family that "
@@ -985,17 +1070,37 @@ int b2e_encoder_create(const B2EModelDesc* desc, const void* const* weights, int
   const int L = desc->num_layers, H = desc->hidden, I = desc->intermediate;
   e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
   const bool esm = desc->arch == B2E_ARCH_ESM2;
+  const bool mbert = desc->arch == B2E_ARCH_MODERNBERT;
+  const int n1 = mbert ? 2 * I : I;   // ModernBERT's Wi holds input and gate rows
   for (int l = 0; l < L; ++l) {
-    const void* wqkv = esm ? e->E(l, 2) : e->L(l, 0);
-    const void* wo = esm ? e->E(l, 4) : e->L(l, 2);
-    const void* w1 = esm ? e->E(l, 8) : e->L(l, 6);
-    const void* w2 = esm ? e->E(l, 10) : e->L(l, 8);
+    const void* wqkv = mbert ? e->Mb(l, 2) : esm ? e->E(l, 2) : e->L(l, 0);
+    const void* wo = mbert ? e->Mb(l, 3) : esm ? e->E(l, 4) : e->L(l, 2);
+    const void* w1 = mbert ? e->Mb(l, 6) : esm ? e->E(l, 8) : e->L(l, 6);
+    const void* w2 = mbert ? e->Mb(l, 7) : esm ? e->E(l, 10) : e->L(l, 8);
     if ((rc = make_tmap_h16(&e->tm_wqkv[l], wqkv, 3 * H, H, gemm_bn_for(3 * H))) ||
         (rc = make_tmap_h16(&e->tm_wo[l], wo, H, H, gemm_bn_for(H))) ||
-        (rc = make_tmap_h16(&e->tm_w1[l], w1, I, H, gemm_bn_for(I))) ||
+        (rc = make_tmap_h16(&e->tm_w1[l], w1, n1, H, gemm_bn_for(n1))) ||
         (rc = make_tmap_h16(&e->tm_w2[l], w2, H, I, gemm_bn_for(H)))) {
       delete e;
       return rc;
+    }
+  }
+  if (mbert) {
+    const size_t n = (size_t)desc->max_pos * 32;
+    if (cudaMalloc(&e->rope_cos, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->rope_sin, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->rope_cos2, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->rope_sin2, n * sizeof(float)) != cudaSuccess) {
+      b2e_encoder_destroy(e);
+      return fail(B2E_ERR_CUDA, "cudaMalloc of the rotary tables failed");
+    }
+    rope_table_theta_kernel<<<(unsigned)((n + 255) / 256), 256>>>(e->rope_cos, e->rope_sin, desc->max_pos, 32,
+                                                                  desc->rope_theta);
+    rope_table_theta_kernel<<<(unsigned)((n + 255) / 256), 256>>>(e->rope_cos2, e->rope_sin2, desc->max_pos, 32,
+                                                                  desc->rope_theta_local);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      b2e_encoder_destroy(e);
+      return fail(B2E_ERR_CUDA, "rotary table kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   if (esm) {
@@ -1022,6 +1127,7 @@ void b2e_encoder_destroy(B2EEncoder* e) {
   cudaFree(e->hidden); cudaFree(e->qkv); cudaFree(e->ctx); cudaFree(e->tmp); cudaFree(e->ffn);
   cudaFree(e->stage_in); cudaFree(e->stage_out);
   cudaFree(e->xres); cudaFree(e->tok_scale); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
+  cudaFree(e->rope_cos2); cudaFree(e->rope_sin2);
   e->drop_graphs();
   e->pool.release();
   e->attn.release();
@@ -1044,8 +1150,8 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
   int rc;
   if ((rc = validate_batch(e, B, S))) return rc;
   if (!ids || !mask || !out_hidden) return fail(B2E_ERR_INVALID, "null tensor pointer");
-  if (out_dtype != B2E_DTYPE_F32 && out_dtype != B2E_DTYPE_F16)
-    return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or F16");
+  if (out_dtype != B2E_DTYPE_F32 && out_dtype != kStorageDtype)
+    return fail(B2E_ERR_INVALID, "encode: out_dtype must be F32 or this build's storage type (%d)", kStorageDtype);
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_workspace(e, B, S))) return rc;
   const B2EModelDesc& d = e->desc;
@@ -1063,17 +1169,18 @@ int b2e_encode(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
   }
-  if (d.arch == B2E_ARCH_ESM2) {
-    if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
-    // emb_layer_norm_after over (residual stream + last FFN output)
+  if (d.arch == B2E_ARCH_ESM2 || d.arch == B2E_ARCH_MODERNBERT) {
+    const bool mb = d.arch == B2E_ARCH_MODERNBERT;
+    if ((rc = mb ? run_modernbert_trunk(e, ids, mask, B, S, st) : run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+    // emb_layer_norm_after / final_norm over (residual stream + last FFN output)
+    const float* fg = (const float*)e->w[mb ? 3 : 1];
+    const float* fb = (const float*)e->w[mb ? 4 : 2];
     if (out_dtype == B2E_DTYPE_F32) {
       DISPATCH_NV(H, (add_layernorm_kernel<NV, float><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
-                         (float*)out_hidden, M, d.eps)));
+                         e->xres, e->tmp, fg, fb, (float*)out_hidden, M, d.eps)));
     } else {
       DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2],
-                         (h16*)out_hidden, M, d.eps)));
+                         e->xres, e->tmp, fg, fb, (h16*)out_hidden, M, d.eps)));
     }
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
@@ -1126,15 +1233,17 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
-  if (d.arch == B2E_ARCH_ESM2) {
-    if ((rc = run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+  if (d.arch == B2E_ARCH_ESM2 || d.arch == B2E_ARCH_MODERNBERT) {
+    const bool mb = d.arch == B2E_ARCH_MODERNBERT;
+    if ((rc = mb ? run_modernbert_trunk(e, ids, mask, B, S, st) : run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+    const float* fg = (const float*)e->w[mb ? 3 : 1];
+    const float* fb = (const float*)e->w[mb ? 4 : 2];
     if (pool_kind == B2E_POOL_LAST_TOKEN) {
       // only the B selected rows go through emb_layer_norm_after (fp32 end to end)
       seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
       last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
       DISPATCH_NV(H, (addnorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], ps.idx, out, B, S,
-                         d.eps)));
+                         e->xres, e->tmp, fg, fb, ps.idx, out, B, S, d.eps)));
       if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
       CUDA_TRY(cudaGetLastError());
       return B2E_OK;
@@ -1145,8 +1254,7 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     const int rows_per = (S + nsplit - 1) / nsplit;
     dim3 grid(B, nsplit);
     DISPATCH_NV(H, (addnorm_pool_kernel<NV, false><<<grid, ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, (const float*)e->w[1], (const float*)e->w[2], ps.w, ps.part, S,
-                       rows_per, d.eps)));
+                       e->xres, e->tmp, fg, fb, ps.w, ps.part, S, rows_per, d.eps)));
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
@@ -1380,14 +1488,14 @@ int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
   return B2E_OK;
 }
 
-int b2e_gemm_f16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+int b2e_gemm_h16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epi, void* stream) {
   if (!A || !W || !out) return fail(B2E_ERR_INVALID, "null tensor pointer");  // bias may be null
   if (epi == B2E_EPI_BIAS_RESID && !resid) return fail(B2E_ERR_INVALID, "resid epilogue needs resid");
   int rc;
   if ((rc = check_gemm_shape(M, N, K))) return rc;
-  if (epi == B2E_EPI_SWIGLU && N % 256 != 0)
-    return fail(B2E_ERR_INVALID, "gemm: SwiGLU epilogue needs N %% 256 == 0 (got %d)", N);
+  if ((epi == B2E_EPI_SWIGLU || epi == B2E_EPI_GEGLU) && N % 256 != 0)
+    return fail(B2E_ERR_INVALID, "gemm: the gated epilogues need N %% 256 == 0 (got %d)", N);
   DeviceInfo info;
   if ((rc = current_device_info(&info))) return rc;
   CUtensorMap ta, tb;
@@ -1410,6 +1518,21 @@ int b2e_attention_d64(const void* qkv, const int64_t* mask, void* ctx, int B, in
   if ((rc = make_tmap_h16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, AT3_KC))) return rc;
   if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
   return launch_attention(tq, tkv, g_attn_scratch, ctx, B, S, heads, info.sms, st);
+}
+
+int b2e_attention_d64_window(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int heads,
+                             int window, void* stream) {
+  if (!qkv || !mask || !ctx) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || S <= 0 || heads <= 0 || window < 0) return fail(B2E_ERR_INVALID, "bad windowed attention problem");
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq, tkv;
+  if ((rc = make_tmap_h16(&tq, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, 128))) return rc;
+  if ((rc = make_tmap_h16(&tkv, qkv, (uint64_t)B * S, (uint64_t)3 * heads * AT3_D, AT3_KC))) return rc;
+  if ((rc = attention_prepare(g_attn_scratch, mask, B, S, st))) return rc;
+  return launch_attention(tq, tkv, g_attn_scratch, ctx, B, S, heads, info.sms, st, window);
 }
 
 int b2e_attention_causal_d128(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int heads,
@@ -1561,7 +1684,9 @@ int launch_bin_pass(const uint32_t* corpus, const uint32_t* qbits, int64_t N, in
   auto hist_k = hamming_hist_kernel<Q>;
   auto sel_k = hamming_select_kernel<Q>;
   int rc;
-  if (smem_hist > 48 * 1024 && (rc = ensure_smem_attr(hist_k, (int)smem_hist))) return rc;
+  // the attribute is set ONCE per kernel and device: to the largest size any call may ask for (Q <= 8 queries of
+  // H <= 8192 stay under 160 KiB by the choice of qp in the caller), not to this call's size
+  if ((rc = ensure_smem_attr(hist_k, 164 * 1024))) return rc;
   hist_k<<<grid, BIN_THREADS, smem_hist, st>>>(corpus, qbits + (size_t)q0 * W, N, W, H,
                                                sc.hist + (size_t)q0 * (H + 1));
   hamming_threshold_kernel<<<1, 32, 0, st>>>(sc.hist + (size_t)q0 * (H + 1), H, K, Q, sc.thr + 2 * q0);
@@ -1631,7 +1756,7 @@ int b2e_search_ubinary(const float* queries, int Q, const uint8_t* corpus_bits, 
   while (n_pow2 < 2 * K || n_pow2 < 64) n_pow2 <<= 1;
   if (n_pow2 < BIN_MAX_CAND) n_pow2 = BIN_MAX_CAND;   // ties beyond 2K still fit up to the buffer size
   const size_t smem = (size_t)n_pow2 * 8 + (size_t)H * 4;
-  if ((rc = ensure_smem_attr(binary_rescore_kernel, (int)smem))) return rc;
+  if ((rc = ensure_smem_attr(binary_rescore_kernel, BIN_MAX_CAND * 8 + 32 * BIN_MAX_WORDS * 4))) return rc;
   binary_rescore_kernel<<<Q, BIN_THREADS, smem, st>>>(sc.cand, sc.n_cand, BIN_MAX_CAND, n_pow2, corpus, W, H,
                                                       queries, K, k, out_scores,
                                                       reinterpret_cast<long long*>(out_indices));
@@ -1651,11 +1776,11 @@ int b2e_layernorm(const void* in, const float* gamma, const float* beta, void* o
   if (out_dtype == B2E_DTYPE_F32) {
     DISPATCH_NV(H, (layernorm_kernel<NV, float><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
                        (const h16*)in, nullptr, gamma, beta, (float*)out, rows, eps)));
-  } else if (out_dtype == B2E_DTYPE_F16) {
+  } else if (out_dtype == kStorageDtype) {
     DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(rows), ROW_THREADS, 0, st>>>(
                        (const h16*)in, nullptr, gamma, beta, (h16*)out, rows, eps)));
   } else {
-    return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or F16");
+    return fail(B2E_ERR_INVALID, "layernorm: out_dtype must be F32 or the storage type");
   }
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;

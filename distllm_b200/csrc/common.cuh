@@ -14,13 +14,20 @@
 namespace b2e {
 
 using bf16 = __nv_bfloat16;   // only at the API surface (hidden states / corpora a caller hands in as bf16)
-// The 16-bit storage type of every weight matrix and every activation between kernels.  IEEE half, not
-// bfloat16: both feed the tensor cores at the same rate, but half keeps 11 significand bits against 8, and
-// with bfloat16 the per-operator rounding alone (1.7e-3 relative, profiles/r02_stage_errors_bf16.log) drifts
-// a 32-layer Mistral-shaped model 1.6e-3 in cosine away from the fp32 reference (tolerance 1e-3;
-// profiles/r02_drift_report_bf16.md).  The reference's own reduced-precision mode is half as well
-// (half_precision -> model.half(), distllm/embed/encoders/auto.py:77-79).  Conversions saturate at +-65504.
+// The 16-bit storage type of every weight matrix and every activation between kernels: ONE type per build of
+// the library.  libb2e.so stores IEEE half, libb2e_bf16.so (same sources, -DB2E_STORAGE_BF16) bfloat16.  Both
+// feed the tensor cores at the same issue rate; they differ in two measured ways (profiles/r02_*):
+//   * half keeps 11 significand bits against 8: per-operator rounding 2.1e-4 vs 1.7e-3 relative.  A 32-layer
+//     Mistral-shaped model drifts 1.6e-3 in cosine from the fp32 reference with bfloat16 (tolerance 1e-3) and
+//     3.3e-5 with half; BERT / ESM-2 depths stay below 5e-5 either way;
+//   * half multiplies cost more power: under the 1 kW cap the SM clock settles ~13 % lower.
+// The Python side therefore loads the bfloat16 build for the BERT and ESM-2 families and the half build for the
+// Mistral family (distllm_b200/_native.py: storage_for_arch).  Half conversions saturate at +-65504.
+#ifdef B2E_STORAGE_BF16
+using h16 = __nv_bfloat16;
+#else
 using h16 = __half;
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -341,22 +348,37 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 //   [17,23) N >> 3            [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_h16(int M, int N, int a_mn_major,
                                                       int b_mn_major) {
-  // A / B format fields [7,10) / [10,13): 0 = f16 (h16 operands), 1 = bf16
-  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+  // A / B format fields [7,10) / [10,13): 0 = f16, 1 = bf16 (the build's storage type)
+#ifdef B2E_STORAGE_BF16
+  constexpr uint32_t fmt = 1u;
+#else
+  constexpr uint32_t fmt = 0u;
+#endif
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ small math / packing
-// two floats -> packed half2 (lo in the low 16 bits), round to nearest, saturating to +-65504 instead of inf
+// two floats -> packed pair of the storage type (lo in the low 16 bits), round to nearest; half saturates to
+// +-65504 instead of inf (bfloat16 has fp32's range)
 __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
   uint32_t r;
+#ifdef B2E_STORAGE_BF16
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
   return r;
 }
 __device__ __forceinline__ float2 unpack_h16x2(uint32_t u) {
+#ifdef B2E_STORAGE_BF16
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+#else
   __half2 v = *reinterpret_cast<__half2*>(&u);
   return __half22float2(v);
+#endif
 }
 // bf16 pairs of a caller-provided bf16 corpus (top-k scan)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
@@ -364,9 +386,20 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ h16 to_h16(float x) {
+#ifdef B2E_STORAGE_BF16
+  return __float2bfloat16_rn(x);
+#else
   h16 r;
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(*reinterpret_cast<unsigned short*>(&r)) : "f"(x));
   return r;
+#endif
+}
+__device__ __forceinline__ float from_h16(h16 x) {
+#ifdef B2E_STORAGE_BF16
+  return __bfloat162float(x);
+#else
+  return __half2float(x);
+#endif
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

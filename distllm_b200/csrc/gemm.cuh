@@ -24,7 +24,10 @@ namespace b2e {
 // EPI_SWIGLU: W holds gate and up rows interleaved in blocks of 64 (weights.py: interleave_gate_up),
 // so columns [128t, 128t+64) of the product are gate and [128t+64, 128t+128) up of outputs
 // [64t, 64t+64); the epilogue writes silu(gate) * up into out [M, N/2].
-enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_SWIGLU = 3 };
+// EPI_GEGLU: the same layout with erf-GELU on the first half of each pair ("input" rows of ModernBERT's Wi, the
+// "gate" rows multiply): out = gelu(input) * gate (transformers/models/modernbert/modeling_modernbert.py:88-91).
+enum GemmEpi : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_SWIGLU = 3, EPI_GEGLU = 4 };
+__host__ __device__ constexpr bool epi_is_glu(int epi) { return epi == EPI_SWIGLU || epi == EPI_GEGLU; }
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 h16 = one 128-byte swizzle row
@@ -180,6 +183,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_gbias(const uint32_t (&acc)[
 // SwiGLU epilogue of one 32-row x 64-output chunk: g, u = the gate / up accumulators (two 32-column
 // TMEM reads each); silu(g) * u -> h16 -> the warp's swizzled staging tile.
 // silu(g) = g / (1 + 2^(-g log2 e)): one ex2 + one rcp per element (hidden under the K loop's MMAs).
+template <bool GELU>
 __device__ __forceinline__ void gemm_swiglu_chunk(const uint32_t (&g)[2][32],
                                                   const uint32_t (&u)[2][32], uint8_t* staging,
                                                   int lane) {
@@ -191,9 +195,13 @@ __device__ __forceinline__ void gemm_swiglu_chunk(const uint32_t (&g)[2][32],
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float x = __uint_as_float(gg[e]);
-      float r;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(-1.4426950408889634f * x)));
-      v[e] = x * r * __uint_as_float(uu[e]);
+      if (GELU) {
+        v[e] = gelu_erf_fast(x) * __uint_as_float(uu[e]);
+      } else {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(-1.4426950408889634f * x)));
+        v[e] = x * r * __uint_as_float(uu[e]);
+      }
     }
     uint4 o;
     o.x = pack_h16x2(v[0], v[1]);
@@ -325,7 +333,7 @@ gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] bo
           (EPI == EPI_BIAS_RESID) ? resid + static_cast<size_t>(row) * N + gcol0 : nullptr;
 
       // the tile's bias slice goes to smem before the accumulator wait (double-buffered by `as`)
-      if (EPI != EPI_SWIGLU) {
+      if (!epi_is_glu(EPI)) {
         for (int i = etid; i < BN; i += GEMM_EPI_WARPS * 32)
           sbias[as * BN + i] = (bias != nullptr) ? __ldg(bias + n_blk * BN + i) : 0.0f;
         asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
@@ -335,8 +343,8 @@ gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] bo
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(as * BN + col0);
-      if constexpr (EPI == EPI_SWIGLU) {
-        static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU epilogue: 128 columns per warp");
+      if constexpr (epi_is_glu(EPI)) {
+        static_assert(!epi_is_glu(EPI) || BN == 256, "SwiGLU epilogue: 128 columns per warp");
         uint32_t g[2][32], u[2][32];
         tmem_ld32(t_base, g[0]);
         tmem_ld32(t_base + 32u, g[1]);
@@ -345,7 +353,7 @@ gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] bo
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         tmem_ld_wait();
-        gemm_swiglu_chunk(g, u, staging, lane);
+        gemm_swiglu_chunk<EPI == EPI_GEGLU>(g, u, staging, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -354,7 +362,7 @@ gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] bo
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < (EPI == EPI_SWIGLU ? 0 : NCHUNK); ++c) {
+      for (int c = 0; c < (epi_is_glu(EPI) ? 0 : NCHUNK); ++c) {
         uint32_t acc[2][32];
         tmem_ld32(t_base + static_cast<uint32_t>(c * 64), acc[0]);
         tmem_ld32(t_base + static_cast<uint32_t>(c * 64 + 32), acc[1]);

@@ -201,7 +201,7 @@ gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box
                               static_cast<uint32_t>(as * G2_BN + col0);
       // Two staging tiles per warp, used alternately: before a tile is overwritten only the TMA store
       // issued TWO stores ago must have finished reading it (bulk groups retire in order).
-      if constexpr (EPI == EPI_SWIGLU) {
+      if constexpr (epi_is_glu(EPI)) {
         uint32_t g[2][32], u[2][32];
         tmem_ld32(t_base, g[0]);
         tmem_ld32(t_base + 32u, g[1]);
@@ -212,7 +212,7 @@ gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box
         tmem_ld_wait();
         if (!(flags & 1)) {
           const int sidx = local & 1;
-          gemm_swiglu_chunk(g, u, staging + sidx * GEMM_STAGING_BYTES, lane);
+          gemm_swiglu_chunk<EPI == EPI_GEGLU>(g, u, staging + sidx * GEMM_STAGING_BYTES, lane);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && row0 < M) {

@@ -203,7 +203,7 @@ __global__ void rope_d128_kernel(h16* __restrict__ qkv, const float* __restrict_
   for (int k = 0; k < 2; ++k) {
     const int i = lane + 32 * k;
     const float c = cos_t[pos * 64 + i], s = sin_t[pos * 64 + i];
-    const float x1 = __half2float(p[i]), x2 = __half2float(p[i + 64]);
+    const float x1 = from_h16(p[i]), x2 = from_h16(p[i + 64]);
     p[i] = to_h16(x1 * c - x2 * s);
     p[i + 64] = to_h16(x2 * c + x1 * s);
   }

@@ -47,12 +47,14 @@ __device__ __forceinline__ void store8(h16* p, const float (&v)[8]) {
   u.w = pack_h16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
-__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {   // b2e_encode(out_dtype = BF16)
+#ifndef B2E_STORAGE_BF16   // (in the bfloat16 build the overload above already is the bf16 store)
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {   // caller-provided bf16 outputs
   __nv_bfloat162 h[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h);
 }
+#endif
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -490,6 +492,30 @@ esm_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ ma
   }
 }
 
+// ModernBERT embeddings (transformers/models/modernbert/modeling_modernbert.py:52-71): x = LayerNorm(tok[ids]);
+// x is the fp32 residual stream AND (layer 0 has no attn_norm: :318-320) the first attention input.
+template <int NV>
+__global__ void __launch_bounds__(ROW_THREADS)
+modernbert_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* __restrict__ xres, h16* __restrict__ hidden, int rows, float eps) {
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t id = ids[row];
+  float x[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) load8(table + static_cast<size_t>(id) * H + v * 256 + lane * 8, x[v]);
+  warp_layernorm<NV>(x, gamma, beta, lane, eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const size_t off = static_cast<size_t>(row) * H + v * 256 + lane * 8;
+    store8(xres + off, x[v]);
+    store8(hidden + off, x[v]);
+  }
+}
+
 // Residual stream update fused with the next LayerNorm (pre-LN blocks):
 //   xres += add (h16 GEMM output; nullptr on the very first call);  out = LayerNorm(xres)
 // The fp32 residual stream keeps 33 layers of accumulation out of h16.
@@ -548,7 +574,7 @@ __global__ void rope_qk_kernel(h16* __restrict__ qkv, const float* __restrict__ 
   h16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
   const int pos = t % S;
   const float c = cos_t[pos * 32 + lane], s = sin_t[pos * 32 + lane];
-  const float x1 = __half2float(p[lane]), x2 = __half2float(p[lane + 32]);
+  const float x1 = from_h16(p[lane]), x2 = from_h16(p[lane + 32]);
   p[lane] = to_h16(x1 * c - x2 * s);
   p[lane + 32] = to_h16(x2 * c + x1 * s);
 }

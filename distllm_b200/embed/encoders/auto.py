@@ -19,11 +19,15 @@ from transformers import PreTrainedTokenizer
 
 from distllm_b200.embed.encoders.native import NativeBertEncoder
 from distllm_b200.embed.encoders.native import NativeMistralEncoder
+from distllm_b200.embed.encoders.native import NativeModernBertEncoder
 from distllm_b200.utils import BaseConfig
 
 # HF model_type -> native forward pass (BERT: post-LN encoder; Mistral: pre-RMSNorm decoder blocks
-# with rotary, grouped-query causal attention and SwiGLU, used as an encoder by the embedding models)
-_NATIVE_BY_MODEL_TYPE = {'bert': NativeBertEncoder, 'mistral': NativeMistralEncoder}
+# with rotary, grouped-query causal attention and SwiGLU, used as an encoder by the embedding models;
+# ModernBERT: pre-LN encoder with rotary, alternating full / sliding-window attention and GeGLU --
+# examples/embed/workstation/modernbert_semchunk.yaml:16-17)
+_NATIVE_BY_MODEL_TYPE = {'bert': NativeBertEncoder, 'mistral': NativeMistralEncoder,
+                         'modernbert': NativeModernBertEncoder}
 _SUPPORTED_MODEL_TYPES = tuple(_NATIVE_BY_MODEL_TYPE)
 
 
@@ -46,7 +50,7 @@ class AutoEncoderConfig(BaseConfig):
 
 
 class AutoEncoder:
-    """Encoder for HF checkpoints of the BERT and Mistral families on the native kernels."""
+    """Encoder for HF checkpoints of the BERT, ModernBERT and Mistral families on the native kernels."""
 
     def __init__(self, config: AutoEncoderConfig):
         from transformers import AutoConfig

@@ -21,10 +21,12 @@ class NativeBertEncoder:
 
     _DESC = staticmethod(W.bert_desc)
     _WEIGHTS = staticmethod(W.bert_weight_list)
+    _ARCH = 'bert'    # picks the build of the library (16-bit storage type): _native.storage_for_arch
 
     def __init__(self, hf_config, state_dict: Mapping[str, torch.Tensor],
-                 device: torch.device | str | None = None) -> None:
-        lib = _native.load()
+                 device: torch.device | str | None = None, storage: str | None = None) -> None:
+        self.storage = storage or _native.storage_for_arch(self._ARCH)
+        lib = _native.load(self.storage)
         if not torch.cuda.is_available():
             raise _native.NativeError(
                 'no CUDA device: the native encoder has no CPU fallback (sm_100a only)')
@@ -35,10 +37,11 @@ class NativeBertEncoder:
         self.desc = self._DESC(hf_config)
         # shape validation BEFORE the weights are converted and uploaded (an unsupported checkpoint must
         # not cost gigabytes of transfers first)
-        _native.check(lib.b2e_check_model(C.byref(self.desc)))
+        _native.check(lib.b2e_check_model(C.byref(self.desc)), lib)
         self.hidden_size = hf_config.hidden_size
         self.max_positions = hf_config.max_position_embeddings
-        self._weights = self._WEIGHTS(state_dict, hf_config.num_hidden_layers, self.device)
+        self._weights = self._WEIGHTS(state_dict, hf_config.num_hidden_layers, self.device,
+                                      _native.STORAGE_TORCH_DTYPE[self.storage])
         n = len(self._weights)
         expected = lib.b2e_num_weights(C.byref(self.desc))
         if n != expected:
@@ -46,7 +49,7 @@ class NativeBertEncoder:
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self._weights])
         handle = C.c_void_p()
         _native.check(lib.b2e_encoder_create(C.byref(self.desc), ptrs, n, self.device.index,
-                                             C.byref(handle)))
+                                             C.byref(handle)), lib)
         self._handle = handle
         self._lib = lib
 
@@ -56,7 +59,8 @@ class NativeBertEncoder:
         pass.  Needs no device and no weights: the encoders call it right after reading ``config.json``,
         before ``from_pretrained`` loads a single parameter."""
         desc = cls._DESC(hf_config)
-        _native.check(_native.load().b2e_check_model(C.byref(desc)))
+        lib = _native.load(_native.storage_for_arch(cls._ARCH))
+        _native.check(lib.b2e_check_model(C.byref(desc)), lib)
 
     def close(self) -> None:
         if getattr(self, '_handle', None):
@@ -99,7 +103,7 @@ class NativeBertEncoder:
         with torch.cuda.device(self.device):
             _native.check(self._lib.b2e_encode(
                 self._handle, ids.data_ptr(), mask.data_ptr(), _native._ptr(types), b, s,
-                out.data_ptr(), _native.dtype_code(out_dtype), _native.stream_ptr(self.device)))
+                out.data_ptr(), _native.dtype_code(out_dtype), _native.stream_ptr(self.device)), self._lib)
         return out
 
     def encode_pooled(self, input_ids: torch.Tensor, attention_mask: torch.Tensor,
@@ -118,7 +122,7 @@ class NativeBertEncoder:
         with torch.cuda.device(self.device):
             _native.check(self._lib.b2e_encode_pooled(
                 self._handle, ids.data_ptr(), mask.data_ptr(), _native._ptr(types), b, s, pool_kind,
-                int(normalize), out.data_ptr(), _native.stream_ptr(self.device)))
+                int(normalize), out.data_ptr(), _native.stream_ptr(self.device)), self._lib)
         return out
 
     def embed_host(self, input_ids: torch.Tensor, attention_mask: torch.Tensor,
@@ -137,7 +141,7 @@ class NativeBertEncoder:
                               pin_memory=True)
         _native.check(self._lib.b2e_embed_host(
             self._handle, input_ids.data_ptr(), attention_mask.data_ptr(),
-            _native._ptr(token_type_ids), n, s, batch, pool_kind, int(normalize), out.data_ptr()))
+            _native._ptr(token_type_ids), n, s, batch, pool_kind, int(normalize), out.data_ptr()), self._lib)
         return out
 
 
@@ -146,6 +150,7 @@ class NativeEsm2Encoder(NativeBertEncoder):
 
     _DESC = staticmethod(W.esm_desc)
     _WEIGHTS = staticmethod(W.esm_weight_list)
+    _ARCH = 'esm'
 
 
 class NativeMistralEncoder(NativeBertEncoder):
@@ -155,3 +160,14 @@ class NativeMistralEncoder(NativeBertEncoder):
 
     _DESC = staticmethod(W.mistral_desc)
     _WEIGHTS = staticmethod(W.mistral_weight_list)
+    _ARCH = 'mistral'
+
+
+class NativeModernBertEncoder(NativeBertEncoder):
+    """ModernBERT (pre-LayerNorm blocks, rotary with one base per layer type, alternating full / sliding-window
+    bidirectional attention, GeGLU) on the tcgen05 GEMMs and the head_dim-64 attention kernel with its
+    sliding-window variant; ``token_type_ids`` unused."""
+
+    _DESC = staticmethod(W.modernbert_desc)
+    _WEIGHTS = staticmethod(W.modernbert_weight_list)
+    _ARCH = 'modernbert'

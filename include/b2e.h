@@ -10,7 +10,8 @@
  *   b2e_encoder_create      distllm/embed/encoders/auto.py:37-97   (AutoEncoder.__init__)
  *   b2e_encode              distllm/embed/encoders/auto.py:119-138 (AutoEncoder.encode ->
  *                           HF BertModel.forward, transformers/models/bert/modeling_bert.py:628-690, or
- *                           HF MistralModel.forward, transformers/models/mistral/modeling_mistral.py:328-400)
+ *                           HF MistralModel.forward, transformers/models/mistral/modeling_mistral.py:328-400, or
+ *                           HF ModernBertModel.forward, transformers/models/modernbert/modeling_modernbert.py:424-490)
  *                           and distllm/embed/encoders/esm2.py:109-134 (Esm2Encoder.encode -> HF
  *                           EsmForMaskedLM, transformers/models/esm/modeling_esm.py:189-516)
  *   b2e_encode_pooled       distllm/embed/embedders/full_sequence.py:59-69 (encode + pool + normalize)
@@ -21,7 +22,7 @@
  *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
  *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
  *   b2e_topk_ip             distllm/rag/search.py:280-336 (exact float32 search of the query path)
- *   b2e_gemm_f16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
+ *   b2e_gemm_h16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
  *                           blocks, exported so the parity tests can pin each kernel separately.
  */
 #ifndef B2E_H_
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define B2E_ABI_VERSION 2   /* 2: 16-bit weights / activations are IEEE half (were bfloat16); b2e_gemm_f16 */
+#define B2E_ABI_VERSION 2   /* 2: the 16-bit storage type is a build property (b2e_storage_dtype); b2e_gemm_h16 */
 
 enum {
   B2E_OK = 0,
@@ -43,7 +44,7 @@ enum {
   B2E_ERR_NO_DEVICE = 4     /* no sm_100 device: there is no CPU fallback */
 };
 
-enum { B2E_ARCH_BERT = 0, B2E_ARCH_ESM2 = 1, B2E_ARCH_MISTRAL = 2 };
+enum { B2E_ARCH_BERT = 0, B2E_ARCH_ESM2 = 1, B2E_ARCH_MISTRAL = 2, B2E_ARCH_MODERNBERT = 3 };
 enum { B2E_DTYPE_F32 = 0, B2E_DTYPE_BF16 = 1, B2E_DTYPE_F16 = 2 };
 enum {
   B2E_POOL_MEAN_REF = 0,     /* mean.py semantics incl. the cross-row end-token quirk (mean.py:36) */
@@ -54,7 +55,8 @@ enum {
   B2E_EPI_BIAS = 0,
   B2E_EPI_BIAS_GELU = 1,
   B2E_EPI_BIAS_RESID = 2,
-  B2E_EPI_SWIGLU = 3 /* W rows = gate/up interleaved in blocks of 64; out is [M, N/2]; no bias */
+  B2E_EPI_SWIGLU = 3, /* W rows = gate/up interleaved in blocks of 64; out = silu(gate)*up [M, N/2]; no bias */
+  B2E_EPI_GEGLU = 4   /* same layout, out = gelu(first half) * second half (ModernBERT's Wi: input | gate) */
 };
 
 typedef struct B2EModelDesc {
@@ -70,25 +72,35 @@ typedef struct B2EModelDesc {
   int32_t type_vocab;
   float eps;             /* LayerNorm / RMSNorm epsilon */
   float rope_theta;      /* unused for BERT */
-  int32_t sliding_window;
+  int32_t sliding_window; /* Mistral: causal window (0 = none); ModernBERT: |i-j| <= sliding_window on local layers */
   int32_t reserved;
+  float rope_theta_local; /* ModernBERT: rotary base of the sliding-attention layers (rope_theta: full-attention layers) */
+  int32_t global_every;   /* ModernBERT: layer l uses full attention iff l % global_every == 0 */
 } B2EModelDesc;
 
 typedef struct B2EEncoder B2EEncoder;
 
 int b2e_version(void);
+/* B2E_DTYPE_F16 (libb2e.so) or B2E_DTYPE_BF16 (libb2e_bf16.so, the same sources built with
+ * -DB2E_STORAGE_BF16): the type of every weight matrix handed to b2e_encoder_create, of every 16-bit
+ * activation and of the operands of the building-block entry points.  Both feed the tensor cores at the same
+ * rate; half keeps 11 significand bits (a 32-layer Mistral-shaped model stays within 1e-3 cosine of fp32 only
+ * with it), bfloat16 draws less power under the 1 kW cap (BERT / ESM-2 depths are within 5e-5 with it).  The
+ * reference's own reduced precision is half (distllm/embed/encoders/auto.py:77-79). */
+int b2e_storage_dtype(void);
 const char* b2e_last_error(void);
 
 /* Number of device weight pointers b2e_encoder_create expects for `desc` (BERT: 5 + 12*L, ESM-2:
- * 3 + 12*L, Mistral: 2 + 6*L; order documented in distllm_b200/embed/encoders/weights.py).  Matrices
- * are IEEE half (fp16) [out,in] row-major, vectors and embedding tables fp32.  (fp16, not bf16: the
- * tensor cores run both at the same rate and fp16 keeps 11 significand bits; the reference's own reduced
- * precision is fp16 too, distllm/embed/encoders/auto.py:77-79.  Values outside +-65504 saturate.)  The pointers stay owned by the
+ * 3 + 12*L, Mistral: 2 + 6*L, ModernBERT: 5 + 8*L; order documented in distllm_b200/embed/encoders/weights.py).  Matrices
+ * are of the build's 16-bit storage type (b2e_storage_dtype) [out,in] row-major, vectors and embedding
+ * tables fp32.  Half values outside +-65504 saturate.  The pointers stay owned by the
  * caller and must outlive the handle.  For B2E_ARCH_ESM2, desc.reserved = mask_token_id + 1 enables
  * ESM's token dropout rescaling (0 = off) and token_type_ids are ignored.  For B2E_ARCH_MISTRAL
  * (head_dim 128, heads % kv_heads == 0, intermediate % 128 == 0) the gate/up projection is ONE matrix
  * with rows interleaved in blocks of 64 (see B2E_EPI_SWIGLU), desc.sliding_window = 0 means none, and
- * token_type_ids are ignored. */
+ * token_type_ids are ignored.  For B2E_ARCH_MODERNBERT (head_dim 64, (2*intermediate) % 256 == 0, no Linear
+ * biases) Wi is ONE matrix with its input / gate halves interleaved in blocks of 64 rows (B2E_EPI_GEGLU),
+ * absent norm biases are passed as zero vectors, token_type_ids are ignored. */
 int b2e_num_weights(const B2EModelDesc* desc);
 /* Shape validation only (no device, no weights): 0 when b2e_encoder_create would accept `desc`,
  * else the error it would fail with.  BERT / ESM-2: head_dim 64, heads*64 == H, H in 256 x
@@ -102,7 +114,7 @@ void b2e_encoder_destroy(B2EEncoder* enc);
 /* Bytes of device workspace the handle holds for a [B,S] batch (grown lazily, never shrunk). */
 int64_t b2e_workspace_bytes(const B2EEncoder* enc, int B, int S);
 
-/* Full forward pass; writes the final hidden state [B,S,H] as out_dtype (F32 or F16). */
+/* Full forward pass; writes the final hidden state [B,S,H] as out_dtype (F32 or the storage type). */
 int b2e_encode(B2EEncoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
                const int64_t* token_type_ids /* nullable */, int B, int S, void* out_hidden,
                int out_dtype, void* stream);
@@ -133,12 +145,17 @@ int b2e_l2_normalize(float* x, int64_t n_rows, int H, void* stream);
 int b2e_adjacent_cosine_dist(const void* emb, int dtype, int64_t n_rows, int H,
                              const int32_t* doc_id, float* out, void* stream);
 
-/* Building blocks (fp16 row-major, fp32 accumulation): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
-int b2e_gemm_f16(const void* A, const void* W, const float* bias, const void* resid, void* out,
+/* Building blocks (storage type, row-major, fp32 accumulation): out[M,N] = epi(A[M,K] . W[N,K]^T + bias [+ resid]). */
+int b2e_gemm_h16(const void* A, const void* W, const float* bias, const void* resid, void* out,
                   int M, int N, int K, int epilogue, void* stream);
 /* qkv [B*S, 3*heads*64] -> ctx [B*S, heads*64]; `reserved` must be NULL (it was a debug score dump). */
 int b2e_attention_d64(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
                       int heads, float* reserved, void* stream);
+/* Same with a BIDIRECTIONAL sliding window: key j is visible to query i iff |i - j| <= window and
+ * attention_mask[b,j] != 0 (window == 0: no window).  ModernBERT's local layers: HF
+ * masking_utils.sliding_window_bidirectional_overlay with config.sliding_window = local_attention / 2. */
+int b2e_attention_d64_window(const void* qkv, const int64_t* attention_mask, void* ctx, int B, int S,
+                             int heads, int window, void* stream);
 /* Causal grouped-query attention, head_dim 128 (Mistral family):
  * qkv [B*S, (heads + 2*kv_heads)*128] with columns q heads | k heads | v heads (rotary already
  * applied) -> ctx [B*S, heads*128].  Key j is visible to query i iff j <= i, attention_mask[b,j] != 0
@@ -165,7 +182,7 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
 int b2e_pack_ubinary(const float* emb, int64_t n_rows, int H, uint8_t* out_bits, void* stream);
 int b2e_search_ubinary(const float* queries, int Q, const uint8_t* corpus_bits, int64_t N, int H, int k,
                        int rescore_multiplier, float* out_scores, int64_t* out_indices, void* stream);
-int b2e_layernorm(const void* in_f16, const float* gamma, const float* beta, void* out, int rows,
+int b2e_layernorm(const void* in_h16, const float* gamma, const float* beta, void* out, int rows,
                   int H, float eps, int out_dtype, void* stream);
 
 #ifdef __cplusplus

@@ -380,6 +380,97 @@ def make_mistral_golden() -> None:
     np.savez_compressed(GOLDEN / 'mistral_tiny_golden.npz', **out)
 
 
+TINY_MODERNBERT = dict(vocab_size=320, hidden_size=256, num_hidden_layers=4, num_attention_heads=4,
+                       intermediate_size=384, max_position_embeddings=512, local_attention=32, norm_eps=1e-5,
+                       pad_token_id=0, bos_token_id=1, eos_token_id=2, cls_token_id=1, sep_token_id=2,
+                       initializer_range=0.05)
+TINY_MODERNBERT_SEED = 1357
+
+
+def tiny_modernbert_texts() -> list[str]:
+    """12 texts behind modernbert_tiny_golden.npz: up to 300 words, so that the sliding window (|i - j| <= 16)
+    and several 64-key chunks / two 128-row query tiles are exercised."""
+    words = [f'w{i:03d}' for i in range(TINY_MODERNBERT['vocab_size'] - 4)]
+    rng = np.random.default_rng(31)
+    lengths = [5, 150, 33, 1, 64, 63, 300, 7, 127, 128, 200, 90]
+    return [' '.join(rng.choice(words, size=n)) for n in lengths]
+
+
+def write_tiny_modernbert_checkpoint(ckpt_dir: Path) -> None:
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from tokenizers.processors import TemplateProcessing
+    from transformers import ModernBertConfig
+    from transformers import ModernBertModel
+    from transformers import PreTrainedTokenizerFast
+
+    from distllm_b200.embed.encoders.weights import random_modernbert_state_dict
+
+    words = [f'w{i:03d}' for i in range(TINY_MODERNBERT['vocab_size'] - 4)]
+    vocab = {t: i for i, t in enumerate(['[PAD]', '[CLS]', '[SEP]', '[UNK]', *words])}
+    cfg = ModernBertConfig(**TINY_MODERNBERT)
+    sd = random_modernbert_state_dict(cfg, seed=TINY_MODERNBERT_SEED, device='cpu')
+    model = ModernBertModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    raw = Tokenizer(WordLevel(vocab, unk_token='[UNK]'))
+    raw.pre_tokenizer = Whitespace()
+    raw.post_processor = TemplateProcessing(single='[CLS] $A [SEP]', special_tokens=[('[CLS]', 1), ('[SEP]', 2)])
+    tok = PreTrainedTokenizerFast(tokenizer_object=raw, pad_token='[PAD]', cls_token='[CLS]', sep_token='[SEP]',
+                                  unk_token='[UNK]', model_input_names=['input_ids', 'attention_mask'])
+    model.eval().save_pretrained(ckpt_dir)
+    tok.save_pretrained(ckpt_dir)
+
+
+def make_modernbert_golden() -> None:
+    """The reference's AutoEncoder (HF ModernBertModel: rotary per layer type, full / sliding-window attention,
+    GeGLU) + MeanPooler / LastTokenPooler + compute_embeddings on a tiny seeded checkpoint (the family of
+    examples/embed/workstation/modernbert_semchunk.yaml)."""
+    from torch.utils.data import DataLoader
+    from transformers import ModernBertConfig
+
+    from distllm.embed.datasets.utils import DataCollator
+    from distllm.embed.datasets.utils import InMemoryDataset
+    from distllm.embed.embedders.full_sequence import compute_embeddings
+    from distllm.embed.encoders.auto import AutoEncoder
+    from distllm.embed.encoders.auto import AutoEncoderConfig
+    from distllm.embed.poolers.last_token import LastTokenPooler
+    from distllm.embed.poolers.last_token import LastTokenPoolerConfig
+    from distllm.embed.poolers.mean import MeanPooler
+    from distllm.embed.poolers.mean import MeanPoolerConfig
+    from distllm_b200.embed.encoders.weights import random_modernbert_state_dict
+
+    cfg = ModernBertConfig(**TINY_MODERNBERT)
+    sd = random_modernbert_state_dict(cfg, seed=TINY_MODERNBERT_SEED, device='cpu')
+    texts = tiny_modernbert_texts()
+    out = {'n_texts': np.array(len(texts)), 'weights_sha256': np.array(weights_digest(sd))}
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp_path = Path(tmp)
+        write_tiny_modernbert_checkpoint(tmp_path / 'ckpt')
+        encoder = AutoEncoder(AutoEncoderConfig(
+            pretrained_model_name_or_path=str(tmp_path / 'ckpt'), quantization=False, eval_mode=True))
+        assert type(encoder.model).__name__ == 'ModernBertModel'
+        assert encoder.tokenizer.model_max_length == TINY_MODERNBERT['max_position_embeddings']
+
+        def loader() -> DataLoader:
+            return DataLoader(InMemoryDataset(texts), batch_size=4, num_workers=0,
+                              collate_fn=DataCollator(encoder.tokenizer))
+
+        for i, batch in enumerate(loader()):
+            out[f'batch{i}/input_ids'] = batch['input_ids'].numpy()
+            out[f'batch{i}/attention_mask'] = batch['attention_mask'].numpy()
+            assert 'token_type_ids' not in batch
+            if i == 1:    # holds the 300-word row
+                with torch.no_grad():
+                    out[f'batch{i}/hidden'] = encoder.encode(batch).numpy()
+        out['n_batches'] = np.array(i + 1)
+        out['pooled/mean_normalized'] = compute_embeddings(loader(), encoder, MeanPooler(MeanPoolerConfig()),
+                                                           normalize=True)
+        out['pooled/last_token'] = compute_embeddings(loader(), encoder, LastTokenPooler(LastTokenPoolerConfig()))
+    np.savez_compressed(GOLDEN / 'modernbert_tiny_golden.npz', **out)
+
+
 WORKER_DATASET = {'name': 'jsonl_chunk', 'buffer_size': 1, 'min_buffer_length': 20, 'batch_size': 5,
                   'num_data_workers': 0, 'pin_memory': False}
 WORKER_EMBEDDER = {'name': 'semantic_chunk', 'breakpoint_percentile_threshold': 80, 'chunk_batch_size': 4,
@@ -442,6 +533,7 @@ def main() -> None:
     make_bert_golden()
     make_esm_golden()
     make_mistral_golden()
+    make_modernbert_golden()
     make_worker_golden()
     for f in sorted(GOLDEN.glob('*.npz')):
         print(f.name, f.stat().st_size, 'bytes')

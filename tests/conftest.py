@@ -101,3 +101,22 @@ def cosine_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = a.astype(np.float64)
     b = b.astype(np.float64)
     return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+
+
+@pytest.fixture(scope='session')
+def modernbert_golden():
+    return np.load(GOLDEN / 'modernbert_tiny_golden.npz')
+
+
+@pytest.fixture(scope='session')
+def tiny_modernbert():
+    """(HF config, seeded state dict) of the tiny ModernBERT checkpoint behind modernbert_tiny_golden.npz."""
+    from transformers import ModernBertConfig
+
+    from oracle.make_golden import TINY_MODERNBERT
+    from oracle.make_golden import TINY_MODERNBERT_SEED
+
+    from distllm_b200.embed.encoders.weights import random_modernbert_state_dict
+
+    cfg = ModernBertConfig(**TINY_MODERNBERT)
+    return cfg, random_modernbert_state_dict(cfg, seed=TINY_MODERNBERT_SEED, device='cpu')

@@ -30,10 +30,11 @@ def test_every_exported_b2e_symbol_is_declared_in_a_header():
     nm = shutil.which('nm')
     if nm is None:
         pytest.skip('binutils nm not available')
-    out = subprocess.run([nm, '-D', '--defined-only', str(_native.LIB_PATH)], capture_output=True, text=True,
-                         check=True).stdout
-    exported = {line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith('b2e_')}
-    assert exported == set(declared_symbols()) | set(declared_symbols(DEBUG_HEADER))
+    for path in _native.LIB_PATHS.values():      # both builds (half / bfloat16 storage) export the same ABI
+        out = subprocess.run([nm, '-D', '--defined-only', str(path)], capture_output=True, text=True,
+                             check=True).stdout
+        exported = {line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith('b2e_')}
+        assert exported == set(declared_symbols()) | set(declared_symbols(DEBUG_HEADER)), path
     assert set(declared_symbols(DEBUG_HEADER)) == set(_native.DEBUG_EXPORTS)
 
 
@@ -78,8 +79,8 @@ def test_version_and_error_string():
 
 
 def test_model_desc_layout_matches_header():
-    # 14 four-byte fields, no padding
-    assert C.sizeof(_native.ModelDesc) == 56
+    # 16 four-byte fields, no padding
+    assert C.sizeof(_native.ModelDesc) == 64
 
 
 def test_num_weights_bert():
@@ -97,7 +98,7 @@ def test_num_weights_bert():
 def test_argument_validation_without_touching_the_gpu():
     lib = _native.load()
     # null pointers / bad shapes are rejected before any CUDA call
-    assert lib.b2e_gemm_f16(None, None, None, None, None, 128, 128, 64, 0, None) == 1
+    assert lib.b2e_gemm_h16(None, None, None, None, None, 128, 128, 64, 0, None) == 1
     assert b'null' in lib.b2e_last_error()
     assert lib.b2e_adjacent_cosine_dist(None, 0, 1, 768, None, None, None) == 0  # <2 rows: no-op
     assert lib.b2e_encode(None, None, None, None, 1, 1, None, 0, None) == 1
@@ -117,3 +118,14 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_native.NativeError):
         average_pool(torch.zeros(2, 4, 256), torch.ones(2, 4, dtype=torch.int64))
+
+
+def test_two_builds_differ_only_in_storage_dtype():
+    f16, bf16 = _native.load('f16'), _native.load('bf16')
+    assert f16.b2e_storage_dtype() == _native.DTYPE_F16 and bf16.b2e_storage_dtype() == _native.DTYPE_BF16
+    assert f16.b2e_version() == bf16.b2e_version() == 2
+    assert _native.storage_of(torch.float16) == 'f16' and _native.storage_of(torch.bfloat16) == 'bf16'
+    with pytest.raises(_native.NativeError):
+        _native.storage_of(torch.float32)
+    # family -> build: the deep Mistral shape needs half, BERT / ESM-2 run the cooler bfloat16 build
+    assert _native.storage_for_arch('mistral') == 'f16' and _native.storage_for_arch('bert') == 'bf16'

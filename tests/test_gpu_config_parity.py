@@ -147,3 +147,36 @@ def test_c3_mistral_7b_full_depth_s1024(weights):
         enc.close()
         del sd
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('weights', ['normal', 'outliers'])
+def test_modernbert_base_full_depth_long_sequences(weights):
+    """ModernBERT-base shape (22 layers, H=768, I=1152, local window +-64, theta 160000 / 10000) at S = 1500 --
+    far beyond one key chunk range of a sliding layer, ragged -- vs the CPU oracle."""
+    from transformers import ModernBertConfig
+
+    from distllm_b200.embed.encoders.native import NativeModernBertEncoder
+    from distllm_b200.embed.encoders.weights import random_modernbert_state_dict
+    from oracle import modernbert as omb
+
+    cfg = ModernBertConfig()      # the published base configuration
+    assert (cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size, cfg.sliding_window) == (22, 768, 1152, 64)
+    sd = random_modernbert_state_dict(cfg, seed=9, device='cpu')
+    if weights == 'outliers':
+        add_outliers(sd, 'modernbert', seed=4)
+    g = torch.Generator().manual_seed(24)
+    b, s = 3, 1500
+    ids = torch.randint(5, cfg.vocab_size - 100, (b, s), generator=g)
+    lens = [1500, 700, 65]
+    mask = ragged_mask(lens, s)
+    ref_hidden = omb.modernbert_forward(sd, cfg, ids, mask)
+    ref = opool.average_pool(ref_hidden, mask.clone()).numpy()
+    enc = NativeModernBertEncoder(cfg, sd)
+    try:
+        got = enc.encode_pooled(ids, mask, None, nv.POOL_MEAN_REF, False).cpu().numpy()
+        check_rows(got, ref, f'ModernBERT {weights} mean')
+        hidden = enc.encode(ids, mask).cpu().numpy()
+        valid = mask.bool().numpy()
+        check_rows(hidden[valid], ref_hidden.numpy()[valid], f'ModernBERT {weights} tokens')
+    finally:
+        enc.close()

@@ -1,5 +1,7 @@
 """-m gpu: each native kernel, called through the C ABI, against a torch fp32 reference or the
-golden vectors produced by the reference.  Tolerances: fp16 outputs carry 2^-11 relative rounding."""
+golden vectors produced by the reference.  The 16-bit kernels run in BOTH builds of the library (h16 =
+float16 -> libb2e.so, bfloat16 -> libb2e_bf16.so); tolerances follow the storage type's rounding
+(2^-11 resp. 2^-8 relative)."""
 
 from __future__ import annotations
 
@@ -19,36 +21,48 @@ def dev():
     return torch.device('cuda:0')
 
 
+@pytest.fixture(params=[torch.float16, torch.bfloat16], ids=['f16', 'bf16'])
+def h16(request):
+    """The 16-bit storage type = which build of the library the call lands in."""
+    return request.param
+
+
+def close(got, ref, h16, scale: float = 1.0):
+    """assert_close with the storage type's rounding: `scale` x (3e-3 for half, 1.2e-2 for bfloat16)."""
+    t = (3e-3 if h16 == torch.float16 else 1.2e-2) * scale
+    torch.testing.assert_close(got, ref, rtol=t, atol=t)
+
+
 GEMM_SHAPES = [(128, 256, 64), (300, 768, 768), (1000, 2304, 768), (517, 3072, 768), (517, 768, 3072),
                (200, 384, 128), (1, 768, 768), (20000, 768, 768)]
 
 
 @pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
 @pytest.mark.parametrize('epi', [nv.EPI_BIAS, nv.EPI_BIAS_GELU, nv.EPI_BIAS_RESID])
-def test_gemm_epilogues(dev, m, n, k, epi):
+def test_gemm_epilogues(dev, m, n, k, epi, h16):
     g = torch.Generator(device=dev).manual_seed(m * 7 + n + k + epi)
-    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).half()
-    w = (torch.randn(n, k, device=dev, generator=g) * 0.05).half()
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(h16)
+    w = (torch.randn(n, k, device=dev, generator=g) * 0.05).to(h16)
     bias = torch.randn(n, device=dev, generator=g) * 0.1
-    resid = torch.randn(m, n, device=dev, generator=g).half()
-    out = nv.gemm_f16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
+    resid = torch.randn(m, n, device=dev, generator=g).to(h16)
+    out = nv.gemm_h16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
     ref = a.float() @ w.float().T + bias
     if epi == nv.EPI_BIAS_GELU:
         ref = torch.nn.functional.gelu(ref)
     if epi == nv.EPI_BIAS_RESID:
         ref = ref + resid.float()
-    assert out.dtype == torch.float16 and out.shape == (m, n)
-    torch.testing.assert_close(out.float(), ref, rtol=3e-3, atol=3e-3)   # fp16 output: 2^-11 relative
+    assert out.dtype == h16 and out.shape == (m, n)
+    close(out.float(), ref, h16)
 
 
-def test_gemm_rejects_bad_shapes(dev):
-    a = torch.zeros(8, 100, device=dev, dtype=torch.float16)
-    w = torch.zeros(128, 100, device=dev, dtype=torch.float16)
+def test_gemm_rejects_bad_shapes(dev, h16):
+    a = torch.zeros(8, 100, device=dev, dtype=h16)
+    w = torch.zeros(128, 100, device=dev, dtype=h16)
     with pytest.raises(nv.NativeError, match='K=100'):
-        nv.gemm_f16(a, w, torch.zeros(128, device=dev))
+        nv.gemm_h16(a, w, torch.zeros(128, device=dev))
     with pytest.raises(nv.NativeError, match='N=100'):
-        nv.gemm_f16(torch.zeros(8, 64, device=dev, dtype=torch.float16),
-                     torch.zeros(100, 64, device=dev, dtype=torch.float16), torch.zeros(100, device=dev))
+        nv.gemm_h16(torch.zeros(8, 64, device=dev, dtype=h16),
+                     torch.zeros(100, 64, device=dev, dtype=h16), torch.zeros(100, device=dev))
 
 
 def ref_attention(qkv, mask, b, s, heads):
@@ -65,23 +79,23 @@ def ref_attention(qkv, mask, b, s, heads):
                                               (2, 512, 12, True), (4, 37, 4, True), (5, 1, 4, False),
                                               (2, 129, 4, True), (1, 384, 12, True), (2, 640, 2, False),
                                               (1, 1026, 4, True), (3, 257, 2, True)])
-def test_attention_matches_reference(dev, b, s, heads, ragged):
+def test_attention_matches_reference(dev, b, s, heads, ragged, h16):
     g = torch.Generator(device=dev).manual_seed(b * 1000 + s)
-    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).half()
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(h16)
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     if ragged:
         for i in range(b):
             mask[i, max(1, s - 17 * (i + 1)):] = 0
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
-    torch.testing.assert_close(ctx.float(), ref_attention(qkv, mask, b, s, heads), rtol=6e-3, atol=4e-3)
+    close(ctx.float(), ref_attention(qkv, mask, b, s, heads), h16, 2.0)
 
 
-def test_attention_mask_with_holes_and_fully_masked_row(dev):
+def test_attention_mask_with_holes_and_fully_masked_row(dev, h16):
     """Arbitrary 0/1 masks (left padding, holes); an all-zero mask degenerates to a uniform
     distribution over the S keys exactly like HF's additive most-negative-finite mask."""
     b, s, heads = 3, 96, 4
     g = torch.Generator(device=dev).manual_seed(9)
-    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).half()
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(h16)
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     mask[0, :40] = 0            # left padding
     mask[1, 10:20] = 0          # a hole
@@ -89,24 +103,24 @@ def test_attention_mask_with_holes_and_fully_masked_row(dev):
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
     ref = ref_attention(qkv, mask, b, s, heads)
     assert torch.isfinite(ctx.float()).all()
-    torch.testing.assert_close(ctx.float(), ref, rtol=6e-3, atol=4e-3)
+    close(ctx.float(), ref, h16, 2.0)
 
 
-def test_attention_many_items_per_cta(dev):
+def test_attention_many_items_per_cta(dev, h16):
     """More work items than SMs: the persistent CTAs recycle Q buffers, ring stages and TMEM slots."""
     b, s, heads = 40, 300, 12
     g = torch.Generator(device=dev).manual_seed(77)
-    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).half()
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(h16)
     lens = torch.randint(1, s + 1, (b,), generator=torch.Generator().manual_seed(5))
     mask = (torch.arange(s)[None] < lens[:, None]).long().to(dev)
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
     ref = ref_attention(qkv, mask, b, s, heads)
     valid = mask.bool().view(-1)
-    torch.testing.assert_close(ctx.float()[valid], ref[valid], rtol=6e-3, atol=4e-3)
+    close(ctx.float()[valid], ref[valid], h16, 2.0)
     assert torch.isfinite(ctx.float()).all()
 
 
-def test_attention_large_scores_trigger_rescale(dev):
+def test_attention_large_scores_trigger_rescale(dev, h16):
     """Scores that grow along the key axis force the lazy online-softmax rescale path."""
     b, s, heads = 2, 512, 2
     g = torch.Generator(device=dev).manual_seed(78)
@@ -114,22 +128,21 @@ def test_attention_large_scores_trigger_rescale(dev):
     # keys later in the sequence get larger norms -> row maxima jump by far more than 2^8
     ramp = torch.linspace(0.2, 6.0, s, device=dev).repeat(b)[:, None]
     qkv[:, heads * 64:2 * heads * 64] *= ramp
-    qkv = qkv.half()
+    qkv = qkv.to(h16)
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
-    torch.testing.assert_close(ctx.float(), ref_attention(qkv, mask, b, s, heads), rtol=1e-2, atol=6e-3)
+    close(ctx.float(), ref_attention(qkv, mask, b, s, heads), h16, 3.0)
 
 
 @pytest.mark.parametrize('h', [256, 768, 1024, 1280])
-def test_layernorm(dev, h):
+def test_layernorm(dev, h, h16):
     g = torch.Generator(device=dev).manual_seed(h)
-    x = (torch.randn(1003, h, device=dev, generator=g) * 3 + 1).half()
+    x = (torch.randn(1003, h, device=dev, generator=g) * 3 + 1).to(h16)
     gamma = torch.randn(h, device=dev, generator=g)
     beta = torch.randn(h, device=dev, generator=g)
     ref = torch.nn.functional.layer_norm(x.float(), (h,), gamma, beta, 1e-12)
     torch.testing.assert_close(nv.layernorm(x, gamma, beta, 1e-12, torch.float32), ref, rtol=1e-4, atol=1e-4)
-    torch.testing.assert_close(nv.layernorm(x, gamma, beta, 1e-12, torch.float16).float(), ref,
-                               rtol=1e-2, atol=1e-2)
+    close(nv.layernorm(x, gamma, beta, 1e-12).float(), ref, h16, 2.0)
 
 
 @pytest.mark.parametrize('case', ['ragged', 'full', 'single', 'left_padded_like'])
@@ -219,26 +232,26 @@ def test_l2_normalize(dev):
 
 # ---------------------------------------------------------------------------- Mistral-family kernels
 @pytest.mark.parametrize('m,i,k', [(128, 128, 64), (300, 768, 512), (1000, 1792, 1024), (5, 256, 4096)])
-def test_gemm_swiglu_epilogue(dev, m, i, k):
+def test_gemm_swiglu_epilogue(dev, m, i, k, h16):
     """gate/up rows interleaved in blocks of 64 -> silu(gate) * up, no bias, [M, I] out."""
     from distllm_b200.embed.encoders.weights import interleave_gate_up
 
     g = torch.Generator(device=dev).manual_seed(m + i + k)
-    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).half()
-    gate = (torch.randn(i, k, device=dev, generator=g) * 0.08).half()
-    up = (torch.randn(i, k, device=dev, generator=g) * 0.08).half()
-    out = nv.gemm_f16(a, interleave_gate_up(gate, up).contiguous(), None, None, nv.EPI_SWIGLU)
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(h16)
+    gate = (torch.randn(i, k, device=dev, generator=g) * 0.08).to(h16)
+    up = (torch.randn(i, k, device=dev, generator=g) * 0.08).to(h16)
+    out = nv.gemm_h16(a, interleave_gate_up(gate, up).contiguous(), None, None, nv.EPI_SWIGLU)
     ref = torch.nn.functional.silu(a.float() @ gate.float().T) * (a.float() @ up.float().T)
-    assert out.dtype == torch.float16 and out.shape == (m, i)
-    torch.testing.assert_close(out.float(), ref, rtol=4e-3, atol=3e-3)
+    assert out.dtype == h16 and out.shape == (m, i)
+    close(out.float(), ref, h16, 1.3)
 
 
-def test_gemm_without_bias(dev):
+def test_gemm_without_bias(dev, h16):
     g = torch.Generator(device=dev).manual_seed(4)
-    a = torch.randn(200, 256, device=dev, generator=g).half()
-    w = (torch.randn(512, 256, device=dev, generator=g) * 0.05).half()
-    out = nv.gemm_f16(a, w, None)
-    torch.testing.assert_close(out.float(), a.float() @ w.float().T, rtol=3e-3, atol=3e-3)
+    a = torch.randn(200, 256, device=dev, generator=g).to(h16)
+    w = (torch.randn(512, 256, device=dev, generator=g) * 0.05).to(h16)
+    out = nv.gemm_h16(a, w, None)
+    close(out.float(), a.float() @ w.float().T, h16)
 
 
 def ref_attention_causal(qkv, mask, b, s, heads, kv_heads, window):
@@ -273,9 +286,9 @@ CAUSAL_CASES = [
 
 
 @pytest.mark.parametrize('b,s,heads,kv_heads,window,padding', CAUSAL_CASES)
-def test_attention_causal_d128_matches_reference(dev, b, s, heads, kv_heads, window, padding):
+def test_attention_causal_d128_matches_reference(dev, b, s, heads, kv_heads, window, padding, h16):
     g = torch.Generator(device=dev).manual_seed(b * 1000 + s + window)
-    qkv = torch.randn(b * s, (heads + 2 * kv_heads) * 128, device=dev, generator=g).half()
+    qkv = torch.randn(b * s, (heads + 2 * kv_heads) * 128, device=dev, generator=g).to(h16)
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     for r in range(b):
         n_pad = min(s - 1, 23 * r + (5 if padding != 'none' else 0)) if padding != 'none' else 0
@@ -288,10 +301,10 @@ def test_attention_causal_d128_matches_reference(dev, b, s, heads, kv_heads, win
     assert torch.isfinite(ctx.float()).all()
     # rows that see no key at all (queries inside left padding) are unspecified; everything else,
     # including padded query positions that still see attended keys, must match
-    torch.testing.assert_close(ctx.float()[alive], ref[alive], rtol=6e-3, atol=4e-3)
+    close(ctx.float()[alive], ref[alive], h16, 2.0)
 
 
-def test_attention_causal_d128_many_items_and_rescale(dev):
+def test_attention_causal_d128_many_items_and_rescale(dev, h16):
     """More items than SMs with mixed lengths, and key norms that grow along the sequence so the lazy
     rescale path runs on top of the causal/window edge masking."""
     b, s, heads, kv_heads, window = 24, 700, 8, 2, 333
@@ -299,14 +312,14 @@ def test_attention_causal_d128_many_items_and_rescale(dev):
     qkv = torch.randn(b * s, (heads + 2 * kv_heads) * 128, device=dev, generator=g)
     ramp = torch.linspace(0.2, 4.0, s, device=dev).repeat(b)[:, None]
     qkv[:, heads * 128:(heads + kv_heads) * 128] *= ramp
-    qkv = qkv.half()
+    qkv = qkv.to(h16)
     lens = torch.randint(1, s + 1, (b,), generator=torch.Generator().manual_seed(6))
     mask = (torch.arange(s)[None] < lens[:, None]).long().to(dev)
     ctx = nv.attention_causal_d128(qkv, mask, b, s, heads, kv_heads, window)
     ref, alive = ref_attention_causal(qkv, mask, b, s, heads, kv_heads, window)
     sel = alive & mask.bool().view(-1)
     assert torch.isfinite(ctx.float()).all()
-    torch.testing.assert_close(ctx.float()[sel], ref[sel], rtol=1e-2, atol=6e-3)
+    close(ctx.float()[sel], ref[sel], h16, 3.0)
 
 
 # ---------------------------------------------------------------------------- exact inner-product top-k
@@ -406,3 +419,41 @@ def test_exact_index_ubinary_through_the_retriever_surface():
     np.testing.assert_allclose(np.array(res.total_scores), ref_s, rtol=1e-5, atol=1e-4)
     kept = index.search(q, top_k=4, score_threshold=float(ref_s[0, 1]))
     assert kept.total_indices[0] == ref_i[0, :2].tolist()
+
+
+@pytest.mark.parametrize('m,i,k', [(300, 1152, 768), (1000, 2624, 1024)])
+def test_gemm_geglu_epilogue(dev, m, i, k, h16):
+    """ModernBERT's gated MLP: Wi rows = input | gate (transformers/models/modernbert/modeling_modernbert.py
+    :88-91), interleaved in blocks of 64 for the epilogue: out = gelu(x Wi_in^T) * (x Wi_gate^T)."""
+    from distllm_b200.embed.encoders.weights import interleave_gate_up
+
+    g = torch.Generator(device=dev).manual_seed(m + i)
+    a = (torch.randn(m, k, device=dev, generator=g) * 0.5).to(h16)
+    w_in = (torch.randn(i, k, device=dev, generator=g) * 0.08).to(h16)
+    w_gate = (torch.randn(i, k, device=dev, generator=g) * 0.08).to(h16)
+    out = nv.gemm_h16(a, interleave_gate_up(w_in, w_gate).contiguous(), None, None, nv.EPI_GEGLU)
+    ref = torch.nn.functional.gelu(a.float() @ w_in.float().T) * (a.float() @ w_gate.float().T)
+    assert out.dtype == h16 and out.shape == (m, i)
+    close(out.float(), ref, h16, 1.3)
+
+
+@pytest.mark.parametrize('b,s,heads,window', [(2, 512, 4, 64), (3, 333, 2, 64), (1, 1500, 2, 64), (2, 200, 4, 16),
+                                              (2, 700, 2, 300)])
+def test_attention_d64_sliding_window(dev, b, s, heads, window, h16):
+    """Bidirectional sliding window |i - j| <= window (ModernBERT's local layers) on ragged batches; rows of
+    padding tiles must stay finite."""
+    g = torch.Generator(device=dev).manual_seed(b * 100 + s + window)
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(h16)
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    for r in range(1, b):
+        mask[r, max(1, s - 90 * r):] = 0
+    ctx = nv.attention_d64_window(qkv, mask, b, s, heads, window)
+    q, k, v = qkv.float().view(b, s, 3, heads, 64).unbind(2)
+    q, k, v = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    i = torch.arange(s, device=dev)
+    vis = ((i[:, None] - i[None, :]).abs() <= window)[None, None] & (mask != 0)[:, None, None, :]
+    scores = (q @ k.transpose(-1, -2) / 8.0).masked_fill(~vis, torch.finfo(torch.float32).min)
+    ref = (torch.softmax(scores, -1) @ v).permute(0, 2, 1, 3).reshape(b * s, heads * 64)
+    valid = mask.bool().view(-1)
+    assert torch.isfinite(ctx.float()).all()
+    close(ctx.float()[valid], ref[valid], h16, 2.0)

@@ -532,3 +532,46 @@ def test_esm2_full_length_properties():
             assert cos.min() > 1 - 1e-5, (row, cos)
     finally:
         native.close()
+
+
+# ---------------------------------------------------------------------------------- ModernBERT
+@pytest.mark.parametrize('storage', ['bf16', 'f16'])
+def test_modernbert_matches_reference_vectors(tiny_modernbert, modernbert_golden, storage):
+    """`auto` encoder on a ModernBERT checkpoint through the plugin API vs the reference's AutoEncoder (HF
+    ModernBertModel) outputs: rotary per layer type, alternating full / sliding-window attention (|i - j| <= 16
+    here), GeGLU, pre-LN with an un-normed first layer; a 302-token row spans three query tiles."""
+    from distllm_b200.embed.encoders.native import NativeModernBertEncoder
+
+    cfg, sd = tiny_modernbert
+    g = modernbert_golden
+    native = NativeModernBertEncoder(cfg, sd, storage=storage)
+    try:
+        encoder = AutoEncoder.from_native(native)
+        batches = [{k: torch.from_numpy(g[f'batch{i}/{k}']) for k in ('input_ids', 'attention_mask')}
+                   for i in range(int(g['n_batches']))]
+        hidden = encoder.encode(BatchEncoding(batches[1])).cpu().numpy()
+        valid = batches[1]['attention_mask'].bool().numpy()
+        assert np.isfinite(hidden).all()
+        cos = cosine_rows(hidden[valid], g['batch1/hidden'][valid])
+        assert cos.min() > 1 - COS_TOL, cos.min()
+        for fused in (True, False):
+            enc = encoder
+            if not fused:
+                class Unfused:
+                    dtype, device, embedding_size = encoder.dtype, encoder.device, encoder.embedding_size
+                    tokenizer = None
+                    encode = staticmethod(encoder.encode)
+                enc = Unfused()
+            result = get_embedder({'name': 'full_sequence'}).embed(
+                loader_of(batches), enc, get_pooler({'name': 'last_token'}))
+            cos = cosine_rows(result.embeddings, g['pooled/last_token'])
+            assert cos.min() > 1 - COS_TOL, (fused, cos)
+            result = get_embedder({'name': 'full_sequence', 'normalize_embeddings': True}).embed(
+                loader_of(batches), enc, get_pooler({'name': 'mean'}))
+            ref = g['pooled/mean_normalized']
+            empty = np.linalg.norm(ref, axis=-1) == 0
+            assert not result.embeddings[empty].any()
+            cos = cosine_rows(result.embeddings[~empty], ref[~empty])
+            assert cos.min() > 1 - COS_TOL, (fused, cos)
+    finally:
+        native.close()

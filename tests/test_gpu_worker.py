@@ -236,3 +236,26 @@ def test_embedding_worker_semantic_chunk_matches_reference_worker(bert_ckpt, tmp
     cos = cosine_rows(np.load(out / 'embeddings.npy'), golden['embeddings'])
     assert cos.min() > 1 - COS_TOL, cos
     registry.clear()
+
+
+def test_embedding_worker_modernbert_checkpoint_dir_matches_reference(tmp_path, modernbert_golden):
+    """`auto` encoder on a ModernBertModel checkpoint dir (the family of the reference's
+    examples/embed/workstation/modernbert_semchunk.yaml) through the worker, normalised mean embeddings."""
+    from distllm_b200.distributed_embedding import embedding_worker
+    from distllm_b200.registry import registry
+    from oracle.make_golden import tiny_modernbert_texts
+    from oracle.make_golden import write_tiny_modernbert_checkpoint
+
+    write_tiny_modernbert_checkpoint(tmp_path / 'ckpt')
+    texts = tiny_modernbert_texts()
+    (tmp_path / 't.jsonl').write_text('\n'.join(json.dumps({'text': t}) for t in texts) + '\n')
+    kw = worker_kwargs(tmp_path / 'ckpt')
+    kw['embedder_kwargs'] = {'name': 'full_sequence', 'normalize_embeddings': True}
+    embedding_worker(tmp_path / 't.jsonl', tmp_path / 'out', **kw)
+    emb = np.load(read_single_output(tmp_path / 'out') / 'embeddings.npy')
+    ref = modernbert_golden['pooled/mean_normalized']
+    live = np.linalg.norm(ref, axis=-1) > 0
+    assert not emb[~live].any()
+    cos = cosine_rows(emb[live], ref[live])
+    assert cos.min() > 1 - COS_TOL, cos
+    registry.clear()

@@ -243,3 +243,39 @@ def test_mistral_oracle_matches_hf_model():
     got = omis.mistral_forward(sd, cfg, ids, mask)
     valid = mask.bool()
     np.testing.assert_allclose(got[valid].numpy(), ref[valid].numpy(), rtol=1e-4, atol=5e-5)
+
+
+def test_modernbert_oracle_matches_reference_and_hf(tiny_modernbert, modernbert_golden):
+    """oracle/modernbert.py vs the reference's AutoEncoder outputs (golden) and vs HF ModernBertModel run here:
+    rotary per layer type, sliding-window layers (|i - j| <= 16 in the tiny config), GeGLU, layer 0 without
+    attn_norm."""
+    from transformers import ModernBertModel
+
+    from oracle import modernbert as omb
+    from oracle import pooling as opool
+
+    cfg, sd = tiny_modernbert
+    g = modernbert_golden
+    batches = [{k: torch.from_numpy(g[f'batch{i}/{k}']) for k in ('input_ids', 'attention_mask')}
+               for i in range(int(g['n_batches']))]
+    hidden = omb.modernbert_forward(sd, cfg, batches[1]['input_ids'], batches[1]['attention_mask'])
+    valid = batches[1]['attention_mask'].bool().numpy()
+    np.testing.assert_allclose(hidden.numpy()[valid], g['batch1/hidden'][valid], atol=5e-5, rtol=0)
+    last = opool.compute_embeddings(batches, lambda b: omb.modernbert_forward(sd, cfg, b['input_ids'], b['attention_mask']),
+                                    opool.last_token_pool)
+    np.testing.assert_allclose(last, g['pooled/last_token'], atol=5e-5, rtol=0)
+    mean = opool.compute_embeddings(
+        [{k: v.clone() for k, v in b.items()} for b in batches],
+        lambda b: omb.modernbert_forward(sd, cfg, b['input_ids'], b['attention_mask']), opool.average_pool, True)
+    np.testing.assert_allclose(mean, g['pooled/mean_normalized'], atol=5e-5, rtol=0)
+    # per-layer states against HF's own hidden_states (layer by layer, final_norm applied to the HF states)
+    cfg._attn_implementation = 'eager'
+    model = ModernBertModel(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = model(input_ids=batches[1]['input_ids'], attention_mask=batches[1]['attention_mask'],
+                    output_hidden_states=True)
+    states = omb.modernbert_forward(sd, cfg, batches[1]['input_ids'], batches[1]['attention_mask'], return_all=True)
+    for layer, ours in enumerate(states, start=1):
+        theirs = model.final_norm(out.hidden_states[layer]) if layer < len(states) else out.last_hidden_state
+        np.testing.assert_allclose(ours.numpy()[valid], theirs.detach().numpy()[valid], atol=5e-5, rtol=0)

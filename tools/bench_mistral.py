@@ -67,15 +67,15 @@ wqkv = (torch.randn(QC, H, device=dev) * 0.02).half()
 wo = (torch.randn(H, H, device=dev) * 0.02).half()
 wgu = (torch.randn(2 * I, H, device=dev) * 0.02).half()
 wd = (torch.randn(H, I, device=dev) * 0.02).half()
-qkv = nv.gemm_f16(x, wqkv, None)
-ffn = nv.gemm_f16(x, wgu, None, None, nv.EPI_SWIGLU)
+qkv = nv.gemm_h16(x, wqkv, None)
+ffn = nv.gemm_h16(x, wgu, None, None, nv.EPI_SWIGLU)
 parts = {
-    'gemm_qkv': (timeit(lambda: nv.gemm_f16(x, wqkv, None)), 2.0 * M * H * QC),
+    'gemm_qkv': (timeit(lambda: nv.gemm_h16(x, wqkv, None)), 2.0 * M * H * QC),
     'attention_causal': (timeit(lambda: nv.attention_causal_d128(qkv, mask, B, S, HEADS, KV, 4096)),
                          2.0 * B * S * (S + 128) * H),
-    'gemm_o': (timeit(lambda: nv.gemm_f16(x, wo, None)), 2.0 * M * H * H),
-    'gemm_gate_up_swiglu': (timeit(lambda: nv.gemm_f16(x, wgu, None, None, nv.EPI_SWIGLU)), 4.0 * M * H * I),
-    'gemm_down': (timeit(lambda: nv.gemm_f16(ffn, wd, None)), 2.0 * M * H * I),
+    'gemm_o': (timeit(lambda: nv.gemm_h16(x, wo, None)), 2.0 * M * H * H),
+    'gemm_gate_up_swiglu': (timeit(lambda: nv.gemm_h16(x, wgu, None, None, nv.EPI_SWIGLU)), 4.0 * M * H * I),
+    'gemm_down': (timeit(lambda: nv.gemm_h16(ffn, wd, None)), 2.0 * M * H * I),
 }
 res['layer_kernels'] = {k: {'ms': round(t, 3), 'tflops': round(f / t / 1e9, 1)} for k, (t, f) in parts.items()}
 res['layer_kernels_sum_ms'] = round(sum(t for t, _ in parts.values()), 3)

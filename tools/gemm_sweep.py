@@ -19,11 +19,11 @@ print('B2E_GEMM =', os.environ.get('B2E_GEMM', '(default)'))
 for name, m, n, k, epi in SHAPES:
     a = torch.randn(m, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * 0.02).half()
     b = None if epi == nv.EPI_SWIGLU else torch.zeros(n, device=dev)
-    for _ in range(3): nv.gemm_f16(a, w, b, None, epi)
+    for _ in range(3): nv.gemm_h16(a, w, b, None, epi)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): nv.gemm_f16(a, w, b, None, epi)
+    for _ in range(10): nv.gemm_h16(a, w, b, None, epi)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f'{name:24s} M={m:6d} N={n:5d} K={k:5d}: {ms:7.3f} ms  {2*m*n*k/ms/1e9:6.0f} TFLOP/s', flush=True)

@@ -13,11 +13,11 @@ flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 a = torch.randn(m, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * 0.02).half(); b = torch.zeros(n, device=dev)
 lib.b2e_debug_set_pair_flags.argtypes = [ctypes.c_int]
 lib.b2e_debug_set_pair_flags(flags)
-nv.gemm_f16(a, w, b); torch.cuda.synchronize()
+nv.gemm_h16(a, w, b); torch.cuda.synchronize()
 buf = torch.zeros(4 * 256, dtype=torch.int64, device=dev)
 lib.b2e_debug_set_clock_buffer.argtypes = [ctypes.c_void_p]
 assert lib.b2e_debug_set_clock_buffer(buf.data_ptr()) == 0
-nv.gemm_f16(a, w, b); torch.cuda.synchronize()
+nv.gemm_h16(a, w, b); torch.cuda.synchronize()
 assert lib.b2e_debug_set_clock_buffer(None) == 0
 t = buf.view(4, 256).cpu().tolist()
 print(f'M={m} N={n} K={k} flags={flags}  ({k // 64} K blocks per tile)')

@@ -40,7 +40,7 @@ def probe_gemm():
         base = a.float() @ w.float().T + bias
         for epi, name in [(nv.EPI_BIAS, 'bias'), (nv.EPI_BIAS_GELU, 'gelu'), (nv.EPI_BIAS_RESID, 'resid')]:
             try:
-                out = nv.gemm_f16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
+                out = nv.gemm_h16(a, w, bias, resid if epi == nv.EPI_BIAS_RESID else None, epi)
                 torch.cuda.synchronize()
             except Exception as exc:  # noqa: BLE001
                 print(f'gemm {m}x{n}x{k} {name}: EXC {exc}', flush=True)
@@ -146,12 +146,12 @@ def probe_time():
         resid = torch.randn(m, n, device=dev).half()
         r = resid if epi == nv.EPI_BIAS_RESID else None
         for _ in range(3):
-            nv.gemm_f16(a, w, bias, r, epi)
+            nv.gemm_h16(a, w, bias, r, epi)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            nv.gemm_f16(a, w, bias, r, epi)
+            nv.gemm_h16(a, w, bias, r, epi)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10

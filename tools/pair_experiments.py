@@ -12,11 +12,11 @@ m, n, k = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (65536, 2304
 print(f'M={m} N={n} K={k}')
 a = torch.randn(m, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * 0.02).half(); b = torch.zeros(n, device=dev)
 def timeit(tag):
-    for _ in range(3): nv.gemm_f16(a, w, b)
+    for _ in range(3): nv.gemm_h16(a, w, b)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): nv.gemm_f16(a, w, b)
+    for _ in range(10): nv.gemm_h16(a, w, b)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     kblocks = -(-((m // 256) * (n // 256)) // 74) * (k // 64)      # K blocks of the busiest cluster

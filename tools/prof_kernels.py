@@ -23,11 +23,11 @@ wqkv = (torch.randn(3 * h, h, device=dev) * 0.02).half()
 wo = (torch.randn(h, h, device=dev) * 0.02).half()
 mask = torch.ones(b, s, dtype=torch.int64, device=dev)
 for _ in range(2):
-    qkv = nv.gemm_f16(x, wqkv, torch.zeros(3 * h, device=dev), None, nv.EPI_BIAS)
+    qkv = nv.gemm_h16(x, wqkv, torch.zeros(3 * h, device=dev), None, nv.EPI_BIAS)
     ctx = nv.attention_d64(qkv, mask, b, s, heads)
-    t = nv.gemm_f16(ctx, wo, torch.zeros(h, device=dev), None, nv.EPI_BIAS)   # residual add lives in the LayerNorm
+    t = nv.gemm_h16(ctx, wo, torch.zeros(h, device=dev), None, nv.EPI_BIAS)   # residual add lives in the LayerNorm
     y = nv.layernorm(t, torch.ones(h, device=dev), torch.zeros(h, device=dev), 1e-12)
-    f = nv.gemm_f16(y, w1, torch.zeros(i, device=dev), None, nv.EPI_BIAS_GELU)
-    t2 = nv.gemm_f16(f, w2, torch.zeros(h, device=dev), None, nv.EPI_BIAS)
+    f = nv.gemm_h16(y, w1, torch.zeros(i, device=dev), None, nv.EPI_BIAS_GELU)
+    t2 = nv.gemm_h16(f, w2, torch.zeros(h, device=dev), None, nv.EPI_BIAS)
 torch.cuda.synchronize()
 print('done')

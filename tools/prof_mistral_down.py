@@ -7,5 +7,5 @@ from distllm_b200 import _native as nv
 dev = torch.device('cuda:0')
 m, n, k = 65536, 4096, 14336
 a = torch.randn(m, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * 0.02).half()
-for _ in range(4): nv.gemm_f16(a, w, None)
+for _ in range(4): nv.gemm_h16(a, w, None)
 torch.cuda.synchronize(); print('done')

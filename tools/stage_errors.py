@@ -47,7 +47,7 @@ print(f'Mistral-7B block, B={B} S={S}: relative error ||native - fp32|| / ||fp32
 # ---- QKV projection
 wqkv = torch.cat([wq, wk, wv])
 qkv_ref = h.float() @ wqkv.float().t()
-qkv = nv.gemm_f16(h, wqkv, None)
+qkv = nv.gemm_h16(h, wqkv, None)
 print(f'qkv GEMM (K={H}): rel {rel(qkv, qkv_ref):.2e}   [16-bit output rounding alone: {rel(qkv_ref.half(), qkv_ref):.2e}]')
 
 # ---- attention on identical (16-bit) q/k/v, no rotary (position-free: isolates the kernel)
@@ -77,26 +77,26 @@ for lo, hi in ((0, 1), (1, 8), (8, 64), (64, 256), (256, S)):
 # ---- o_proj
 ctx_in = ctx_ref.half().contiguous()
 o_ref = ctx_in.float() @ wo.float().t()
-o = nv.gemm_f16(ctx_in, wo, None)
+o = nv.gemm_h16(ctx_in, wo, None)
 print(f'o_proj GEMM (K={HEADS * D}): rel {rel(o, o_ref):.2e}')
 
 # ---- gate/up + SwiGLU
 gu = interleave_gate_up(wg, wu).contiguous()
 act_ref = F.silu(h.float() @ wg.float().t()) * (h.float() @ wu.float().t())
-act = nv.gemm_f16(h, gu, None, None, nv.EPI_SWIGLU)
+act = nv.gemm_h16(h, gu, None, None, nv.EPI_SWIGLU)
 print(f'gate/up GEMM + SwiGLU: rel {rel(act, act_ref):.2e}   [16-bit rounding alone: {rel(act_ref.half(), act_ref):.2e}]')
 
 # ---- down projection (K = 14336)
 act_in = act_ref.half().contiguous()
 d_ref = act_in.float() @ wd.float().t()
-dn = nv.gemm_f16(act_in, wd, None)
+dn = nv.gemm_h16(act_in, wd, None)
 print(f'down GEMM (K={I}): rel {rel(dn, d_ref):.2e}   [16-bit rounding alone: {rel(d_ref.half(), d_ref):.2e}]')
 
 # ---- the BERT / ESM building blocks at their shapes: GELU GEMM, d64 attention
 hb = torch.randn(4096, 768, generator=g, device=dev).half()
 w1, b1 = rnd(3072, 768), torch.randn(3072, generator=g, device=dev) * 0.02
 ref = F.gelu(hb.float() @ w1.float().t() + b1)
-got = nv.gemm_f16(hb, w1, b1, None, nv.EPI_BIAS_GELU)
+got = nv.gemm_h16(hb, w1, b1, None, nv.EPI_BIAS_GELU)
 print(f'BERT FFN-up GEMM + erf-GELU: rel {rel(got, ref):.2e}   [16-bit rounding alone: {rel(ref.half(), ref):.2e}]')
 b2, s2, h2 = 4, 512, 12
 qkv2 = (torch.randn(b2 * s2, 3 * h2 * 64, generator=g, device=dev) * 1.2).half()

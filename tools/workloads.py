@@ -101,6 +101,7 @@ _OUT_ROWS = {
     'bert': ('attention.output.dense.weight', 'output.dense.weight'),
     'esm': ('attention.output.dense.weight', 'output.dense.weight'),
     'mistral': ('self_attn.o_proj.weight', 'mlp.down_proj.weight'),
+    'modernbert': ('attn.Wo.weight', 'mlp.Wo.weight'),
 }
 
 
@@ -130,7 +131,8 @@ def add_outliers(state_dict: dict, family: str, seed: int = 0, n_massive: int = 
         if name.endswith(out_names):
             t[massive.to(t.device)] *= scale
         elif t.dim() == 1 and ('LayerNorm.weight' in name or 'layer_norm_after.weight' in name
-                               or name.endswith('layernorm.weight') or name == 'norm.weight'):
+                               or name.endswith('layernorm.weight') or name == 'norm.weight'
+                               or name.endswith('_norm.weight') or name.endswith('.norm.weight')):
             gain = torch.exp(torch.rand(t.shape, generator=g) * (hi - lo) + lo)
             gain[massive] = massive_gain
             gain[loud] = loud_gain
