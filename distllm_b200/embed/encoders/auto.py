@@ -9,7 +9,6 @@ architecture that is not built raises.
 
 from __future__ import annotations
 
-import warnings
 from typing import Literal
 from typing import Optional
 
@@ -45,7 +44,7 @@ class AutoEncoderConfig(BaseConfig):
     eval_mode: bool = True
     # Kept for compatibility: there is no tracing compiler in this path
     compile_model: bool = False
-    # Kept for compatibility: NF4 is not reproduced, weights run as fp16 on the tensor cores
+    # NF4 (bitsandbytes) weight quantisation, emulated at load time: the GEMMs run on dequant(quant(W))
     quantization: bool = True
 
 
@@ -64,12 +63,6 @@ class AutoEncoder:
                 f'(built: {_SUPPORTED_MODEL_TYPES}); there is no eager fallback.',
             )
         _NATIVE_BY_MODEL_TYPE[hf_config.model_type].validate(hf_config)   # before any weight is loaded
-        if config.quantization:
-            warnings.warn(
-                'quantization=True (bitsandbytes NF4) is not reproduced by the native encoder; '
-                'running fp16 tensor-core weights instead.',
-                stacklevel=2,
-            )
         model = AutoModel.from_pretrained(config.pretrained_model_name_or_path)
         tokenizer = AutoTokenizer.from_pretrained(
             config.tokenizer_name or config.pretrained_model_name_or_path,
@@ -78,8 +71,17 @@ class AutoEncoder:
         tokenizer.model_max_length = hf_config.max_position_embeddings
 
         self.config = config
-        self._native = _NATIVE_BY_MODEL_TYPE[hf_config.model_type](hf_config, model.state_dict())
-        del model
+        state_dict = model.state_dict()
+        if config.quantization:
+            # the reference's default (auto.py:44-56): every nn.Linear weight goes through 4-bit NormalFloat with
+            # double quantisation and is dequantised in front of each matmul -- what the GEMMs see is
+            # dequant(quant(W)).  That tensor is computed once here (embed/encoders/nf4.py restates bitsandbytes'
+            # published algorithm; the 4-bit STORAGE is not reproduced, the arithmetic is).
+            from distllm_b200.embed.encoders.nf4 import quantize_state_dict_nf4
+
+            state_dict = quantize_state_dict_nf4(state_dict, device='cuda' if torch.cuda.is_available() else None)
+        self._native = _NATIVE_BY_MODEL_TYPE[hf_config.model_type](hf_config, state_dict)
+        del model, state_dict
         self._tokenizer = tokenizer
         self._dtype = torch.float16 if config.half_precision else torch.float32
 

@@ -259,3 +259,32 @@ def test_embedding_worker_modernbert_checkpoint_dir_matches_reference(tmp_path, 
     cos = cosine_rows(emb[live], ref[live])
     assert cos.min() > 1 - COS_TOL, cos
     registry.clear()
+
+
+def test_auto_encoder_quantization_true_runs_nf4_weights(bert_ckpt):
+    """`quantization=True` (the reference's YAML default, auto.py:31,44-56): the native GEMMs run on
+    dequant(NF4(W)).  Checked against the oracle forward on the SAME round-tripped weights (cosine) and against
+    the unquantised model (must differ: NF4 changes every Linear weight by ~9 %)."""
+    import torch
+    from transformers import BertConfig
+
+    from distllm_b200.embed import get_encoder
+    from distllm_b200.embed.encoders.nf4 import quantize_state_dict_nf4
+    from distllm_b200.embed.encoders.weights import random_bert_state_dict
+    from oracle import bert as obert
+    from oracle.make_golden import TINY
+    from oracle.make_golden import TINY_SEED
+
+    root, texts = bert_ckpt
+    enc_q = get_encoder({'name': 'auto', 'pretrained_model_name_or_path': str(root / 'ckpt'), 'quantization': True})
+    batch = enc_q.tokenizer(texts[:4], padding=True, truncation=True, return_tensors='pt')
+    got = enc_q.encode(batch.to(enc_q.device)).cpu().numpy()
+    cfg = BertConfig(**TINY)
+    sd = random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
+    ref_q = obert.bert_forward(quantize_state_dict_nf4(sd), cfg, batch['input_ids'], batch['attention_mask'],
+                               batch['token_type_ids']).numpy()
+    ref_f = obert.bert_forward(sd, cfg, batch['input_ids'], batch['attention_mask'], batch['token_type_ids']).numpy()
+    valid = batch['attention_mask'].bool().numpy()
+    assert cosine_rows(got[valid], ref_q[valid]).min() > 1 - COS_TOL
+    assert cosine_rows(got[valid], ref_f[valid]).min() < 1 - 1e-3     # quantisation is visible
+    enc_q.native.close()

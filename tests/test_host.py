@@ -619,3 +619,41 @@ def test_exact_index_config_accepts_the_reference_fields(tmp_path):
         ExactIndexConfig(search_algorithm='hnsw')      # the approximate branch is not built
     with pytest.raises(Exception):
         ExactIndexConfig(precision='uint8')            # the reference itself only accepts float32 / ubinary
+
+
+def test_nf4_roundtrip_structure():
+    import torch
+
+    """embed/encoders/nf4.py (restatement of bitsandbytes' NF4 + double quantisation, reference auto.py:44-56):
+    every dequantised weight is (one of the 16 NF4 code values) x (its block's scale); errors stay within the
+    spacing of the code; only nn.Linear weights of the blocks are touched."""
+    from distllm_b200.embed.encoders.nf4 import NF4_CODE
+    from distllm_b200.embed.encoders.nf4 import dynamic_map_8bit
+    from distllm_b200.embed.encoders.nf4 import nf4_roundtrip
+    from distllm_b200.embed.encoders.nf4 import quantize_state_dict_nf4
+
+    code8 = dynamic_map_8bit()
+    assert len(code8) == 256 and code8[-1] == 1.0 and (code8 == 0).sum() == 1 and bool((code8[1:] > code8[:-1]).all())
+    assert len(NF4_CODE) == 16 and NF4_CODE[0] == -1.0 and NF4_CODE[7] == 0.0 and NF4_CODE[-1] == 1.0
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(96, 200, generator=g) * 0.02
+    r = nf4_roundtrip(w, double_quant=False)
+    blocks_w, blocks_r = w.flatten().view(-1, 64), r.flatten().view(-1, 64)
+    absmax = blocks_w.abs().amax(1, keepdim=True)
+    ratio = blocks_r / absmax
+    code = torch.tensor(NF4_CODE)
+    assert float((ratio[..., None] - code).abs().amin(-1).max()) < 1e-6      # code value x block absmax
+    # nearest code value: the error is at most half the widest gap of the code, relative to the block scale
+    widest = float((code[1:] - code[:-1]).max())
+    assert float(((blocks_r - blocks_w).abs() / absmax).max()) <= widest / 2 + 1e-6
+    # the block maximum itself is reproduced exactly (it maps to +-1)
+    assert torch.allclose(blocks_r.abs().amax(1), absmax[:, 0], rtol=1e-6)
+    # double quantisation perturbs the block scales by a fraction of a percent only
+    r2 = nf4_roundtrip(w)
+    assert 0 < float((r2 - r).norm() / r.norm()) < 0.02
+    assert 0.05 < float((r2 - w).norm() / w.norm()) < 0.15
+    sd = {'encoder.layer.0.attention.self.query.weight': w, 'encoder.layer.0.attention.self.query.bias': w[0],
+          'embeddings.word_embeddings.weight': w, 'encoder.layer.0.output.LayerNorm.weight': w[0]}
+    q = quantize_state_dict_nf4(sd)
+    assert torch.equal(q['encoder.layer.0.attention.self.query.weight'], r2)
+    assert all(q[k] is sd[k] for k in sd if 'query.weight' not in k)
