@@ -419,7 +419,7 @@ int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, in
   const int grid = items < sms ? (int)items : sms;
   const float scale_log2e = 0.08838834764831845f * 1.4426950408889634f;  // 128^-0.5 * log2(e)
   attention4_d128_causal_kernel<<<grid, AT4_THREADS, AT4_SMEM_BYTES, st>>>(
-      tq, tkv, sc.bias, sc.kv_chunks, tctx, B, S, attn_s_pad(S), heads, kv_heads, window, scale_log2e);
+      tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S, attn_s_pad(S), heads, kv_heads, window, scale_log2e);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }

@@ -29,10 +29,14 @@ from distllm_b200 import _native
 HALF_MAX = 65504.0
 
 
-def to_half(t: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """Checkpoint matrix (fp32 / 16-bit / fp16) -> contiguous fp16 device tensor, saturating at +-65504 (weights
-    never get near it; the clamp only keeps a broken checkpoint from turning into inf)."""
-    return t.detach().to(device=device, dtype=torch.float32).clamp_(-HALF_MAX, HALF_MAX).to(torch.float16).contiguous()
+def to_storage(t: torch.Tensor, device: torch.device, dtype: torch.dtype) -> torch.Tensor:
+    """Checkpoint matrix (fp32 / bf16 / fp16) -> contiguous device tensor of the library build's 16-bit storage
+    type.  float16 saturates at +-65504 (weights never get near it; the clamp only keeps a broken checkpoint
+    from turning into inf)."""
+    x = t.detach().to(device=device, dtype=torch.float32)
+    if dtype == torch.float16:
+        x = x.clamp(-HALF_MAX, HALF_MAX)
+    return x.to(dtype).contiguous()
 
 
 def bert_desc(hf_config) -> _native.ModelDesc:

@@ -421,7 +421,7 @@ def test_exact_index_ubinary_through_the_retriever_surface():
     assert kept.total_indices[0] == ref_i[0, :2].tolist()
 
 
-@pytest.mark.parametrize('m,i,k', [(300, 1152, 768), (1000, 2624, 1024)])
+@pytest.mark.parametrize('m,i,k', [(300, 1152, 768), (1000, 2688, 1024)])
 def test_gemm_geglu_epilogue(dev, m, i, k, h16):
     """ModernBERT's gated MLP: Wi rows = input | gate (transformers/models/modernbert/modeling_modernbert.py
     :88-91), interleaved in blocks of 64 for the epilogue: out = gelu(x Wi_in^T) * (x Wi_gate^T)."""

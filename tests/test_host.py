@@ -657,3 +657,52 @@ def test_nf4_roundtrip_structure():
     q = quantize_state_dict_nf4(sd)
     assert torch.equal(q['encoder.layer.0.attention.self.query.weight'], r2)
     assert all(q[k] is sd[k] for k in sd if 'query.weight' not in k)
+
+
+@pytest.mark.parametrize('dtype', ['float16', 'bfloat16'])
+def test_weight_lists_follow_the_abi_order_on_cpu(dtype):
+    """embed/encoders/weights.py: every family's state dict -> ABI-ordered tensor list (count = b2e_num_weights,
+    matrices in the build's 16-bit storage type, vectors fp32).  Runs on CPU tensors: no GPU needed."""
+    import ctypes as C
+
+    import torch
+    from transformers import BertConfig
+    from transformers import EsmConfig
+    from transformers import MistralConfig
+    from transformers import ModernBertConfig
+
+    from distllm_b200 import _native
+    from distllm_b200.embed.encoders import weights as W
+
+    dt = getattr(torch, dtype)
+    lib = _native.load(_native.storage_of(dt))
+    cases = [
+        (BertConfig(vocab_size=50, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                    max_position_embeddings=32), W.random_bert_state_dict, W.bert_desc, W.bert_weight_list),
+        (EsmConfig(vocab_size=33, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                   max_position_embeddings=40, position_embedding_type='rotary', token_dropout=True, mask_token_id=32,
+                   pad_token_id=1), W.random_esm_state_dict, W.esm_desc, W.esm_weight_list),
+        (MistralConfig(vocab_size=50, hidden_size=256, num_hidden_layers=2, num_attention_heads=2,
+                       num_key_value_heads=1, head_dim=128, intermediate_size=384, max_position_embeddings=64),
+         W.random_mistral_state_dict, W.mistral_desc, W.mistral_weight_list),
+        (ModernBertConfig(vocab_size=50, hidden_size=256, num_hidden_layers=4, num_attention_heads=4,
+                          intermediate_size=200, max_position_embeddings=64, local_attention=16, pad_token_id=0,
+                          bos_token_id=1, eos_token_id=2, cls_token_id=1, sep_token_id=2),
+         W.random_modernbert_state_dict, W.modernbert_desc, W.modernbert_weight_list),
+    ]
+    for cfg, make, desc_fn, list_fn in cases:
+        sd = make(cfg, seed=0, device='cpu')
+        desc = desc_fn(cfg)
+        tensors = list_fn(sd, cfg.num_hidden_layers, torch.device('cpu'), dt)
+        assert len(tensors) == lib.b2e_num_weights(C.byref(desc)), type(cfg).__name__
+        assert lib.b2e_check_model(C.byref(desc)) == 0, lib.b2e_last_error()
+        assert all(t.is_contiguous() for t in tensors)
+        assert {t.dtype for t in tensors if t.dim() == 2 and t.shape[0] != cfg.vocab_size
+                and t.shape[0] != getattr(cfg, 'max_position_embeddings', -1)
+                and t.shape[0] != getattr(cfg, 'type_vocab_size', -1)} == {dt}
+        assert all(t.dtype == torch.float32 for t in tensors if t.dim() == 1)
+    # ModernBERT: intermediate 200 is zero-padded to 256 (gelu(0) * 0 feeds zero columns of mlp.Wo)
+    mb = cases[3]
+    tensors = mb[3](mb[1](mb[0], seed=0, device='cpu'), 4, torch.device('cpu'), dt)
+    assert tensors[5 + 6].shape == (512, 256) and tensors[5 + 7].shape == (256, 256)
+    assert not tensors[5 + 7][:, 200:].any()

@@ -16,11 +16,11 @@ dev = torch.device('cuda:0')
 b, s, heads, h, i = (int(sys.argv[1]) if len(sys.argv) > 1 else 128), 512, 12, 768, 3072
 m = b * s
 torch.manual_seed(0)
-x = torch.randn(m, h, device=dev).half()
-w1 = (torch.randn(i, h, device=dev) * 0.02).half()
-w2 = (torch.randn(h, i, device=dev) * 0.02).half()
-wqkv = (torch.randn(3 * h, h, device=dev) * 0.02).half()
-wo = (torch.randn(h, h, device=dev) * 0.02).half()
+x = torch.randn(m, h, device=dev).to(torch.bfloat16)
+w1 = (torch.randn(i, h, device=dev) * 0.02).to(torch.bfloat16)
+w2 = (torch.randn(h, i, device=dev) * 0.02).to(torch.bfloat16)
+wqkv = (torch.randn(3 * h, h, device=dev) * 0.02).to(torch.bfloat16)
+wo = (torch.randn(h, h, device=dev) * 0.02).to(torch.bfloat16)
 mask = torch.ones(b, s, dtype=torch.int64, device=dev)
 for _ in range(2):
     qkv = nv.gemm_h16(x, wqkv, torch.zeros(3 * h, device=dev), None, nv.EPI_BIAS)
