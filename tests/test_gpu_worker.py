@@ -278,7 +278,8 @@ def test_auto_encoder_quantization_true_runs_nf4_weights(bert_ckpt):
     root, texts = bert_ckpt
     enc_q = get_encoder({'name': 'auto', 'pretrained_model_name_or_path': str(root / 'ckpt'), 'quantization': True})
     batch = enc_q.tokenizer(texts[:4], padding=True, truncation=True, return_tensors='pt')
-    got = enc_q.encode(batch.to(enc_q.device)).cpu().numpy()
+    on_device = enc_q.tokenizer(texts[:4], padding=True, truncation=True, return_tensors='pt').to(enc_q.device)
+    got = enc_q.encode(on_device).cpu().numpy()   # (BatchEncoding.to moves in place: `batch` stays on the host)
     cfg = BertConfig(**TINY)
     sd = random_bert_state_dict(cfg, seed=TINY_SEED, device='cpu')
     ref_q = obert.bert_forward(quantize_state_dict_nf4(sd), cfg, batch['input_ids'], batch['attention_mask'],
