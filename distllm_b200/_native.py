@@ -83,6 +83,7 @@ DEBUG_EXPORTS = (
     'b2e_debug_set_clock_buffer',
     'b2e_debug_set_layers',
     'b2e_debug_set_att3_variant',
+    'b2e_debug_set_packing',
 )
 
 

@@ -166,6 +166,7 @@ __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], flo
 struct At3Item {
   int b, h, pr, n, np;   // n: key chunks to visit; np: leading chunks whose 64 keys are all attended
   int j0;                // first key chunk (0 unless a sliding window narrows the range)
+  int row0, nq, len;     // first row of the sequence in the token arrays, its 128-row query tiles, its rows
 };
 // window > 0 (bidirectional sliding window, |q - k| <= window): the pair of query tiles [256 pr, 256 pr + 255]
 // only needs the key chunks that overlap [256 pr - window, 256 pr + 255 + window]; BOTH tiles walk that same
@@ -173,8 +174,10 @@ struct At3Item {
 // always visited: rows of padding tiles must still come out finite.
 __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
                                               const int* __restrict__ kv_chunks,
-                                              const int* __restrict__ plain_chunks, int n_items, int window) {
-  At3Item it{0, 0, 0, 0, 0, 0};
+                                              const int* __restrict__ plain_chunks, int n_items, int window,
+                                              int S, const int* __restrict__ seq_cu,
+                                              const int* __restrict__ seq_len) {
+  At3Item it{0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (item < n_items) {
     it.pr = item % npairs;
     const int bh = item / npairs;
@@ -182,7 +185,12 @@ __device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
     it.b = bh / heads;
     it.n = __ldg(kv_chunks + it.b);
     it.np = plain_chunks != nullptr ? __ldg(plain_chunks + it.b) : 0;
-    if (window > 0) {
+    // token layout (pack.cuh): rows [row0, row0 + len) hold the sequence; padded layout when seq_cu is null
+    it.row0 = seq_cu != nullptr ? __ldg(seq_cu + it.b) : it.b * S;
+    it.len = seq_len != nullptr ? __ldg(seq_len + it.b) : S;
+    it.nq = (it.len + 127) / 128;
+    if (2 * it.pr >= it.nq) it.n = 0;   // both query tiles lie beyond the sequence: nothing to do
+    if (window > 0 && it.n > 0) {
       int lo = (256 * it.pr - window) / AT3_KC;
       if (256 * it.pr - window < 0) lo = 0;
       int hi = (256 * it.pr + 255 + window) / AT3_KC;
@@ -215,8 +223,11 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
                       const float* __restrict__ bias,             // [B, S_pad]
                       const int* __restrict__ kv_chunks,          // [B]
                       const int* __restrict__ plain_chunks,       // [B] or nullptr
-                      const __grid_constant__ CUtensorMap tm_ctx, // [B, S, H] h16, box 64 x 128 x 1
-                      int B, int S, int S_pad, int heads, float scale_log2e, int window) {
+                      const __grid_constant__ CUtensorMap tm_ctx, // [T, H] h16, box 64 x 128 (full tiles)
+                      int B, int S, int S_pad, int heads, float scale_log2e, int window,
+                      const int* __restrict__ seq_cu,    // [B] first row of each sequence, or nullptr (= b*S)
+                      const int* __restrict__ seq_len,   // [B] rows of each sequence, or nullptr (= S)
+                      h16* __restrict__ ctx_out) {       // [T, H]: partial last tiles are stored row by row
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
@@ -289,15 +300,15 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
           const int pr = cur.pr, h = cur.h, b = cur.b;
-          const int row_base = b * S;
+          const int row_base = cur.row0;
           const int buf = it & 1;
           for (int slot = 0; slot < 2; ++slot) {
             const int t = 2 * pr + slot;
-            if (t >= nq) break;
+            if (t >= cur.nq) break;
             const int idx = buf * 2 + slot;
             const uint32_t bit = 1u << idx;
             // the buffer is free once the last Q K^T of its previous tile has completed
@@ -342,12 +353,12 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
+        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
+          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
           const int n = cur.n;
           const int buf = it & 1;
-          const bool active = 2 * cur.pr + slot < nq;
+          const bool active = 2 * cur.pr + slot < cur.nq;
           if (slot == 0) AT3_STAMP(2, 9000 + n);
           if (!active) {
             // this slot has no query tile in the item: it still owes the ring one arrival per chunk,
@@ -427,7 +438,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
-    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window);
+    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
     // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
     // is ordered (A before B), which merely de-phases the two warpgroups
@@ -437,17 +448,17 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
-      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window);
-      const int pr = cur.pr, h = cur.h, b = cur.b, n = cur.n;
+      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+      const int pr = cur.pr, h = cur.h, n = cur.n;
       const int t = 2 * pr + slot;
-      if (t >= nq && pingpong) {
+      if (t >= cur.nq && pingpong) {
         // no query tile for this slot in the item: keep the other warpgroup's turns coming
         for (int j = 0; j < ((pp_mode & 1) ? n : 1); ++j) {
           asm volatile("bar.sync %0, 256;" ::"r"(4 + slot) : "memory");
           asm volatile("bar.arrive %0, 256;" ::"r"(4 + (slot ^ 1)) : "memory");
         }
       }
-      if (t < nq) {
+      if (t < cur.nq) {
         constexpr bool kPlainCount = (V & 1) != 0;
         constexpr bool kPrefetch = (V & 2) != 0;
         constexpr int kPoly = (V >> 2) & 3;
@@ -616,11 +627,21 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         mbar_arrive(o_empty + 8u * slot);   // O's TMEM columns may be overwritten by the next tile
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
-        if (r == 0) {
-          // rows >= S of the last tile are clipped by the 3-D [B,S,H] tensor map
-          tma_store_3d(&tm_ctx, ostage_addr, h * AT3_D, t * 128, b);
-          tma_store_commit();
-          AT3_STAMP(slot, 902);
+        const int valid = cur.len - t * 128;   // rows of this tile that belong to the sequence
+        if (valid >= 128) {
+          if (r == 0) {
+            tma_store_2d(&tm_ctx, ostage_addr, h * AT3_D, cur.row0 + t * 128);
+            tma_store_commit();
+            AT3_STAMP(slot, 902);
+          }
+        } else if (r < valid) {
+          // last, partial tile of the sequence: the rows behind it belong to the NEXT sequence (packed layout)
+          // or do not exist -- every thread stores its own row (it staged that row itself: no hazard)
+          h16* dst = ctx_out + static_cast<size_t>(cur.row0 + t * 128 + r) * H + h * AT3_D;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(dst + u * 8) =
+                *reinterpret_cast<const uint4*>(ostage + r * 128 + ((u ^ (r & 7)) << 4));
         }
       }
       chunk_base += static_cast<uint32_t>(n);

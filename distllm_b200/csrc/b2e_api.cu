@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "mistral_ops.cuh"
+#include "pack.cuh"
 #include "rowops.cuh"
 #include "topk.cuh"
 
@@ -173,7 +174,7 @@ int ensure_smem_attr(Kern kern, int bytes) {
 template <int BN, int STAGES, int EPI>
 int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                     const float* bias, const h16* resid, int M, int N, int K, int sms,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int* m_dev = nullptr) {
   using Cfg = GemmCfg<BN, STAGES>;
   auto kern = gemm_h16_tcgen05_kernel<BN, STAGES, EPI>;
   {
@@ -200,10 +201,10 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, bias, resid, M, N, K));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, bias, resid, M, N, K, m_dev));
     return B2E_OK;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K, m_dev);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -211,23 +212,23 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
 template <int BN, int STAGES>
 int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                    const float* bias, const h16* resid, int M, int N, int K, int epi, int sms,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* m_dev = nullptr) {
   switch (epi) {
     case B2E_EPI_BIAS:
-      return launch_gemm_cfg<BN, STAGES, EPI_BIAS>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS>(ta, tb, tout, bias, resid, M, N, K, sms, st, m_dev);
     case B2E_EPI_BIAS_GELU:
-      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_GELU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+      return launch_gemm_cfg<BN, STAGES, EPI_BIAS_GELU>(ta, tb, tout, bias, resid, M, N, K, sms, st, m_dev);
     case B2E_EPI_BIAS_RESID:
       return launch_gemm_cfg<BN, STAGES, EPI_BIAS_RESID>(ta, tb, tout, bias, resid, M, N, K, sms,
                                                          st);
     case B2E_EPI_SWIGLU:
       if constexpr (BN == 256)
-        return launch_gemm_cfg<256, STAGES, EPI_SWIGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+        return launch_gemm_cfg<256, STAGES, EPI_SWIGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st, m_dev);
       else
         return fail(B2E_ERR_INVALID, "SwiGLU epilogue needs N %% 256 == 0");
     case B2E_EPI_GEGLU:
       if constexpr (BN == 256)
-        return launch_gemm_cfg<256, STAGES, EPI_GEGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st);
+        return launch_gemm_cfg<256, STAGES, EPI_GEGLU>(ta, tb, tout, bias, resid, M, N, K, sms, st, m_dev);
       else
         return fail(B2E_ERR_INVALID, "GeGLU epilogue needs N %% 256 == 0");
   }
@@ -257,7 +258,7 @@ int check_gemm_shape(int M, int N, int K) {
 template <int STAGES, int EPI>
 int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                      const float* bias, const h16* resid, int M, int N, int K, int sms,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int* m_dev = nullptr) {
   using Cfg = Gemm2Cfg<STAGES>;
   auto kern = gemm2_h16_pair_kernel<STAGES, EPI>;
   {
@@ -267,14 +268,16 @@ int launch_gemm2_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
   int grid = 2 * tiles;
   if (grid > (sms & ~1)) grid = sms & ~1;
-  kern<<<grid, G2_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K);
+  kern<<<grid, G2_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tout, bias, resid, M, N, K, m_dev);
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
 
 // A map: [M,K] box 128 rows; W map: [N,K] box gemm_bn_for(N) rows.
+// m_dev (nullable): device-resident row count <= M (packed token layout); M sizes the grid and the tensor maps.
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const float* bias,
-                const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st) {
+                const void* resid, int M, int N, int K, int epi, int sms, cudaStream_t st,
+                const int* m_dev = nullptr) {
   const h16* r = static_cast<const h16*>(resid);
   // output tiles leave through TMA stores: [M,N] row-major, box = 64 columns x 32 rows
   CUtensorMap tout;
@@ -285,16 +288,16 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const f
   if (N % 256 == 0 && gemm_use_pair()) {
     constexpr int PS = 5;   // 5 x 32 KiB stages + two staging tiles per epilogue warp
     switch (epi) {
-      case B2E_EPI_BIAS: return launch_gemm2_cfg<PS, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<PS, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<PS, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      case B2E_EPI_SWIGLU: return launch_gemm2_cfg<PS, EPI_SWIGLU>(ta, tb, tout, bias, r, M, N, K, sms, st);
-      case B2E_EPI_GEGLU: return launch_gemm2_cfg<PS, EPI_GEGLU>(ta, tb, tout, bias, r, M, N, K, sms, st);
+      case B2E_EPI_BIAS: return launch_gemm2_cfg<PS, EPI_BIAS>(ta, tb, tout, bias, r, M, N, K, sms, st, m_dev);
+      case B2E_EPI_BIAS_GELU: return launch_gemm2_cfg<PS, EPI_BIAS_GELU>(ta, tb, tout, bias, r, M, N, K, sms, st, m_dev);
+      case B2E_EPI_BIAS_RESID: return launch_gemm2_cfg<PS, EPI_BIAS_RESID>(ta, tb, tout, bias, r, M, N, K, sms, st, m_dev);
+      case B2E_EPI_SWIGLU: return launch_gemm2_cfg<PS, EPI_SWIGLU>(ta, tb, tout, bias, r, M, N, K, sms, st, m_dev);
+      case B2E_EPI_GEGLU: return launch_gemm2_cfg<PS, EPI_GEGLU>(ta, tb, tout, bias, r, M, N, K, sms, st, m_dev);
     }
     return fail(B2E_ERR_INVALID, "unknown epilogue %d", epi);
   }
-  if (N % 256 == 0) return launch_gemm_bn<256, 4>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
-  return launch_gemm_bn<128, 6>(ta, tb, tout, bias, r, M, N, K, epi, sms, st);
+  if (N % 256 == 0) return launch_gemm_bn<256, 4>(ta, tb, tout, bias, r, M, N, K, epi, sms, st, m_dev);
+  return launch_gemm_bn<128, 6>(ta, tb, tout, bias, r, M, N, K, epi, sms, st, m_dev);
 }
 
 // Per-forward attention inputs derived from the mask (attention3.cuh): additive key bias rows and
@@ -363,15 +366,24 @@ inline int att3_variant() {
   return g_att3_variant;
 }
 
+// Token layout of a forward pass (pack.cuh): null pointers = the padded [B, S] layout.
+struct SeqLayout {
+  const int* cu = nullptr;       // [B + 1]
+  const int* len = nullptr;      // [B]
+  const int* t_real = nullptr;   // [2]: rows in use, packed flag
+  const int* tok_src = nullptr;  // [B * S]
+};
+
 template <int V>
 int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
-                       const CUtensorMap& tctx, int B, int S, int heads, int grid, float scale_log2e,
-                       cudaStream_t st, int window = 0) {
+                       const CUtensorMap& tctx, void* ctx, const SeqLayout& lay, int B, int S, int heads,
+                       int grid, float scale_log2e, cudaStream_t st, int window = 0) {
   auto kern = attention3_d64_kernel<V>;
   const int arc = ensure_smem_attr(kern, AT3_SMEM_BYTES);
   if (arc) return arc;
   kern<<<grid, AT3_THREADS, AT3_SMEM_BYTES, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
-                                                  attn_s_pad(S), heads, scale_log2e, window);
+                                                  attn_s_pad(S), heads, scale_log2e, window, lay.cu, lay.len,
+                                                  static_cast<h16*>(ctx));
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -379,23 +391,25 @@ int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const Attn
 // tq: [T,3H] box 64x128, tkv: [T,3H] box 64x64.  `sc` must have been prepared for this batch's mask.
 // window > 0: bidirectional sliding window |q - k| <= window (ModernBERT's local layers), else full attention.
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc, void* ctx,
-                     int B, int S, int heads, int sms, cudaStream_t st, int window = 0) {
+                     int B, int S, int heads, int sms, cudaStream_t st, int window = 0,
+                     const SeqLayout& lay = SeqLayout()) {
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
   const int grid = items < sms ? (int)items : sms;
-  CUtensorMap tctx;  // [B, S, H]: the output store clips rows >= S per sequence
+  CUtensorMap tctx;  // [B*S, H]: full 128-row tiles leave through TMA, a sequence's partial last tile row by row
   int rc;
-  if ((rc = make_tmap_h16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT3_D, 128))) return rc;
-  if (window > 0) return launch_attention_v<17>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st, window);
+  if ((rc = make_tmap_h16(&tctx, ctx, (uint64_t)B * S, (uint64_t)heads * AT3_D, 128))) return rc;
+  if (window > 0)
+    return launch_attention_v<17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
   switch (att3_variant()) {
-    case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 2: return launch_attention_v<2>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 3: return launch_attention_v<3>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 7: return launch_attention_v<7>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 11: return launch_attention_v<11>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
-    case 5: return launch_attention_v<5>(tq, tkv, sc, tctx, B, S, heads, grid, scale_log2e, st);
+    case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 2: return launch_attention_v<2>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 3: return launch_attention_v<3>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 7: return launch_attention_v<7>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 11: return launch_attention_v<11>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 5: return launch_attention_v<5>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
   }
   return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11)", att3_variant());
 }
@@ -568,6 +582,10 @@ struct B2EEncoder {
   h16 *hidden = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr;
   PoolScratch pool;
   AttnScratch attn;
+  // padding-free token layout of the pooled forward pass (pack.cuh)
+  int *pk_len_raw = nullptr, *pk_ok = nullptr, *pk_len = nullptr, *pk_cu = nullptr, *pk_treal = nullptr,
+      *pk_src = nullptr;
+  size_t pk_cap_b = 0, pk_cap_t = 0;
   // weight tensor maps, one per layer
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w1, tm_w2;
   // host-loop staging
@@ -649,10 +667,19 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     CUDA_TRY(cudaMalloc(&e->ctx, tokens * (size_t)e->ctx_cols() * 2));
     CUDA_TRY(cudaMalloc(&e->tmp, tokens * H * 2));
     CUDA_TRY(cudaMalloc(&e->ffn, tokens * I * 2));
+    // zeroed once: with the packed token layout rows behind the last attended token are never written by a
+    // forward pass but ARE read (partial GEMM tiles, the last key chunk of the last sequence) -- they must
+    // hold finite values, never whatever the allocator left there
+    CUDA_TRY(cudaMemset(e->hidden, 0, tokens * H * 2));
+    CUDA_TRY(cudaMemset(e->qkv, 0, tokens * (size_t)e->qkv_cols() * 2));
+    CUDA_TRY(cudaMemset(e->ctx, 0, tokens * (size_t)e->ctx_cols() * 2));
+    CUDA_TRY(cudaMemset(e->tmp, 0, tokens * H * 2));
+    CUDA_TRY(cudaMemset(e->ffn, 0, tokens * I * 2));
     if (e->has_xres()) {
       cudaFree(e->xres);
       e->xres = nullptr;
       CUDA_TRY(cudaMalloc(&e->xres, tokens * H * 4));
+      CUDA_TRY(cudaMemset(e->xres, 0, tokens * H * 4));
     }
     e->cap_tokens = tokens;
   }
@@ -664,7 +691,53 @@ int ensure_workspace(B2EEncoder* e, int B, int S) {
     CUDA_TRY(cudaMalloc(&e->tok_scale, sizeof(float) * B));
     e->cap_scale = B;
   }
+  if ((size_t)B > e->pk_cap_b) {
+    ++e->ws_gen;
+    cudaFree(e->pk_len_raw); cudaFree(e->pk_ok); cudaFree(e->pk_len); cudaFree(e->pk_cu); cudaFree(e->pk_treal);
+    e->pk_len_raw = e->pk_ok = e->pk_len = e->pk_cu = e->pk_treal = nullptr;
+    e->pk_cap_b = 0;
+    CUDA_TRY(cudaMalloc(&e->pk_len_raw, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&e->pk_ok, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&e->pk_len, sizeof(int) * B));
+    CUDA_TRY(cudaMalloc(&e->pk_cu, sizeof(int) * (B + 1)));
+    CUDA_TRY(cudaMalloc(&e->pk_treal, sizeof(int) * 2));
+    e->pk_cap_b = B;
+  }
+  if (tokens > e->pk_cap_t) {
+    ++e->ws_gen;
+    cudaFree(e->pk_src);
+    e->pk_src = nullptr;
+    e->pk_cap_t = 0;
+    CUDA_TRY(cudaMalloc(&e->pk_src, sizeof(int) * tokens));
+    e->pk_cap_t = tokens;
+  }
   return e->pool.ensure(B, S, (size_t)B * pool_nsplit(S) * e->desc.hidden);
+}
+
+// B2E_PACKED=0 keeps the padded [B, S] layout on every path (A/B measurements, debugging)
+int g_packing = -1;   // -1: not decided yet (B2E_PACKED), 0 / 1: b2e_debug_set_packing or the environment
+inline bool packing_enabled() {
+  if (g_packing < 0) {
+    const char* e = getenv("B2E_PACKED");
+    g_packing = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_packing == 1;
+}
+
+// Token layout of this forward pass (pack.cuh), decided and built ON DEVICE from the mask: attended tokens
+// back to back when every mask row is a non-empty prefix and `enable`, else the identity ([B, S]) layout
+// expressed through the same descriptors.
+int pack_prepare(B2EEncoder* e, const int64_t* mask, int B, int S, bool enable, cudaStream_t st, SeqLayout* lay) {
+  pack_lengths_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, e->pk_len_raw, e->pk_ok, B, S);
+  pack_scan_kernel<<<1, 256, 0, st>>>(e->pk_len_raw, e->pk_ok, e->pk_len, e->pk_cu, e->pk_treal, B, S,
+                                      enable ? 1 : 0);
+  pack_fill_kernel<<<dim3((S + 255) / 256, B), 256, 0, st>>>(e->pk_len, e->pk_cu, e->pk_src, B, S);
+  CUDA_TRY(cudaGetLastError());
+  lay->cu = e->pk_cu;
+  lay->len = e->pk_len;
+  lay->t_real = e->pk_treal;
+  lay->tok_src = e->pk_src;
+  return B2E_OK;
 }
 
 int validate_batch(const B2EEncoder* e, int B, int S) {
@@ -682,13 +755,14 @@ int validate_batch(const B2EEncoder* e, int B, int S) {
 // of the final layer split as e->tmp (FFN-down output + bias) and e->hidden (the residual it still has
 // to be added to); every earlier LayerNorm output lives in e->hidden.
 int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const int64_t* types,
-                   int B, int S, cudaStream_t st) {
+                   int B, int S, cudaStream_t st,
+                   const SeqLayout& lay = SeqLayout()) {
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, I = d.intermediate;
   int rc;
   DISPATCH_NV(H, (embed_layernorm_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      ids, types, e->word(), e->pos(), e->type(), e->emb_g(), e->emb_b(), e->hidden,
-                     M, S, d.eps)));
+                     M, S, d.eps, lay.t_real, lay.tok_src)));
   CUDA_TRY(cudaGetLastError());
 
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
@@ -701,27 +775,27 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
 
   for (int l = 0; l < d.num_layers; ++l) {
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->L(l, 1), nullptr, M,
-                          3 * H, H, B2E_EPI_BIAS, e->sms, st)))
+                          3 * H, H, B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
-    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st)))
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st, 0, lay)))
       return rc;
     // the residual add rides on the LayerNorm's coalesced reads, not on the GEMM epilogue
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->L(l, 3), nullptr, M, H, H,
-                          B2E_EPI_BIAS, e->sms, st)))
+                          B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->tmp, e->hidden, (const float*)e->L(l, 4), (const float*)e->L(l, 5),
-                       e->hidden, M, d.eps)));
+                       e->hidden, M, d.eps, lay.t_real)));
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->L(l, 7), nullptr, M, I,
-                          H, B2E_EPI_BIAS_GELU, e->sms, st)))
+                          H, B2E_EPI_BIAS_GELU, e->sms, st, lay.t_real)))
       return rc;
     if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->L(l, 9), nullptr, M, H, I,
-                          B2E_EPI_BIAS, e->sms, st)))
+                          B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     if (l + 1 < d.num_layers) {
       DISPATCH_NV(H, (layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->tmp, e->hidden, (const float*)e->L(l, 10), (const float*)e->L(l, 11),
-                         e->hidden, M, d.eps)));
+                         e->hidden, M, d.eps, lay.t_real)));
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -734,14 +808,15 @@ int run_bert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, const
 // and emits the next GEMM's h16 input.  Leaves xres (before the last FFN output is added) and e->tmp
 // (that FFN-down output): the caller applies emb_layer_norm_after to xres + tmp.
 int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
-                  cudaStream_t st) {
+                  cudaStream_t st, const SeqLayout& lay = SeqLayout()) {
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
   const int mask_token = d.reserved - 1;  // reserved = mask_token_id + 1, 0 = token dropout off
   int rc;
   esm_token_scale_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, mask, e->tok_scale, B, S, mask_token);
   DISPATCH_NV(H, (esm_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                     ids, mask, (const float*)e->w[0], e->tok_scale, e->xres, M, S, mask_token)));
+                     ids, mask, (const float*)e->w[0], e->tok_scale, e->xres, M, S, mask_token, lay.t_real,
+                     lay.tok_src)));
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
@@ -753,32 +828,32 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
 
   DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      e->xres, nullptr, (const float*)e->E(0, 0), (const float*)e->E(0, 1), e->hidden,
-                     M, d.eps)));
+                     M, d.eps, lay.t_real)));
   const long long rope_work = (long long)M * d.heads * 2;
   for (int l = 0; l < L; ++l) {
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->E(l, 3), nullptr, M,
-                          3 * H, H, B2E_EPI_BIAS, e->sms, st)))
+                          3 * H, H, B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
-                                                                    M, S, d.heads);
-    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st)))
+                                                                    M, S, d.heads, lay.t_real, lay.tok_src);
+    if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st, 0, lay)))
       return rc;
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->E(l, 5), nullptr, M, H, H,
-                          B2E_EPI_BIAS, e->sms, st)))
+                          B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->xres, e->tmp, (const float*)e->E(l, 6), (const float*)e->E(l, 7), e->hidden,
-                       M, d.eps)));
+                       M, d.eps, lay.t_real)));
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, (const float*)e->E(l, 9), nullptr, M, I, H,
-                          B2E_EPI_BIAS_GELU, e->sms, st)))
+                          B2E_EPI_BIAS_GELU, e->sms, st, lay.t_real)))
       return rc;
     if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, (const float*)e->E(l, 11), nullptr, M, H, I,
-                          B2E_EPI_BIAS, e->sms, st)))
+                          B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     if (l + 1 < L) {
       DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->E(l + 1, 0), (const float*)e->E(l + 1, 1),
-                         e->hidden, M, d.eps)));
+                         e->hidden, M, d.eps, lay.t_real)));
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -844,13 +919,13 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
 // :424-490 (model).  Leaves xres (before the last MLP output is added) and e->tmp (that output): the caller
 // applies final_norm to xres + tmp.
 int run_modernbert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
-                         cudaStream_t st) {
+                         cudaStream_t st, const SeqLayout& lay = SeqLayout()) {
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
   int rc;
   DISPATCH_NV(H, (modernbert_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      ids, (const float*)e->w[0], (const float*)e->w[1], (const float*)e->w[2], e->xres,
-                     e->hidden, M, d.eps)));
+                     e->hidden, M, d.eps, lay.t_real)));
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
@@ -865,26 +940,27 @@ int run_modernbert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask,
     if (l > 0) {
       DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                          e->xres, e->tmp, (const float*)e->Mb(l, 0), (const float*)e->Mb(l, 1), e->hidden, M,
-                         d.eps)));
+                         d.eps, lay.t_real)));
     }
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, 3 * H, H, B2E_EPI_BIAS,
-                          e->sms, st)))
+                          e->sms, st, lay.t_real)))
       return rc;
     rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(
-        e->qkv, global ? e->rope_cos : e->rope_cos2, global ? e->rope_sin : e->rope_sin2, M, S, d.heads);
+        e->qkv, global ? e->rope_cos : e->rope_cos2, global ? e->rope_sin : e->rope_sin2, M, S, d.heads,
+        lay.t_real, lay.tok_src);
     if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st,
-                               global ? 0 : d.sliding_window)))
+                               global ? 0 : d.sliding_window, lay)))
       return rc;
-    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, H, B2E_EPI_BIAS, e->sms, st)))
+    if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, H, B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
     DISPATCH_NV(H, (add_layernorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                        e->xres, e->tmp, (const float*)e->Mb(l, 4), (const float*)e->Mb(l, 5), e->hidden, M,
-                       d.eps)));
+                       d.eps, lay.t_real)));
     // Wi with its input / gate halves interleaved: gelu(input) * gate in the epilogue -> [M, I]
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, nullptr, nullptr, M, 2 * I, H, B2E_EPI_GEGLU,
-                          e->sms, st)))
+                          e->sms, st, lay.t_real)))
       return rc;
-    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, nullptr, nullptr, M, H, I, B2E_EPI_BIAS, e->sms, st)))
+    if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, nullptr, nullptr, M, H, I, B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
   }
   CUDA_TRY(cudaGetLastError());
@@ -911,6 +987,12 @@ int b2e_debug_set_att3_clock(void* device_buffer) {
 
 int b2e_debug_set_att3_flags(int flags) {
   CUDA_TRY(cudaMemcpyToSymbol(g_att3_flags, &flags, sizeof(flags)));
+  return B2E_OK;
+}
+
+// 0: every forward pass keeps the padded [B, S] token layout; 1: pooled passes pack attended tokens (default)
+int b2e_debug_set_packing(int on) {
+  g_packing = on ? 1 : 0;
   return B2E_OK;
 }
 
@@ -1128,6 +1210,8 @@ void b2e_encoder_destroy(B2EEncoder* e) {
   cudaFree(e->stage_in); cudaFree(e->stage_out);
   cudaFree(e->xres); cudaFree(e->tok_scale); cudaFree(e->rope_cos); cudaFree(e->rope_sin);
   cudaFree(e->rope_cos2); cudaFree(e->rope_sin2);
+  cudaFree(e->pk_len_raw); cudaFree(e->pk_ok); cudaFree(e->pk_len); cudaFree(e->pk_cu); cudaFree(e->pk_treal);
+  cudaFree(e->pk_src);
   e->drop_graphs();
   e->pool.release();
   e->attn.release();
@@ -1233,9 +1317,14 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
+  // Pooled paths of the head_dim-64 families run on the padding-free token layout (pack.cuh): only attended
+  // tokens go through the GEMMs, norms and attention query tiles; nothing here can observe a padded position.
+  SeqLayout lay;
+  if ((rc = pack_prepare(e, mask, B, S, packing_enabled(), st, &lay))) return rc;
   if (d.arch == B2E_ARCH_ESM2 || d.arch == B2E_ARCH_MODERNBERT) {
     const bool mb = d.arch == B2E_ARCH_MODERNBERT;
-    if ((rc = mb ? run_modernbert_trunk(e, ids, mask, B, S, st) : run_esm_trunk(e, ids, mask, B, S, st))) return rc;
+    if ((rc = mb ? run_modernbert_trunk(e, ids, mask, B, S, st, lay) : run_esm_trunk(e, ids, mask, B, S, st, lay)))
+      return rc;
     const float* fg = (const float*)e->w[mb ? 3 : 1];
     const float* fb = (const float*)e->w[mb ? 4 : 2];
     if (pool_kind == B2E_POOL_LAST_TOKEN) {
@@ -1243,7 +1332,7 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
       seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
       last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
       DISPATCH_NV(H, (addnorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, fg, fb, ps.idx, out, B, S, d.eps)));
+                         e->xres, e->tmp, fg, fb, ps.idx, out, B, S, d.eps, lay.cu)));
       if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
       CUDA_TRY(cudaGetLastError());
       return B2E_OK;
@@ -1254,18 +1343,18 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     const int rows_per = (S + nsplit - 1) / nsplit;
     dim3 grid(B, nsplit);
     DISPATCH_NV(H, (addnorm_pool_kernel<NV, false><<<grid, ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, fg, fb, ps.w, ps.part, S, rows_per, d.eps)));
+                       e->xres, e->tmp, fg, fb, ps.w, ps.part, S, rows_per, d.eps, lay.cu)));
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
-  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st))) return rc;
+  if ((rc = run_bert_trunk(e, ids, mask, types, B, S, st, lay))) return rc;
   const float* g = (const float*)e->L(l, 10);
   const float* bt = (const float*)e->L(l, 11);
   if (pool_kind == B2E_POOL_LAST_TOKEN) {
     seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
     last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
     DISPATCH_NV(H, (layernorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
-                       e->tmp, e->hidden, ps.idx, g, bt, out, B, S, d.eps)));
+                       e->tmp, e->hidden, ps.idx, g, bt, out, B, S, d.eps, lay.cu)));
     if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
     CUDA_TRY(cudaGetLastError());
     return B2E_OK;
@@ -1277,7 +1366,7 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
   const int rows_per = (S + nsplit - 1) / nsplit;
   dim3 grid(B, nsplit);
   DISPATCH_NV(H, (layernorm_pool_kernel<NV><<<grid, ROW_THREADS, 0, st>>>(
-                     e->tmp, e->hidden, g, bt, ps.w, ps.part, S, rows_per, d.eps)));
+                     e->tmp, e->hidden, g, bt, ps.w, ps.part, S, rows_per, d.eps, lay.cu)));
   CUDA_TRY(cudaGetLastError());
   return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
 }

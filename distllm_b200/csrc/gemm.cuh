@@ -218,7 +218,8 @@ gemm_h16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K] bo
                          const __grid_constant__ CUtensorMap tm_b,    // [N,K] box 64 x BN
                          const __grid_constant__ CUtensorMap tm_out,  // [M,N] box 64 x 32
                          const float* __restrict__ bias, const h16* __restrict__ resid, int M,
-                         int N, int K) {
+                         int N, int K, const int* __restrict__ m_dev) {
+  if (m_dev != nullptr) M = __ldg(m_dev);   // device-resident row count (packed token layout)
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);

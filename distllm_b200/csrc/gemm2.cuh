@@ -51,7 +51,10 @@ gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box
                        const __grid_constant__ CUtensorMap tm_b,    // [N,K], box 64 x 128
                        const __grid_constant__ CUtensorMap tm_out,  // [M,N] (SwiGLU: [M,N/2]), box 64 x 32
                        const float* __restrict__ bias, const h16* __restrict__ resid, int M, int N,
-                       int K) {
+                       int K, const int* __restrict__ m_dev) {
+  // m_dev (nullable): the row count lives on the device (packed token layout, pack.cuh); M is then only the
+  // upper bound the grid and the tensor maps were sized for
+  if (m_dev != nullptr) M = __ldg(m_dev);
   using Cfg = Gemm2Cfg<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);

@@ -109,12 +109,13 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 addnorm_gather_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                      const int* __restrict__ idx, float* __restrict__ out, int B, int S, float eps) {
+                      const int* __restrict__ idx, float* __restrict__ out, int B, int S, float eps,
+                      const int* __restrict__ cu = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (b >= B) return;
-  const size_t row = static_cast<size_t>(b) * S + idx[b];
+  const size_t row = (cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * S) + idx[b];
   float x[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -138,7 +139,8 @@ template <int NV, bool RMS>
 __global__ void __launch_bounds__(ROW_THREADS)
 addnorm_pool_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ w, float* __restrict__ part, int S, int rows_per, float eps) {
+                    const float* __restrict__ w, float* __restrict__ part, int S, int rows_per, float eps,
+                    const int* __restrict__ cu = nullptr) {
   constexpr int H = NV * 256;
   __shared__ float red[H];
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
@@ -153,7 +155,7 @@ addnorm_pool_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
     const float wv = w[static_cast<size_t>(b) * S + s];
     if (wv == 0.0f) continue;  // warp-uniform
     float x[NV][8];
-    const size_t row = static_cast<size_t>(b) * S + s;
+    const size_t row = (cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * S) + s;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const size_t off = row * H + v * 256 + lane * 8;

@@ -98,14 +98,17 @@ embed_layernorm_kernel(const int64_t* __restrict__ ids, const int64_t* __restric
                        const float* __restrict__ word, const float* __restrict__ pos,
                        const float* __restrict__ type, const float* __restrict__ gamma,
                        const float* __restrict__ beta, h16* __restrict__ out, int rows, int S,
-                       float eps) {
+                       float eps, const int* __restrict__ n_dev, const int* __restrict__ tok_src) {
+  // n_dev / tok_src (nullable, pack.cuh): rows in use and the [B,S] position each packed row comes from
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
-  const int64_t id = ids[row];
-  const int64_t tt = type_ids ? type_ids[row] : 0;
-  const int p = row % S;
+  const int src = tok_src != nullptr ? __ldg(tok_src + row) : row;
+  const int64_t id = ids[src];
+  const int64_t tt = type_ids ? type_ids[src] : 0;
+  const int p = src % S;
   float x[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -139,10 +142,13 @@ __device__ __forceinline__ void load8_residual(const h16* in, const h16* resid, 
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_kernel(const h16* __restrict__ in, const h16* resid, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, OutT* out, int rows, float eps) {
+                 const float* __restrict__ beta, OutT* out, int rows, float eps,
+                 const int* __restrict__ n_dev = nullptr, const int* __restrict__ out_row = nullptr) {
+  // n_dev: device-resident row count; out_row: where each row goes in `out` (scatter back to [B,S])
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
   float x[NV][8];
 #pragma unroll
@@ -151,8 +157,9 @@ layernorm_kernel(const h16* __restrict__ in, const h16* resid, const float* __re
     load8_residual(in + off, resid ? resid + off : nullptr, x[v]);
   }
   warp_layernorm<NV>(x, gamma, beta, lane, eps);
+  const size_t orow = out_row != nullptr ? static_cast<size_t>(__ldg(out_row + row)) : static_cast<size_t>(row);
 #pragma unroll
-  for (int v = 0; v < NV; ++v) store8(out + static_cast<size_t>(row) * H + v * 256 + lane * 8, x[v]);
+  for (int v = 0; v < NV; ++v) store8(out + orow * H + v * 256 + lane * 8, x[v]);
 }
 
 // LayerNorm of selected rows only: out[b] = LN(in[b*S + idx[b]])  (last-token pooling).
@@ -161,12 +168,12 @@ __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_gather_kernel(const h16* __restrict__ in, const h16* __restrict__ resid,
                         const int* __restrict__ idx, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float* __restrict__ out, int B, int S,
-                        float eps) {
+                        float eps, const int* __restrict__ cu = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (b >= B) return;
-  const size_t row = static_cast<size_t>(b) * S + idx[b];
+  const size_t row = (cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * S) + idx[b];
   float x[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -281,7 +288,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_pool_kernel(const h16* __restrict__ in, const h16* __restrict__ resid,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ w,
-                      float* __restrict__ part, int S, int rows_per, float eps) {
+                      float* __restrict__ part, int S, int rows_per, float eps,
+                      const int* __restrict__ cu = nullptr) {
   constexpr int H = NV * 256;
   __shared__ float red[H];
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
@@ -296,7 +304,8 @@ layernorm_pool_kernel(const h16* __restrict__ in, const h16* __restrict__ resid,
     const float wv = w[static_cast<size_t>(b) * S + s];
     if (wv == 0.0f) continue;  // warp-uniform
     float x[NV][8];
-    const size_t row = static_cast<size_t>(b) * S + s;
+    // (a row with a non-zero weight is an attended row: it exists in the packed layout too)
+    const size_t row = (cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * S) + s;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const size_t off = row * H + v * 256 + lane * 8;
@@ -473,13 +482,16 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 esm_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
                  const float* __restrict__ word, const float* __restrict__ scale,
-                 float* __restrict__ xres, int rows, int S, int mask_token) {
+                 float* __restrict__ xres, int rows, int S, int mask_token,
+                 const int* __restrict__ n_dev = nullptr, const int* __restrict__ tok_src = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
-  const int64_t id = ids[row];
-  float f = scale[row / S] * static_cast<float>(mask[row]);
+  const int src = tok_src != nullptr ? __ldg(tok_src + row) : row;
+  const int64_t id = ids[src];
+  float f = scale[src / S] * static_cast<float>(mask[src]);
   if (mask_token >= 0 && id == mask_token) f = 0.0f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -498,12 +510,14 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 modernbert_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                        float* __restrict__ xres, h16* __restrict__ hidden, int rows, float eps) {
+                        float* __restrict__ xres, h16* __restrict__ hidden, int rows, float eps,
+                        const int* __restrict__ n_dev = nullptr, const int* __restrict__ tok_src = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
-  const int64_t id = ids[row];
+  const int64_t id = ids[tok_src != nullptr ? __ldg(tok_src + row) : row];
   float x[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) load8(table + static_cast<size_t>(id) * H + v * 256 + lane * 8, x[v]);
@@ -523,10 +537,11 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
 add_layernorm_kernel(float* __restrict__ xres, const h16* __restrict__ add,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     OutT* __restrict__ out, int rows, float eps) {
+                     OutT* __restrict__ out, int rows, float eps, const int* __restrict__ n_dev = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
   float x[NV][8];
 #pragma unroll
@@ -563,16 +578,19 @@ __global__ void rope_table_kernel(float* __restrict__ cos_t, float* __restrict__
 //   out[i] = x[i] cos - x[i+32] sin ;  out[i+32] = x[i+32] cos + x[i] sin     (position = t % S)
 // One warp per (token, head pair of Q|K); lane = frequency index i.
 __global__ void rope_qk_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t,
-                               const float* __restrict__ sin_t, int T, int S, int heads) {
+                               const float* __restrict__ sin_t, int T, int S, int heads,
+                               const int* __restrict__ n_dev = nullptr,
+                               const int* __restrict__ tok_src = nullptr) {
   const int H = heads * 64;
   const int lane = threadIdx.x & 31;
   const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n_dev != nullptr) T = __ldg(n_dev);
   const long long n_work = static_cast<long long>(T) * heads * 2;  // q heads then k heads
   if (w >= n_work) return;
   const int t = static_cast<int>(w / (heads * 2));
   const int hk = static_cast<int>(w % (heads * 2));  // [0, heads): q head, [heads, 2*heads): k head
   h16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
-  const int pos = t % S;
+  const int pos = (tok_src != nullptr ? __ldg(tok_src + t) : t) % S;   // position inside its sequence
   const float c = cos_t[pos * 32 + lane], s = sin_t[pos * 32 + lane];
   const float x1 = from_h16(p[lane]), x2 = from_h16(p[lane + 32]);
   p[lane] = to_h16(x1 * c - x2 * s);

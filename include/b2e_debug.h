@@ -22,6 +22,10 @@ int b2e_debug_set_layers(struct B2EEncoder* enc, int n_layers);
 int b2e_debug_set_att3_clock(void* device_buffer);
 /* softmax scheduling experiments of the attention kernels (see attention3.cuh g_att3_flags) */
 int b2e_debug_set_att3_flags(int flags);
+/* 0: keep the padded [B, S] token layout on every path; 1 (default, also B2E_PACKED=1): pooled forward passes run
+ * on the attended tokens only (csrc/pack.cuh).  Drops the handle's cached CUDA graphs' validity: call it before
+ * b2e_embed_host, not between its batches. */
+int b2e_debug_set_packing(int on);
 /* which instantiated softmax variant of attention3_d64_kernel<V> the next launches use (also B2E_ATT3) */
 int b2e_debug_set_att3_variant(int variant);
 /* CTA-pair GEMM: bit 0 = skip the epilogue's math and stores (experiment) */

@@ -575,3 +575,56 @@ def test_modernbert_matches_reference_vectors(tiny_modernbert, modernbert_golden
             assert cos.min() > 1 - COS_TOL, (fused, cos)
     finally:
         native.close()
+
+
+# ---------------------------------------------------------------------------------- padding-free layout
+@pytest.mark.parametrize('family', ['bert', 'esm', 'modernbert'])
+def test_packed_token_layout_equals_padded(family, tiny_bert, tiny_esm, tiny_modernbert):
+    """Pooled forward passes run on the attended tokens only (csrc/pack.cuh).  Same batch, packing on vs off
+    (b2e_debug_set_packing): right-padded ragged batches must give the same embeddings (padded positions can
+    not influence a pooled row), batches with left padding / holes / empty rows fall back to the padded layout
+    by themselves."""
+    import ctypes
+
+    from distllm_b200.embed.encoders.native import NativeEsm2Encoder
+    from distllm_b200.embed.encoders.native import NativeModernBertEncoder
+
+    cfg, sd = {'bert': tiny_bert, 'esm': tiny_esm, 'modernbert': tiny_modernbert}[family]
+    cls = {'bert': NativeBertEncoder, 'esm': NativeEsm2Encoder, 'modernbert': NativeModernBertEncoder}[family]
+    enc = cls(cfg, sd)
+    lib = enc._lib
+    lib.b2e_debug_set_packing.argtypes = [ctypes.c_int]
+    g = torch.Generator().manual_seed(5)
+    s_max = min(cfg.max_position_embeddings, 300)
+    try:
+        for b, s, lens in [(7, 50, [50, 3, 17, 50, 1, 33, 2]), (5, s_max, [s_max, 129, 128, 64, 7]),
+                           (3, 40, [40, 40, 40])]:
+            lens = [min(n, s) for n in lens]
+            ids = torch.randint(4, min(cfg.vocab_size, 24) if family == 'esm' else cfg.vocab_size - 1, (b, s),
+                                generator=g)
+            mask = (torch.arange(s)[None] < torch.tensor(lens)[:, None]).long()
+            for kind in (nv.POOL_MEAN_REF, nv.POOL_MEAN_PER_ROW, nv.POOL_LAST_TOKEN):
+                lib.b2e_debug_set_packing(1)
+                packed = enc.encode_pooled(ids, mask, None, kind, True).clone()
+                lib.b2e_debug_set_packing(0)
+                padded = enc.encode_pooled(ids, mask, None, kind, True).clone()
+                assert torch.isfinite(packed).all()
+                live = padded.norm(dim=-1) > 0
+                assert torch.equal(live, packed.norm(dim=-1) > 0)
+                cos = torch.nn.functional.cosine_similarity(packed[live], padded[live])
+                assert cos.min().item() > 1 - 1e-6, (family, b, s, kind, cos)
+        # masks the packer must refuse (identity layout): results are then bit-identical by construction
+        s = 40
+        ids = torch.randint(4, min(cfg.vocab_size, 24) if family == 'esm' else cfg.vocab_size - 1, (4, s), generator=g)
+        mask = torch.ones(4, s, dtype=torch.int64)
+        mask[0, :10] = 0          # left padding
+        mask[1, 5:9] = 0          # a hole
+        mask[2, 20:] = 0
+        lib.b2e_debug_set_packing(1)
+        a = enc.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, False).clone()
+        lib.b2e_debug_set_packing(0)
+        b_ = enc.encode_pooled(ids, mask, None, nv.POOL_MEAN_PER_ROW, False).clone()
+        assert torch.equal(a, b_)
+    finally:
+        lib.b2e_debug_set_packing(1)
+        enc.close()
