@@ -162,6 +162,58 @@ __device__ __forceinline__ float at3_exp_pack_plain(const uint32_t (&s)[32], flo
   return sum0 + sum1;
 }
 
+// The same two exponentials of poly_exp2 as ONE stream of packed fp32x2 instructions.
+__device__ __forceinline__ void poly_exp2_x2(uint64_t x, float& p_lo, float& p_hi) {
+  float x0, x1;
+  f32x2_split(x, x0, x1);
+  x = f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = f32x2(12582912.0f, 12582912.0f);
+  const uint64_t t = add_f32x2(x, magic);
+  const uint64_t f = sub_f32x2(x, sub_f32x2(t, magic));
+  uint64_t p = f32x2(0.009560510f, 0.009560510f);
+  p = fma_f32x2(p, f, f32x2(0.055917039f, 0.055917039f));
+  p = fma_f32x2(p, f, f32x2(0.240249811f, 0.240249811f));
+  p = fma_f32x2(p, f, f32x2(0.693121968f, 0.693121968f));
+  p = fma_f32x2(p, f, f32x2(0.999999191f, 0.999999191f));
+  float t0, t1, q0, q1;
+  f32x2_split(t, t0, t1);
+  f32x2_split(p, q0, q1);
+  p_lo = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p_hi = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// at3_exp_pack_plain with packed fp32x2 arithmetic: x = fma(s, scale, -m) and the row sum take one FMA-pipe
+// instruction per PAIR of scores; POLY16 of every 16 exponentials (whole pairs: 0, 4, 6 or 8) run on the FMA pipe.
+template <int POLY16>
+__device__ __forceinline__ float at3_exp_pack_plain_x2(const uint32_t (&s)[32], float scale, float neg_m,
+                                                       uint32_t* pk) {
+  const uint64_t sc2 = f32x2(scale, scale), nm2 = f32x2(neg_m, neg_m);
+  uint64_t sum_a = 0, sum_b = 0;   // two fp32 zeros each
+#pragma unroll
+  for (int i = 0; i < 32; i += 16) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      const uint64_t x =
+          fma_f32x2(f32x2(__uint_as_float(s[i + k]), __uint_as_float(s[i + k + 1])), sc2, nm2);
+      const bool poly = (POLY16 >= 2 && k == 14) || (POLY16 >= 4 && k == 6) || (POLY16 >= 6 && k == 10) ||
+                        (POLY16 >= 8 && k == 2);
+      float p0, p1;
+      if (poly) {
+        poly_exp2_x2(x, p0, p1);
+      } else {
+        float x0, x1;
+        f32x2_split(x, x0, x1);
+        p0 = fast_exp2(x0);
+        p1 = fast_exp2(x1);
+      }
+      if (k & 2) sum_b = add_f32x2(sum_b, f32x2(p0, p1)); else sum_a = add_f32x2(sum_a, f32x2(p0, p1));
+      pk[(i + k) / 2] = pack_h16x2(p0, p1);
+    }
+  }
+  float a, b;
+  f32x2_split(add_f32x2(sum_a, sum_b), a, b);
+  return a + b;
+}
+
 // One work item = (sequence b, head h, pair of query tiles pr); n = key chunks to visit.
 struct At3Item {
   int b, h, pr, n, np;   // n: key chunks to visit; np: leading chunks whose 64 keys are all attended
@@ -214,6 +266,8 @@ __device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the 
 //   bit 1  S_{j+1} is fetched from TMEM right behind the store of P_j, so that tcgen05.ld's latency runs
 //          under the publish (st wait, fence, arrive) instead of in front of the next chunk's exponentials
 //   bits 2-3  exponentials per four that run on the FMA pipe (plain chunks only): 0, 1 or 2
+//   bit 5  packed fp32x2 arithmetic on plain chunks; bits 2-3 then mean 0, 4, 6 or 8 exponentials per 16 on
+//          the FMA pipe
 //   bit 4  bidirectional sliding window (`window` > 0: ModernBERT's local layers): chunk range per item narrowed
 //          to the band, scores outside |q - k| <= window masked per element
 template <int V>
@@ -524,16 +578,24 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             }
           }
           bool done = false;
+          auto plain_exp = [&](const uint32_t (&sv)[32], uint32_t* out) {
+            if constexpr ((V & 32) != 0) {
+              constexpr int kPoly16 = kPoly == 0 ? 0 : 2 + 2 * kPoly;   // 0, 4, 6, 8
+              return at3_exp_pack_plain_x2<kPoly16>(sv, scale_log2e, -m_used, out);
+            } else {
+              return at3_exp_pack_plain<(kPoly > 2 ? 2 : kPoly)>(sv, scale_log2e, -m_used, out);
+            }
+          };
           if (plain) {
             if (j == 0) {
               // exact maximum of the raw scores first (scale > 0: max commutes with the scaling)
               m_used = scale_log2e * at3_smax_plain(s1, at3_smax_plain(s0, -INFINITY));
-              l = at3_exp_pack_plain<kPoly>(s0, scale_log2e, -m_used, pk);
-              l += at3_exp_pack_plain<kPoly>(s1, scale_log2e, -m_used, pk + 16);
+              l = plain_exp(s0, pk);
+              l += plain_exp(s1, pk + 16);
               done = true;
             } else {
-              float sum = at3_exp_pack_plain<kPoly>(s0, scale_log2e, -m_used, pk);
-              sum += at3_exp_pack_plain<kPoly>(s1, scale_log2e, -m_used, pk + 16);
+              float sum = plain_exp(s0, pk);
+              sum += plain_exp(s1, pk + 16);
               // every p <= row sum: a sum within 2^threshold proves that no score ran away
               // (a NaN sum -- inf - inf cannot occur here -- would fail the test and take the general path)
               const bool calm = sum <= 256.0f;   // 2^AT3_RESCALE_THRESHOLD

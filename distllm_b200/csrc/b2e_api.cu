@@ -410,8 +410,13 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
     case 7: return launch_attention_v<7>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 11: return launch_attention_v<11>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 5: return launch_attention_v<5>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 33: return launch_attention_v<33>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 37: return launch_attention_v<37>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 41: return launch_attention_v<41>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 45: return launch_attention_v<45>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
   }
-  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11)", att3_variant());
+  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45)",
+              att3_variant());
 }
 
 // Causal grouped-query attention, head_dim 128 (attention4.cuh).  qkv is [B*S, (heads + 2 kv_heads)*128]
