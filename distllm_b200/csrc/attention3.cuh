@@ -224,22 +224,44 @@ struct At3Item {
 // only needs the key chunks that overlap [256 pr - window, 256 pr + 255 + window]; BOTH tiles walk that same
 // range (the band is applied per element), so every role sees the same chunk list.  At least one chunk is
 // always visited: rows of padding tiles must still come out finite.
-__device__ __forceinline__ At3Item at3_decode(int item, int npairs, int heads,
-                                              const int* __restrict__ kv_chunks,
-                                              const int* __restrict__ plain_chunks, int n_items, int window,
-                                              int S, const int* __restrict__ seq_cu,
-                                              const int* __restrict__ seq_len) {
+// Decoding an item is split in two so that the global loads of the NEXT item's per-sequence numbers are issued
+// at the top of the current item and first touched at its end: warps issue in order, so arithmetic placed right
+// behind the loads would stall every role for a full L2 / DRAM round trip once per item
+// (profiles/r02_ncu_att3_source.md: `long_sb` on the per-item branches).
+struct At3Raw {
+  int b, h, pr;
+  int n, np, row0, len;   // loaded: key chunks, plain chunks, first row, rows
+  int ok;                 // item < n_items
+};
+__device__ __forceinline__ At3Raw at3_fetch(int item, int npairs, int heads, const int* __restrict__ kv_chunks,
+                                            const int* __restrict__ plain_chunks, int n_items, int S,
+                                            const int* __restrict__ seq_cu, const int* __restrict__ seq_len) {
+  At3Raw r;
+  r.ok = item < n_items;
+  const int it = r.ok ? item : 0;   // always a valid index: the loads need no branch
+  r.pr = it % npairs;
+  const int bh = it / npairs;
+  r.h = bh % heads;
+  r.b = bh / heads;
+  r.n = __ldg(kv_chunks + r.b);
+  r.np = plain_chunks != nullptr ? __ldg(plain_chunks + r.b) : 0;
+  // token layout (pack.cuh): rows [row0, row0 + len) hold the sequence; padded layout when seq_cu is null
+  r.row0 = seq_cu != nullptr ? __ldg(seq_cu + r.b) : r.b * S;
+  r.len = seq_len != nullptr ? __ldg(seq_len + r.b) : S;
+  return r;
+}
+__device__ __forceinline__ At3Item at3_finish(At3Raw r, int window) {
+  // the loaded values become visible to the arithmetic below only here
+  asm volatile("" : "+r"(r.n), "+r"(r.np), "+r"(r.row0), "+r"(r.len));
   At3Item it{0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (item < n_items) {
-    it.pr = item % npairs;
-    const int bh = item / npairs;
-    it.h = bh % heads;
-    it.b = bh / heads;
-    it.n = __ldg(kv_chunks + it.b);
-    it.np = plain_chunks != nullptr ? __ldg(plain_chunks + it.b) : 0;
-    // token layout (pack.cuh): rows [row0, row0 + len) hold the sequence; padded layout when seq_cu is null
-    it.row0 = seq_cu != nullptr ? __ldg(seq_cu + it.b) : it.b * S;
-    it.len = seq_len != nullptr ? __ldg(seq_len + it.b) : S;
+  if (r.ok) {
+    it.b = r.b;
+    it.h = r.h;
+    it.pr = r.pr;
+    it.n = r.n;
+    it.np = r.np;
+    it.row0 = r.row0;
+    it.len = r.len;
     it.nq = (it.len + 127) / 128;
     if (2 * it.pr >= it.nq) it.n = 0;   // both query tiles lie beyond the sequence: nothing to do
     if (window > 0 && it.n > 0) {
@@ -354,9 +376,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = cur.row0;
           const int buf = it & 1;
@@ -388,7 +410,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
                          bias + static_cast<size_t>(b) * S_pad + jk, AT3_KC * 4, fb);
             AT3_STAMP(3, it * 100 + j);
           }
-          cur = nxt;
+          cur = at3_finish(nxt, window);
         }
       }
     } else if (warp == 8 || warp == 10) {
@@ -407,9 +429,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int n = cur.n;
           const int buf = it & 1;
           const bool active = 2 * cur.pr + slot < cur.nq;
@@ -474,7 +496,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             }
           }
           chunk_base += static_cast<uint32_t>(n);
-          cur = nxt;
+          cur = at3_finish(nxt, window);
         }
       }
     }
@@ -492,7 +514,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
-    At3Item cur = at3_decode(item, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+    At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
     // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
     // is ordered (A before B), which merely de-phases the two warpgroups
@@ -502,7 +524,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
-      const At3Item nxt = at3_decode(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, window, S, seq_cu, seq_len);
+      const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
       const int pr = cur.pr, h = cur.h, n = cur.n;
       const int t = 2 * pr + slot;
       if (t >= cur.nq && pingpong) {
@@ -707,7 +729,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         }
       }
       chunk_base += static_cast<uint32_t>(n);
-      cur = nxt;
+      cur = at3_finish(nxt, window);
     }
     if (r == 0) tma_store_wait_all();
   }

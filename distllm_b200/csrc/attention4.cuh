@@ -94,21 +94,37 @@ struct At4Item {
   int b, h, pr, lo[2], hi[2], hi_u;
   int np;   // leading key chunks of the sequence whose 64 keys are all attended
 };
-__device__ __forceinline__ At4Item at4_decode(int item, int npairs, int heads, int nq, int window,
-                                              const int* __restrict__ kv_chunks, int n_items,
-                                              int bh_total, const int* __restrict__ plain_chunks = nullptr) {
+// Two steps, like attention3.cuh's at3_fetch / at3_finish: the next item's per-sequence numbers are loaded at
+// the top of the current item and first touched at its end (warps issue in order).
+struct At4Raw {
+  int b, h, pr, kvc, np, ok;
+};
+__device__ __forceinline__ At4Raw at4_fetch(int item, int npairs, int heads, const int* __restrict__ kv_chunks,
+                                            int n_items, int bh_total,
+                                            const int* __restrict__ plain_chunks = nullptr) {
+  At4Raw r;
+  r.ok = item < n_items;
+  const int it = r.ok ? item : 0;
+  r.pr = npairs - 1 - it / bh_total;   // heaviest (latest) query tiles first
+  const int bh = it % bh_total;
+  r.h = bh % heads;
+  r.b = bh / heads;
+  r.kvc = __ldg(kv_chunks + r.b);
+  r.np = plain_chunks != nullptr ? __ldg(plain_chunks + r.b) : 0;
+  return r;
+}
+__device__ __forceinline__ At4Item at4_finish(At4Raw r, int nq, int window) {
+  asm volatile("" : "+r"(r.kvc), "+r"(r.np));
   At4Item it{0, 0, 0, {0, 0}, {0, 0}, 0, 0};
-  if (item < n_items) {
-    it.pr = npairs - 1 - item / bh_total;   // heaviest (latest) query tiles first
-    const int bh = item % bh_total;
-    it.h = bh % heads;
-    it.b = bh / heads;
-    const int kvc = __ldg(kv_chunks + it.b);
-    it.np = plain_chunks != nullptr ? __ldg(plain_chunks + it.b) : 0;
+  if (r.ok) {
+    it.pr = r.pr;
+    it.h = r.h;
+    it.b = r.b;
+    it.np = r.np;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int t = 2 * it.pr + s;
-      int hi = min(kvc, 2 * t + 2);
+      int hi = min(r.kvc, 2 * t + 2);
       int lo = (window > 0) ? max(0, 128 * t - window + 1) / AT4_KC : 0;
       if (lo >= hi) lo = hi - 1;
       if (t >= nq) { lo = 0; hi = 0; }
@@ -191,10 +207,9 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         uint32_t chunk_ctr = 0;       // ring position, runs across items
         uint32_t q_loads[2] = {0, 0}; // Q tiles loaded so far per slot
         int item = blockIdx.x;
-        At4Item cur = at4_decode(item, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
+        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total), nq, window);
         for (; item < n_items; item += gridDim.x) {
-          const At4Item nxt =
-              at4_decode(item + gridDim.x, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
+          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total);
           const int row_base = cur.b * S;
           const int hk = cur.h / group;
           const int n_active = (cur.hi[1] > 0) ? 2 : 1;
@@ -239,7 +254,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
                          bias + static_cast<size_t>(cur.b) * S_pad + j * AT4_KC, AT4_KC * 4, fb);
           }
           try_q(true);
-          cur = nxt;
+          cur = at4_finish(nxt, nq, window);
         }
       }
     } else if (warp == 8 || warp == 10) {
@@ -259,10 +274,9 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         uint32_t p_par = 0;        // bit sbuf: parity of the p_ready phase to wait for
         uint32_t tile_cnt = 0;
         int item = blockIdx.x;
-        At4Item cur = at4_decode(item, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
+        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total), nq, window);
         for (; item < n_items; item += gridDim.x) {
-          const At4Item nxt =
-              at4_decode(item + gridDim.x, npairs, heads, nq, window, kv_chunks, n_items, bh_total);
+          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total);
           const int n_u = cur.hi_u - cur.lo[0];
           const int my_lo = slot ? cur.lo[1] : cur.lo[0];
           const int my_hi = slot ? cur.hi[1] : cur.hi[0];
@@ -331,7 +345,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
           }
           for (int c = c_hi; c < n_u; ++c) pass_on(c);
           chunk_base += static_cast<uint32_t>(n_u);
-          cur = nxt;
+          cur = at4_finish(nxt, nq, window);
         }
       }
     }
@@ -347,12 +361,11 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
     uint32_t s_par = 0;   // bit sbuf: parity of the s_ready[slot][sbuf] phase to wait for
     uint32_t o_cnt = 0;
     int item = blockIdx.x;
-    At4Item cur = at4_decode(item, npairs, heads, nq, window, kv_chunks, n_items, bh_total, plain_chunks);
+    At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total, plain_chunks), nq, window);
     uint8_t* ostage = smem + AT4_SMEM_OST + slot * AT4_QSLAB;
     const uint32_t ostage_addr = sb + AT4_SMEM_OST + slot * AT4_QSLAB;
     for (; item < n_items; item += gridDim.x) {
-      const At4Item nxt =
-          at4_decode(item + gridDim.x, npairs, heads, nq, window, kv_chunks, n_items, bh_total, plain_chunks);
+      const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total, plain_chunks);
       const int t = 2 * cur.pr + slot;
       const int lo = slot ? cur.lo[1] : cur.lo[0];
       const int hi = slot ? cur.hi[1] : cur.hi[0];
@@ -501,7 +514,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         }
       }
       chunk_base += static_cast<uint32_t>(cur.hi_u - cur.lo[0]);
-      cur = nxt;
+      cur = at4_finish(nxt, nq, window);
     }
     if (r == 0) tma_store_wait_all();
   }

@@ -930,7 +930,7 @@ int run_modernbert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask,
   int rc;
   DISPATCH_NV(H, (modernbert_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
                      ids, (const float*)e->w[0], (const float*)e->w[1], (const float*)e->w[2], e->xres,
-                     e->hidden, M, d.eps, lay.t_real)));
+                     e->hidden, M, d.eps, lay.t_real, lay.tok_src)));
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn, tm_qkv, tm_kv64;
