@@ -17,9 +17,9 @@ import torch
 LIB_PATH = Path(__file__).resolve().parent / 'libb2e.so'
 LIB_PATHS = {'f16': LIB_PATH, 'bf16': LIB_PATH.with_name('libb2e_bf16.so')}
 STORAGE_TORCH_DTYPE = {'f16': torch.float16, 'bf16': torch.bfloat16}
-# Which build an encoder family runs on.  Measured (profiles/r02_drift_report_*.md, r02_storage_ab.md): with
+# Which build an encoder family runs on.  Measured (profiles/r02_drift_report_*.md, r02_notes.md section 1): with
 # bfloat16 the 12-layer BERT and 33-layer ESM-2 shapes stay within 5e-5 cosine of the fp32 reference and the
-# GEMMs hold a ~13 % higher clock under the 1 kW power cap; the 32-layer Mistral-7B shape needs half (3.3e-5
+# GEMMs sustain ~5 % more TFLOP/s under the board's power cap; the 32-layer Mistral-7B shape needs half (3.3e-5
 # against 1.6e-3 with bfloat16; tolerance 1e-3).  B2E_STORAGE=f16|bf16 overrides for every family.
 _STORAGE_BY_ARCH = {'bert': 'bf16', 'esm': 'bf16', 'modernbert': 'bf16', 'mistral': 'f16'}
 
