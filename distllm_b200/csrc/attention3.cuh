@@ -367,6 +367,13 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     }                                                                  \
   } while (0)
 
+  // waits of the single-thread roles (loader, MMA issuers): flag bit 2 parks the thread in hardware instead of
+  // polling -- those threads sit on the sub-partitions of softmax warps 0-2 and 4-6 and their polling loops
+  // executed more warp instructions than the kernel has MUFU.EX2 (profiles/r02_ncu_att3_source.md)
+  const bool park = (g_att3_flags & 4) != 0;
+  auto bg_wait = [&](uint32_t bar, uint32_t parity) {
+    if (park) mbar_wait_parked(bar, parity); else mbar_wait(bar, parity);
+  };
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 9) {
@@ -388,7 +395,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             const int idx = buf * 2 + slot;
             const uint32_t bit = 1u << idx;
             // the buffer is free once the last Q K^T of its previous tile has completed
-            if (q_any & bit) mbar_wait(q_empty + 8u * idx, ((q_par >> idx) & 1u) ^ 1u);
+            if (q_any & bit) bg_wait(q_empty + 8u * idx, ((q_par >> idx) & 1u) ^ 1u);
             const uint32_t qb = q_full + 8u * idx;
             mbar_expect_tx(qb, AT3_QTILE);
             tma_load_2d(sb + AT3_SMEM_Q + idx * AT3_QTILE, &tm_q, qb, h * AT3_D, row_base + t * 128);
@@ -399,7 +406,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
           for (int j = 0; j < n; ++j, ++chunk_ctr) {
             const int st = chunk_ctr % AT3_NST;
             const uint32_t use = chunk_ctr / AT3_NST;
-            if (use > 0) mbar_wait(kv_empty + 8u * st, (use - 1) & 1u);
+            if (use > 0) bg_wait(kv_empty + 8u * st, (use - 1) & 1u);
             const uint32_t fb = kv_full + 8u * st;
             mbar_expect_tx(fb, 2 * AT3_KVTILE + AT3_KC * 4);
             const uint32_t dst = sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE;
@@ -441,7 +448,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             // and may give it only once the stage has been filled for THIS use
             for (int j = 0; j < n; ++j) {
               const uint32_t c = chunk_base + j;
-              mbar_wait(kv_full + 8u * (c % AT3_NST), (c / AT3_NST) & 1u);
+              bg_wait(kv_full + 8u * (c % AT3_NST), (c / AT3_NST) & 1u);
               mbar_arrive(kv_empty + 8u * (c % AT3_NST));
             }
           } else {
@@ -450,7 +457,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
             auto issue_qk = [&](int j) {
               const uint32_t c = chunk_base + j;
               const int st = c % AT3_NST;
-              mbar_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);
+              bg_wait(kv_full + 8u * st, (c / AT3_NST) & 1u);
               tc_fence_after();
               const uint64_t k_desc =
                   make_smem_desc_sw128(sb + AT3_SMEM_KV + st * 2 * AT3_KVTILE, 16, 1024);
@@ -462,7 +469,7 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
               if (slot == 0) AT3_STAMP(2, j * 10 + 1);
               if (j + 1 == n) tc_commit(q_empty + 8u * qidx);
             };
-            mbar_wait(q_full + 8u * qidx, q_cnt[buf] & 1u);
+            bg_wait(q_full + 8u * qidx, q_cnt[buf] & 1u);
             ++q_cnt[buf];
             issue_qk(0);
             for (int j = 0; j < n; ++j) {
@@ -470,10 +477,10 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
               // P V was issued one iteration ago (tcgen05 ops of one thread execute in order)
               if (j + 1 < n) issue_qk(j + 1);
               const int sbuf = j & 1;
-              mbar_wait(p_ready + 8u * (slot * 2 + sbuf), (p_par >> sbuf) & 1u);
+              bg_wait(p_ready + 8u * (slot * 2 + sbuf), (p_par >> sbuf) & 1u);
               p_par ^= 1u << sbuf;
               // the previous tile's epilogue (o_empty) precedes this tile's first p_ready
-              if (j == 0 && tile_cnt > 0) mbar_wait(o_empty + 8u * slot, (tile_cnt - 1) & 1u);
+              if (j == 0 && tile_cnt > 0) bg_wait(o_empty + 8u * slot, (tile_cnt - 1) & 1u);
               tc_fence_after();
               const uint32_t c = chunk_base + j;
               const int st = c % AT3_NST;

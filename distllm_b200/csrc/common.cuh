@@ -93,6 +93,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// The same wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint
+// runs out) instead of returning to a polling loop every few dozen clocks.  For single-thread roles that share
+// an SM sub-partition with compute warps: their polling otherwise takes issue slots from those warps.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "B2E_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra B2E_DONE;\n\t"
+      "bra B2E_WAIT;\n\t"
+      "B2E_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -20,7 +20,9 @@ int b2e_debug_set_layers(struct B2EEncoder* enc, int n_layers);
 /* device buffer of 4 x 512 int64: CTA 0 of the streaming attention kernels records (clock64, event
  * code) pairs per role (softmax slot A/B, MMA issuer, loader); NULL switches it off */
 int b2e_debug_set_att3_clock(void* device_buffer);
-/* softmax scheduling experiments of the attention kernels (see attention3.cuh g_att3_flags) */
+/* scheduling experiments of the attention kernels (attention3.cuh g_att3_flags): bits 0-1 ordering of the two
+ * softmax warpgroups (0 free-running, 1 strict ping-pong, 2 de-phased once per item = default), bit 2 the loader
+ * and MMA-issuer threads wait parked in hardware (mbarrier.try_wait with a suspend-time hint) instead of polling */
 int b2e_debug_set_att3_flags(int flags);
 /* 0: keep the padded [B, S] token layout on every path; 1 (default, also B2E_PACKED=1): pooled forward passes run
  * on the attended tokens only (csrc/pack.cuh).  Drops the handle's cached CUDA graphs' validity: call it before

@@ -17,6 +17,9 @@ dev = torch.device('cuda:0')
 lib = nv.load()
 lib.b2e_debug_set_att3_variant.argtypes = [ctypes.c_int]
 variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '0,1,5,33,37,41,45').split(',')]
+# optional second argument: scheduling flags (b2e_debug_set_att3_flags) to run every variant with, e.g. "2,6"
+flag_sets = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [None]
+lib.b2e_debug_set_att3_flags.argtypes = [ctypes.c_int]
 
 
 def reference(qkv, mask, b, s, heads):
@@ -46,8 +49,10 @@ for b, s, heads in [(512, 512, 12), (128, 512, 12), (64, 1026, 20)]:
     qkv = torch.randn(b * s, 3 * heads * 64, device=dev).half()
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
     base = None
-    for v in variants:
+    for v, fl in [(v, fl) for v in variants for fl in flag_sets]:
         lib.b2e_debug_set_att3_variant(v)
+        if fl is not None:
+            assert lib.b2e_debug_set_att3_flags(fl) == 0
         for _ in range(3):
             out = nv.attention_d64(qkv, mask, b, s, heads)
         torch.cuda.synchronize()
@@ -61,6 +66,8 @@ for b, s, heads in [(512, 512, 12), (128, 512, 12), (64, 1026, 20)]:
         if base is None:
             base = out.float()
         diff = (out.float() - base).abs().max().item()
-        print(f'B={b} S={s} heads={heads} variant {v:2d}: {ms:.3f} ms  {4.0 * b * heads * s * s * 64 / ms / 1e9:.0f} TFLOP/s'
+        print(f'B={b} S={s} heads={heads} variant {v:2d}{"" if fl is None else f" flags {fl}"}: {ms:.3f} ms  {4.0 * b * heads * s * s * 64 / ms / 1e9:.0f} TFLOP/s'
               f'  max |out - variant {variants[0]}| = {diff:.4f}', flush=True)
 lib.b2e_debug_set_att3_variant(0)
+if flag_sets != [None]:
+    lib.b2e_debug_set_att3_flags(2)
