@@ -839,8 +839,8 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, (const float*)e->E(l, 3), nullptr, M,
                           3 * H, H, B2E_EPI_BIAS, e->sms, st, lay.t_real)))
       return rc;
-    rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
-                                                                    M, S, d.heads, lay.t_real, lay.tok_src);
+    rope_halves_kernel<32><<<(unsigned)((rope_work * 4 + 255) / 256), 256, 0, st>>>(
+        e->qkv, e->rope_cos, e->rope_sin, M, S, 2 * d.heads, 3 * H, lay.t_real, lay.tok_src);
     if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st, 0, lay)))
       return rc;
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, (const float*)e->E(l, 5), nullptr, M, H, H,
@@ -892,8 +892,8 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, QC, H, B2E_EPI_BIAS,
                           e->sms, st)))
       return rc;
-    rope_d128_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(e->qkv, e->rope_cos, e->rope_sin,
-                                                                      M, S, n_rot, QC);
+    rope_halves_kernel<64><<<(unsigned)((rope_work * 8 + 255) / 256), 256, 0, st>>>(
+        e->qkv, e->rope_cos, e->rope_sin, M, S, n_rot, QC);
     if ((rc = launch_attention_causal_d128(e->qkv, e->attn, e->ctx, B, S, d.heads, d.kv_heads,
                                            d.sliding_window, e->sms, st)))
       return rc;
@@ -950,9 +950,9 @@ int run_modernbert_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask,
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, 3 * H, H, B2E_EPI_BIAS,
                           e->sms, st, lay.t_real)))
       return rc;
-    rope_qk_kernel<<<(unsigned)((rope_work + 7) / 8), 256, 0, st>>>(
-        e->qkv, global ? e->rope_cos : e->rope_cos2, global ? e->rope_sin : e->rope_sin2, M, S, d.heads,
-        lay.t_real, lay.tok_src);
+    rope_halves_kernel<32><<<(unsigned)((rope_work * 4 + 255) / 256), 256, 0, st>>>(
+        e->qkv, global ? e->rope_cos : e->rope_cos2, global ? e->rope_sin : e->rope_sin2, M, S, 2 * d.heads,
+        3 * H, lay.t_real, lay.tok_src);
     if ((rc = launch_attention(tm_qkv, tm_kv64, e->attn, e->ctx, B, S, d.heads, e->sms, st,
                                global ? 0 : d.sliding_window, lay)))
       return rc;

@@ -188,27 +188,4 @@ __global__ void rope_table_theta_kernel(float* __restrict__ cos_t, float* __rest
   sin_t[i] = s;
 }
 
-// In-place rotary embedding of the first `n_rot` heads of every row of qkv [T, ld] (head_dim 128,
-// halves of 64; q heads are followed directly by the k heads, so one pass rotates both):
-//   out[i] = x[i] cos_i - x[i+64] sin_i ;  out[i+64] = x[i+64] cos_i + x[i] sin_i   (position = t % S)
-// One warp per (token, head); a lane owns frequencies lane and lane + 32.
-__global__ void rope_d128_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t,
-                                 const float* __restrict__ sin_t, int T, int S, int n_rot, int ld) {
-  const int lane = threadIdx.x & 31;
-  const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= static_cast<long long>(T) * n_rot) return;
-  const int t = static_cast<int>(w / n_rot);
-  const int hd = static_cast<int>(w % n_rot);
-  h16* p = qkv + static_cast<size_t>(t) * ld + hd * 128;
-  const int pos = t % S;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int i = lane + 32 * k;
-    const float c = cos_t[pos * 64 + i], s = sin_t[pos * 64 + i];
-    const float x1 = from_h16(p[i]), x2 = from_h16(p[i + 64]);
-    p[i] = to_h16(x1 * c - x2 * s);
-    p[i + 64] = to_h16(x2 * c + x1 * s);
-  }
-}
-
 }  // namespace b2e

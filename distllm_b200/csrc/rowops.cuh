@@ -574,27 +574,43 @@ __global__ void rope_table_kernel(float* __restrict__ cos_t, float* __restrict__
   sin_t[i] = s;
 }
 
-// In-place rotary embedding of the Q and K thirds of qkv [T, 3H] (head_dim 64, halves of 32):
-//   out[i] = x[i] cos - x[i+32] sin ;  out[i+32] = x[i+32] cos + x[i] sin     (position = t % S)
-// One warp per (token, head pair of Q|K); lane = frequency index i.
-__global__ void rope_qk_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t,
-                               const float* __restrict__ sin_t, int T, int S, int heads,
-                               const int* __restrict__ n_dev = nullptr,
-                               const int* __restrict__ tok_src = nullptr) {
-  const int H = heads * 64;
-  const int lane = threadIdx.x & 31;
-  const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// In-place rotary embedding of the first `n_rot` heads of every row of qkv [T, ld], head_dim 2 * HALF in the
+// "halves" convention (rotate_half):
+//   out[i] = x[i] cos_i - x[i+HALF] sin_i ;  out[i+HALF] = x[i+HALF] cos_i + x[i] sin_i
+// with the position of a row inside its sequence = tok_src[t] % S (packed layout) or t % S.  The rotated heads
+// start at column 0: Q heads directly followed by the K heads in every layout this library uses.
+// A thread owns 8 consecutive frequencies (one 16-byte vector from each half), HALF / 8 threads share a head,
+// so a warp moves 1 KiB (HALF = 32) or 2 x 512 B (HALF = 64) of contiguous bytes per access: the kernel is a plain
+// HBM stream (the first version, one 2-byte element per lane, ran at a quarter of the roofline and cost 13 % of
+// the ESM2-650M step, profiles/r02_ncu_launches_c5.md).
+template <int HALF>
+__global__ void __launch_bounds__(256)
+rope_halves_kernel(h16* __restrict__ qkv, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                   int T, int S, int n_rot, int ld, const int* __restrict__ n_dev = nullptr,
+                   const int* __restrict__ tok_src = nullptr) {
+  constexpr int TPH = HALF / 8;   // threads per head
   if (n_dev != nullptr) T = __ldg(n_dev);
-  const long long n_work = static_cast<long long>(T) * heads * 2;  // q heads then k heads
-  if (w >= n_work) return;
-  const int t = static_cast<int>(w / (heads * 2));
-  const int hk = static_cast<int>(w % (heads * 2));  // [0, heads): q head, [heads, 2*heads): k head
-  h16* p = qkv + static_cast<size_t>(t) * 3 * H + hk * 64;  // K third starts right after Q's H columns
-  const int pos = (tok_src != nullptr ? __ldg(tok_src + t) : t) % S;   // position inside its sequence
-  const float c = cos_t[pos * 32 + lane], s = sin_t[pos * 32 + lane];
-  const float x1 = from_h16(p[lane]), x2 = from_h16(p[lane + 32]);
-  p[lane] = to_h16(x1 * c - x2 * s);
-  p[lane + 32] = to_h16(x2 * c + x1 * s);
+  const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long unit = gtid / TPH;
+  const int g = static_cast<int>(gtid % TPH);
+  if (unit >= static_cast<long long>(T) * n_rot) return;
+  const int t = static_cast<int>(unit / n_rot);
+  const int hd = static_cast<int>(unit % n_rot);
+  h16* p = qkv + static_cast<size_t>(t) * ld + hd * (2 * HALF) + g * 8;
+  const int pos = (tok_src != nullptr ? __ldg(tok_src + t) : t) % S;
+  float c[8], sn[8], x1[8], x2[8];
+  load8(cos_t + static_cast<size_t>(pos) * HALF + g * 8, c);
+  load8(sin_t + static_cast<size_t>(pos) * HALF + g * 8, sn);
+  load8(p, x1);
+  load8(p + HALF, x2);
+  float o1[8], o2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o1[i] = x1[i] * c[i] - x2[i] * sn[i];
+    o2[i] = x2[i] * c[i] + x1[i] * sn[i];
+  }
+  store8(p, o1);
+  store8(p + HALF, o2);
 }
 
 }  // namespace b2e
