@@ -71,6 +71,8 @@ EXPORTS = (
     'b2e_attention_d64_window',
     'b2e_attention_causal_d128',
     'b2e_topk_ip',
+    'b2e_topk_ip_tc',
+    'b2e_max_row_norm',
     'b2e_pack_ubinary',
     'b2e_search_ubinary',
     'b2e_layernorm',
@@ -84,6 +86,7 @@ DEBUG_EXPORTS = (
     'b2e_debug_set_layers',
     'b2e_debug_set_att3_variant',
     'b2e_debug_set_packing',
+    'b2e_debug_topk_tc_fell_back',
 )
 
 
@@ -159,6 +162,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.b2e_attention_causal_d128.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b2e_topk_ip.restype = i32
     lib.b2e_topk_ip.argtypes = [vp, i32, vp, i32, i64, i32, i32, vp, vp, vp]
+    lib.b2e_topk_ip_tc.restype = i32
+    lib.b2e_topk_ip_tc.argtypes = [vp, i32, vp, i64, i32, i32, C.c_float, vp, vp, vp]
+    lib.b2e_max_row_norm.restype = i32
+    lib.b2e_max_row_norm.argtypes = [vp, i64, i32, C.POINTER(C.c_float), vp]
     lib.b2e_pack_ubinary.restype = i32
     lib.b2e_pack_ubinary.argtypes = [vp, i64, i32, vp, vp]
     lib.b2e_search_ubinary.restype = i32
@@ -297,9 +304,11 @@ def attention_causal_d128(
     return ctx
 
 
-def topk_ip(queries: torch.Tensor, corpus: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+def topk_ip(queries: torch.Tensor, corpus: torch.Tensor, k: int,
+            max_norm: float | None = None) -> tuple[torch.Tensor, torch.Tensor]:
     """Exact inner-product top-k: queries [Q,H] f32, corpus [N,H] f32|bf16 (CUDA) -> (scores [Q,k] f32,
-    indices [Q,k] i64), sorted by descending score."""
+    indices [Q,k] i64), sorted by descending score.  ``max_norm`` (an upper bound of the corpus rows' Euclidean
+    norms, see :func:`max_row_norm`) selects the tensor-core scan for a float32 corpus; the results are the same."""
     lib = load()
     _cuda_contig(queries, 'queries'), _cuda_contig(corpus, 'corpus')
     if queries.dtype != torch.float32:
@@ -309,9 +318,35 @@ def topk_ip(queries: torch.Tensor, corpus: torch.Tensor, k: int) -> tuple[torch.
     scores = torch.empty((q, k), dtype=torch.float32, device=queries.device)
     indices = torch.empty((q, k), dtype=torch.int64, device=queries.device)
     with torch.cuda.device(queries.device):
-        check(lib.b2e_topk_ip(queries.data_ptr(), q, corpus.data_ptr(), dtype_code(corpus.dtype), n, h, k,
-                              scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
+        if max_norm is not None and corpus.dtype == torch.float32:
+            check(lib.b2e_topk_ip_tc(queries.data_ptr(), q, corpus.data_ptr(), n, h, k, float(max_norm),
+                                     scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
+        else:
+            check(lib.b2e_topk_ip(queries.data_ptr(), q, corpus.data_ptr(), dtype_code(corpus.dtype), n, h, k,
+                                  scores.data_ptr(), indices.data_ptr(), stream_ptr(queries.device)))
     return scores, indices
+
+
+def max_row_norm(matrix: torch.Tensor) -> float:
+    """Largest Euclidean row norm of a float32 CUDA matrix (index-build step of the tensor-core search)."""
+    lib = load()
+    _cuda_contig(matrix, 'matrix')
+    if matrix.dtype != torch.float32:
+        raise NativeError('max_row_norm expects float32')
+    out = C.c_float(0.0)
+    with torch.cuda.device(matrix.device):
+        check(lib.b2e_max_row_norm(matrix.data_ptr(), matrix.shape[0], matrix.shape[1], C.byref(out),
+                                   stream_ptr(matrix.device)))
+    return float(out.value)
+
+
+def topk_tc_fell_back() -> bool:
+    """Whether this thread's last tensor-core search had to redo the call with the exact scan (debug hook)."""
+    lib = load()
+    out = C.c_int(0)
+    lib.b2e_debug_topk_tc_fell_back.argtypes = [C.POINTER(C.c_int)]
+    check(lib.b2e_debug_topk_tc_fell_back(C.byref(out)))
+    return bool(out.value)
 
 
 def pack_ubinary(embeddings: torch.Tensor) -> torch.Tensor:

@@ -25,6 +25,7 @@
 #include "pack.cuh"
 #include "rowops.cuh"
 #include "topk.cuh"
+#include "topk_tc.cuh"
 
 using namespace b2e;
 
@@ -91,6 +92,24 @@ int make_tmap_h16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled(rows=%llu, cols=%llu, box_rows=%u) -> %d",
+                (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r);
+  return B2E_OK;
+}
+
+// 2-D float32 row-major tensor, box = 32 columns (128 bytes) x box_rows, 128-byte swizzle; rows beyond the
+// tensor read as zeros
+int make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled f32(rows=%llu, cols=%llu, box_rows=%u) -> %d",
                 (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r);
   return B2E_OK;
 }
@@ -1674,7 +1693,7 @@ thread_local TopkScratch g_topk_scratch;
 
 template <typename T, int QT, int ROWS, int VMAX>
 int launch_topk_cfg(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
-                    int64_t* out_index, int sms, cudaStream_t st) {
+                    int64_t* out_index, int sms, cudaStream_t st, const int* run_flag = nullptr) {
   // queries per pass: bounded by QT and by ~160 KiB of shared memory for the query tile
   int qt = QT;
   while (qt > 1 && (size_t)qt * H * 4 > 160 * 1024) qt >>= 1;
@@ -1691,10 +1710,10 @@ int launch_topk_cfg(const float* queries, int Q, const T* corpus, int64_t N, int
     const int nq = (Q - q0 < qt) ? (Q - q0) : qt;
     const size_t smem = (size_t)nq * H * 4 + (size_t)nq * k * 12 + 8 + (size_t)nq * 12;
     kern<<<grid, TOPK_THREADS, smem, st>>>(queries + (size_t)q0 * H, corpus, nq, (long long)N, H, k,
-                                           g_topk_scratch.score, g_topk_scratch.index);
+                                           g_topk_scratch.score, g_topk_scratch.index, run_flag);
     topk_merge_kernel<<<nq, TOPK_THREADS, 0, st>>>(g_topk_scratch.score, g_topk_scratch.index, grid, nq,
                                                    k, out_score + (size_t)q0 * k,
-                                                   out_index + (size_t)q0 * k, k);
+                                                   out_index + (size_t)q0 * k, k, run_flag);
   }
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
@@ -1703,11 +1722,56 @@ int launch_topk_cfg(const float* queries, int Q, const T* corpus, int64_t N, int
 // one to four queries: the narrow, deeper scan; more: 16 queries per pass
 template <typename T, int VWIDE, int VNARROW>
 int launch_topk(const float* queries, int Q, const T* corpus, int64_t N, int H, int k, float* out_score,
-                int64_t* out_index, int sms, cudaStream_t st) {
+                int64_t* out_index, int sms, cudaStream_t st, const int* run_flag = nullptr) {
   if (Q <= 4)
-    return launch_topk_cfg<T, 4, 8, VNARROW>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st);
-  return launch_topk_cfg<T, TOPK_QT, 4, VWIDE>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st);
+    return launch_topk_cfg<T, 4, 8, VNARROW>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st, run_flag);
+  return launch_topk_cfg<T, TOPK_QT, 4, VWIDE>(queries, Q, corpus, N, H, k, out_score, out_index, sms, st,
+                                               run_flag);
 }
+
+// ---- tensor-core fast path (topk_tc.cuh)
+struct TcScratch {
+  float* scores = nullptr;      // [tiles * 128, 16]
+  float* qpad = nullptr;        // [16, H]
+  TcQuery* meta = nullptr;      // [16]
+  unsigned* hist = nullptr;     // [16, TC_BINS]
+  unsigned* cand = nullptr;     // [16, TC_MAX_CAND]
+  unsigned* n_cand = nullptr;   // [16]
+  int* flag = nullptr;          // [2]: fallback requested; passes that requested it (debug)
+  float* norm2 = nullptr;       // [1]
+  size_t cap_rows = 0, cap_h = 0;
+  int device = -1;
+  void release() {
+    cudaFree(scores); cudaFree(qpad); cudaFree(meta); cudaFree(hist); cudaFree(cand); cudaFree(n_cand);
+    cudaFree(flag); cudaFree(norm2);
+    scores = qpad = norm2 = nullptr; meta = nullptr; hist = cand = n_cand = nullptr; flag = nullptr;
+    cap_rows = cap_h = 0;
+  }
+  int ensure(size_t rows, size_t h) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != device) {
+      release();
+      device = dev;
+    }
+    if (rows <= cap_rows && h <= cap_h && flag != nullptr) return B2E_OK;
+    const size_t r = rows > cap_rows ? rows : cap_rows, hh = h > cap_h ? h : cap_h;
+    release();
+    CUDA_TRY(cudaMalloc(&scores, r * TC_NQ * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&qpad, (size_t)TC_NQ * hh * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&meta, TC_NQ * sizeof(TcQuery)));
+    CUDA_TRY(cudaMalloc(&hist, (size_t)TC_NQ * TC_BINS * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&cand, (size_t)TC_NQ * TC_MAX_CAND * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&n_cand, TC_NQ * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&flag, 2 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&norm2, sizeof(float)));
+    CUDA_TRY(cudaMemset(flag, 0, 2 * sizeof(int)));
+    cap_rows = r;
+    cap_h = hh;
+    return B2E_OK;
+  }
+};
+thread_local TcScratch g_tc_scratch;
 }  // namespace
 }  // extern "C++"
 
@@ -1730,6 +1794,80 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
       return launch_topk<bf16, 3, 2>(queries, Q, (const bf16*)corpus, N, H, k, out_scores, out_indices, info.sms, st);
   }
   return fail(B2E_ERR_INVALID, "topk: corpus dtype %d (F32 or BF16)", corpus_dtype);
+}
+
+// largest Euclidean row norm of a float32 matrix (synchronises the stream: an index-build step, not a query step)
+int b2e_max_row_norm(const float* x, int64_t N, int H, float* out_host, void* stream) {
+  if (!x || !out_host) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  if (N <= 0 || H <= 0 || H % 4 != 0) return fail(B2E_ERR_INVALID, "max_row_norm: N=%lld H=%d", (long long)N, H);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  TcScratch& sc = g_tc_scratch;
+  if ((rc = sc.ensure(TC_ROWS, 128))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(sc.norm2, 0, sizeof(float), st));
+  max_row_norm2_kernel<<<info.sms * 4, 256, 0, st>>>(x, (long long)N, H, sc.norm2);
+  float n2 = 0.0f;
+  CUDA_TRY(cudaMemcpyAsync(&n2, sc.norm2, sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *out_host = sqrtf(n2);
+  return B2E_OK;
+}
+
+// Exact inner-product top-k with the scan on the tensor cores (topk_tc.cuh).  corpus_max_norm bounds the Euclidean
+// norm of every corpus row (b2e_max_row_norm; 1 for normalised embeddings): it sizes the TF32 error margin.
+// Same results as b2e_topk_ip; small problems and anything the fast path cannot take go there directly.
+int b2e_topk_ip_tc(const float* queries, int Q, const float* corpus, int64_t N, int H, int k,
+                   float corpus_max_norm, float* out_scores, int64_t* out_indices, void* stream) {
+  if (!queries || !corpus || !out_scores || !out_indices) return fail(B2E_ERR_INVALID, "null tensor pointer");
+  const bool fast = N >= 32768 && N < (int64_t)4000000000ll && H % 128 == 0 && H <= 8192 && k > 0 && k <= TOPK_MAX_K &&
+                    corpus_max_norm > 0.0f && corpus_max_norm < 1e30f && Q > 0;
+  if (!fast) return b2e_topk_ip(queries, Q, corpus, B2E_DTYPE_F32, N, H, k, out_scores, out_indices, stream);
+  int rc;
+  DeviceInfo info;
+  if ((rc = current_device_info(&info))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tiles = (N + TC_ROWS - 1) / TC_ROWS;
+  TcScratch& sc = g_tc_scratch;
+  if ((rc = sc.ensure((size_t)tiles * TC_ROWS, (size_t)H))) return rc;
+  CUtensorMap tm_c, tm_q;
+  if ((rc = make_tmap_f32(&tm_c, corpus, (uint64_t)N, (uint64_t)H, TC_ROWS))) return rc;
+  if ((rc = make_tmap_f32(&tm_q, sc.qpad, TC_NQ, (uint64_t)H, TC_NQ))) return rc;
+  if ((rc = ensure_smem_attr(tf32_scan_kernel, TC_SMEM_BYTES))) return rc;
+  if ((rc = ensure_smem_attr(score_hist_kernel, TC_NQ * TC_BINS * 4))) return rc;
+  if ((rc = ensure_smem_attr(exact_rescore_kernel, TC_MAX_CAND * 8 + 8192 * 4))) return rc;
+  CUDA_TRY(cudaMemsetAsync(sc.flag, 0, 2 * sizeof(int), st));
+  const int grid_scan = tiles < info.sms ? (int)tiles : info.sms;
+  const int grid_rows = info.sms * 2;
+  for (int q0 = 0; q0 < Q; q0 += TC_NQ) {
+    const int nq = Q - q0 < TC_NQ ? Q - q0 : TC_NQ;
+    tc_prepare_queries_kernel<<<TC_NQ, 256, 0, st>>>(queries + (size_t)q0 * H, nq, H, corpus_max_norm, sc.qpad,
+                                                     sc.meta);
+    CUDA_TRY(cudaMemsetAsync(sc.hist, 0, (size_t)TC_NQ * TC_BINS * sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(sc.n_cand, 0, TC_NQ * sizeof(unsigned), st));
+    tf32_scan_kernel<<<grid_scan, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_c, tm_q, sc.scores, tiles, H);
+    score_hist_kernel<<<grid_rows, 512, (size_t)nq * TC_BINS * 4, st>>>(sc.scores, (long long)N, nq, sc.meta,
+                                                                        sc.hist);
+    score_threshold_kernel<<<1, 32 * TC_NQ, 0, st>>>(sc.hist, nq, (long long)N, k, sc.meta);
+    score_select_kernel<<<grid_rows, 512, 0, st>>>(sc.scores, (long long)N, nq, sc.meta, sc.cand, sc.n_cand);
+    exact_rescore_kernel<<<nq, 512, (size_t)TC_MAX_CAND * 8 + (size_t)H * 4, st>>>(
+        sc.cand, sc.n_cand, sc.meta, queries + (size_t)q0 * H, corpus, H, k, out_scores + (size_t)q0 * k,
+        out_indices + (size_t)q0 * k, sc.flag);
+  }
+  CUDA_TRY(cudaGetLastError());
+  // the exact scan redoes the call when a candidate list overflowed; otherwise its kernels return at once
+  return launch_topk<float, 6, 3>(queries, Q, corpus, N, H, k, out_scores, out_indices, info.sms, st, sc.flag);
+}
+
+// 1 when the last b2e_topk_ip_tc call of this thread had to fall back to the exact scan (synchronises the device)
+int b2e_debug_topk_tc_fell_back(int* out) {
+  if (!out) return fail(B2E_ERR_INVALID, "null pointer");
+  *out = 0;
+  if (g_tc_scratch.flag == nullptr) return B2E_OK;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, g_tc_scratch.flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return B2E_OK;
 }
 
 // ---- ubinary retrieval: packed bits, Hamming top-K, float rescoring (binsearch.cuh)

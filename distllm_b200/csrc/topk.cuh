@@ -109,7 +109,9 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
                  const T* __restrict__ corpus,        // [N, H]
                  int nq, long long N, int H, int k,
                  float* __restrict__ part_score,      // [gridDim.x, nq, k]
-                 int64_t* __restrict__ part_index) {
+                 int64_t* __restrict__ part_index,
+                 const int* __restrict__ run_flag = nullptr) {   // non-null: do nothing unless *run_flag != 0
+  if (run_flag != nullptr && *run_flag == 0) return;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* qs = reinterpret_cast<float*>(smem_raw);
   float* set_score = qs + static_cast<size_t>(nq) * H;
@@ -222,7 +224,8 @@ topk_scan_kernel(const float* __restrict__ queries,   // [nq, H] (this pass's qu
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_merge_kernel(const float* __restrict__ part_score, const int64_t* __restrict__ part_index, int parts,
                   int nq, int k, float* __restrict__ out_score, int64_t* __restrict__ out_index,
-                  int out_stride) {
+                  int out_stride, const int* __restrict__ run_flag = nullptr) {
+  if (run_flag != nullptr && *run_flag == 0) return;
   __shared__ float s_score[TOPK_MAX_K];
   __shared__ int64_t s_index[TOPK_MAX_K];
   __shared__ float s_kth;

@@ -11,7 +11,7 @@ Mirrors the float32 / exact branch of distllm/rag/search.py:
                                             tokenizer(padding=True, truncation=True), encode, pool, fp32)
 
 The index itself is the device-resident matrix: no faiss file.  ``precision='float32'`` is the exact
-IndexFlatIP search (``b2e_topk_ip``); ``precision='ubinary'`` is the reference's binary branch
+IndexFlatIP search (``b2e_topk_ip`` / ``b2e_topk_ip_tc``: TF32 scan on the tensor cores, exact fp32 decision); ``precision='ubinary'`` is the reference's binary branch
 (search.py:34-56, :202-260, :280-336: packbits(x > 0) corpus, Hamming top-(k * rescore_multiplier), float
 rescoring) on ``b2e_pack_ubinary`` / ``b2e_search_ubinary``, 1/32 of the HBM traffic per query.  The HNSW
 (approximate) branch is not built -- ``search_algorithm='hnsw'`` raises.  There is no CPU fallback.
@@ -91,6 +91,11 @@ class ExactIndex:
         dtype = torch.float32 if self.config.corpus_dtype == 'float32' else torch.bfloat16
         self.corpus = matrix.to(device=dev, dtype=dtype).contiguous()
         self.embedding_size = matrix.shape[1]
+        # bound of the row norms: sizes the TF32 margin of the tensor-core scan (b2e_topk_ip_tc).  Computed once
+        # here, a hair above the measured maximum; None (bf16 corpus, odd widths) keeps the CUDA-core scan.
+        self.max_norm = None
+        if dtype == torch.float32 and matrix.shape[0] > 0 and matrix.shape[1] % 128 == 0:
+            self.max_norm = _native.max_row_norm(self.corpus) * 1.0001
 
     def __len__(self) -> int:
         return self.corpus.shape[0]
@@ -116,7 +121,7 @@ class ExactIndex:
                 raise _native.NativeError('ubinary search: more rows tie at the threshold Hamming distance than '
                                           'the candidate buffer holds (duplicate corpus rows?)')
         else:
-            scores, indices = _native.topk_ip(queries, self.corpus, top_k)
+            scores, indices = _native.topk_ip(queries, self.corpus, top_k, max_norm=self.max_norm)
         scores, indices = scores.cpu(), indices.cpu()
         total_scores, total_indices = [], []
         for s_row, i_row in zip(scores.tolist(), indices.tolist()):

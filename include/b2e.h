@@ -21,7 +21,8 @@
  *   b2e_pool_last_token     distllm/embed/poolers/last_token.py:12-39
  *   b2e_l2_normalize        distllm/embed/embedders/full_sequence.py:68-69 (F.normalize)
  *   b2e_adjacent_cosine_dist distllm/embed/embedders/semantic_chunk.py:24-55
- *   b2e_topk_ip             distllm/rag/search.py:280-336 (exact float32 search of the query path)
+ *   b2e_topk_ip / b2e_topk_ip_tc / b2e_max_row_norm
+ *                           distllm/rag/search.py:280-336 (exact float32 search of the query path)
  *   b2e_gemm_h16 / b2e_attention_d64 / b2e_attention_causal_d128 / b2e_layernorm: the building
  *                           blocks, exported so the parity tests can pin each kernel separately.
  */
@@ -169,6 +170,17 @@ int b2e_attention_causal_d128(const void* qkv, const int64_t* attention_mask, vo
  * index); when N < k the tail is filled with -inf / -1. */
 int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtype, int64_t N, int H,
                 int k, float* out_scores, int64_t* out_indices, void* stream);
+/* The same search for a float32 corpus with the scan on the tensor cores (TF32) and the decision on exact fp32
+ * dot products of the few rows the approximation cannot rule out; identical contract and results (a query whose
+ * candidates do not fit the 4096-row buffer makes the call fall back to b2e_topk_ip's scan on the device).
+ * corpus_max_norm >= the Euclidean norm of every corpus row (1 for L2-normalised embeddings; b2e_max_row_norm
+ * computes it once when the index is built): it sizes the error margin.  Problems below 32 768 rows go straight
+ * to b2e_topk_ip.  N < 4e9. */
+int b2e_topk_ip_tc(const float* queries, int Q, const float* corpus, int64_t N, int H, int k,
+                   float corpus_max_norm, float* out_scores, int64_t* out_indices, void* stream);
+/* Largest Euclidean row norm of a device-resident float32 [N,H] matrix -> *out_host (synchronises `stream`:
+ * an index-build step).  H % 4 == 0. */
+int b2e_max_row_norm(const float* x, int64_t N, int H, float* out_host, void* stream);
 /* Binary retrieval (distllm/rag/search.py, precision='ubinary', search_algorithm='exact'):
  * b2e_pack_ubinary = sentence_transformers quantize_embeddings(x, 'ubinary') as called from search.py:34-56
  * (np.packbits(x > 0): eight dimensions per byte, first dimension in the most significant bit), fp32

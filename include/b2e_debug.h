@@ -28,6 +28,8 @@ int b2e_debug_set_att3_flags(int flags);
  * on the attended tokens only (csrc/pack.cuh).  Drops the handle's cached CUDA graphs' validity: call it before
  * b2e_embed_host, not between its batches. */
 int b2e_debug_set_packing(int on);
+/* *out = 1 when this thread's last b2e_topk_ip_tc call had to fall back to the exact scan (synchronises the device) */
+int b2e_debug_topk_tc_fell_back(int* out);
 /* which instantiated softmax variant of attention3_d64_kernel<V> the next launches use (also B2E_ATT3) */
 int b2e_debug_set_att3_variant(int variant);
 /* CTA-pair GEMM: bit 0 = skip the epilogue's math and stores (experiment) */

@@ -323,6 +323,28 @@ def test_attention_causal_d128_many_items_and_rescale(dev, h16):
 
 
 # ---------------------------------------------------------------------------- exact inner-product top-k
+def check_topk_against_oracle(queries, corpus, k, scores, idx, atol=2e-5):
+    from oracle import search as osearch
+
+    q = queries.shape[0]
+    ref_s, ref_i = osearch.topk_inner_product(queries.cpu().numpy(), corpus.float().cpu().numpy(), k)
+    kk = ref_s.shape[1]
+    got_s, got_i = scores.cpu().numpy(), idx.cpu().numpy()
+    # scores: fp32 dot products in a different summation order
+    np.testing.assert_allclose(got_s[:, :kk], ref_s, rtol=0, atol=atol)
+    assert (np.diff(got_s[:, :kk], axis=1) <= 0).all()
+    if kk < k:   # fewer rows than k: the tail is marked empty
+        assert (got_i[:, kk:] == -1).all() and np.isinf(got_s[:, kk:]).all()
+    # indices: identical wherever the oracle's neighbouring scores are not within rounding of each other
+    full = queries.cpu().numpy().astype(np.float64) @ corpus.float().cpu().numpy().astype(np.float64).T
+    for r in range(q):
+        assert len(set(got_i[r, :kk].tolist())) == kk
+        np.testing.assert_allclose(full[r, got_i[r, :kk]], ref_s[r], rtol=0, atol=atol)
+        clear = np.abs(np.diff(ref_s[r])) > 5 * atol
+        stable = np.concatenate([[True], clear]) & np.concatenate([clear, [True]])
+        assert (got_i[r, :kk][stable] == ref_i[r][stable]).all()
+
+
 @pytest.mark.parametrize('q,n,h,k', [(1, 1000, 768, 10), (7, 5000, 768, 100), (16, 20000, 768, 5),
                                      (33, 3000, 256, 64), (3, 17, 128, 8), (2, 5, 768, 10),
                                      (5, 40000, 1280, 256), (4, 2000, 4096, 20), (1, 1, 768, 1)])
@@ -341,22 +363,60 @@ def test_topk_inner_product_matches_oracle(dev, q, n, h, k, dtype):
     queries = queries / queries.norm(dim=1, keepdim=True)
     corpus = corpus.to(dtype).contiguous()
     scores, idx = nv.topk_ip(queries, corpus, k)
-    ref_s, ref_i = osearch.topk_inner_product(queries.cpu().numpy(), corpus.float().cpu().numpy(), k)
-    kk = ref_s.shape[1]
-    got_s, got_i = scores.cpu().numpy(), idx.cpu().numpy()
-    # scores: fp32 dot products in a different summation order
-    np.testing.assert_allclose(got_s[:, :kk], ref_s, rtol=0, atol=2e-5)
-    assert (np.diff(got_s[:, :kk], axis=1) <= 0).all()
-    if kk < k:   # fewer rows than k: the tail is marked empty
-        assert (got_i[:, kk:] == -1).all() and np.isinf(got_s[:, kk:]).all()
-    # indices: identical wherever the oracle's neighbouring scores are not within rounding of each other
-    full = queries.cpu().numpy().astype(np.float64) @ corpus.float().cpu().numpy().astype(np.float64).T
-    for r in range(q):
-        assert len(set(got_i[r, :kk].tolist())) == kk
-        np.testing.assert_allclose(full[r, got_i[r, :kk]], ref_s[r], rtol=0, atol=2e-5)
-        clear = np.abs(np.diff(ref_s[r])) > 1e-4
-        stable = np.concatenate([[True], clear]) & np.concatenate([clear, [True]])
-        assert (got_i[r, :kk][stable] == ref_i[r][stable]).all()
+    check_topk_against_oracle(queries, corpus, k, scores, idx)
+
+
+@pytest.mark.parametrize('q,n,h,k', [(1, 40000, 768, 10), (16, 100000, 768, 100), (5, 70001, 1280, 256),
+                                     (33, 50000, 256, 64), (3, 32768, 128, 1), (7, 33000, 4096, 20)])
+@pytest.mark.parametrize('normalised', [True, False])
+def test_topk_tensor_core_scan_matches_oracle(dev, q, n, h, k, normalised):
+    """b2e_topk_ip_tc: TF32 scan on the tensor cores, exact fp32 decision -- the SAME contract as b2e_topk_ip."""
+    g = torch.Generator(device=dev).manual_seed(q * 17 + n + k)
+    corpus = torch.randn(n, h, device=dev, generator=g)
+    queries = torch.randn(q, h, device=dev, generator=g)
+    if normalised:
+        corpus = corpus / corpus.norm(dim=1, keepdim=True)
+        queries = queries / queries.norm(dim=1, keepdim=True)
+        atol = 2e-5
+    else:   # row norms spread over a factor of four: the margin is sized by the LARGEST norm
+        corpus = corpus * (0.5 + 1.5 * torch.rand(n, 1, device=dev, generator=g))
+        atol = 2e-5 * float(corpus.norm(dim=1).max() * queries.norm(dim=1).max())
+    corpus = corpus.contiguous()
+    max_norm = nv.max_row_norm(corpus)
+    assert abs(max_norm - float(corpus.norm(dim=1).max())) <= 1e-5 * max_norm
+    scores, idx = nv.topk_ip(queries, corpus, k, max_norm=max_norm)
+    # normalised rows (what the reference indexes: faiss.normalize_L2, search.py:258-278) must stay on the fast
+    # path; with spread-out norms the one global bound may be too loose and the call may redo itself exactly
+    if normalised:
+        assert not nv.topk_tc_fell_back()
+    check_topk_against_oracle(queries, corpus, k, scores, idx, atol=atol)
+    # and the two paths agree with each other far inside the oracle tolerance
+    s2, i2 = nv.topk_ip(queries, corpus, k)
+    assert torch.allclose(scores, s2, rtol=0, atol=atol / 4)
+    same = (idx == i2).float().mean().item()
+    assert same > 0.98, same
+
+
+def test_topk_tensor_core_scan_falls_back_on_degenerate_corpus(dev):
+    """Thousands of rows tie with the k-th best (a corpus of duplicates): the candidate buffer overflows, the call
+    is redone by the exact scan on the device -- same scores as b2e_topk_ip bit for bit (WHICH of thousands of
+    identical rows are named is not defined by either scan)."""
+    g = torch.Generator(device=dev).manual_seed(5)
+    base = torch.randn(8, 768, device=dev, generator=g)
+    base = base / base.norm(dim=1, keepdim=True)
+    corpus = base.repeat(6000, 1).contiguous()      # 48 000 rows, 8 distinct
+    queries = torch.randn(3, 768, device=dev, generator=g)
+    scores, idx = nv.topk_ip(queries, corpus, 10, max_norm=1.0)
+    assert nv.topk_tc_fell_back()
+    s2, i2 = nv.topk_ip(queries, corpus, 10)
+    assert torch.equal(scores, s2) and torch.equal(idx % 8, i2 % 8)
+    assert all(len(set(row.tolist())) == 10 for row in idx.cpu())
+    best = (queries @ base.T).argmax(dim=1)
+    assert torch.equal((idx[:, 0] % 8).cpu(), best.cpu())
+    # a too-small norm bound can only shrink the margin, never corrupt memory; with the true bound it is exact
+    corpus2 = torch.randn(40000, 768, device=dev, generator=g)
+    s3, i3 = nv.topk_ip(queries, corpus2, 10, max_norm=nv.max_row_norm(corpus2))
+    check_topk_against_oracle(queries, corpus2, 10, s3, i3, atol=2e-5 * 28 * float(queries.norm(dim=1).max()))
 
 
 def test_topk_rejects_bad_arguments(dev):

@@ -1,5 +1,7 @@
 """Exact inner-product top-k over a device-resident embedding matrix (retrieval query path): time per
 search and achieved HBM bandwidth (algorithmic bytes = one read of the corpus per query tile of 16).
+Both scans for a float32 corpus: "fma" = b2e_topk_ip (CUDA cores), "tf32" = b2e_topk_ip_tc (tensor-core scan +
+exact fp32 decision; results checked equal to the first on every configuration).
 usage: bench_topk.py [N] [H]"""
 import json, sys
 from pathlib import Path
@@ -18,16 +20,26 @@ for dtype in (torch.float32, torch.bfloat16):
     for q, k in [(1, 10), (4, 10), (16, 10), (16, 100), (64, 10)]:
         queries = torch.randn(q, H, device=dev, generator=g)
         queries = queries / queries.norm(dim=1, keepdim=True)
-        for _ in range(2): nv.topk_ip(queries, corpus, k)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5): nv.topk_ip(queries, corpus, k)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        passes = (q + 15) // 16
-        gbs = passes * N * H * corpus.element_size() / ms / 1e6
-        print(json.dumps({'N': N, 'H': H, 'corpus': str(dtype).split('.')[-1], 'queries': q, 'k': k, 'ms': round(ms, 3),
-                          'queries_per_s': round(q / ms * 1e3, 1), 'corpus_GBps': round(gbs, 1),
-                          'frac_of_hbm': round(gbs / hbm, 3)}), flush=True)
+        ref = None
+        for scan in (('fma', 'tf32') if dtype == torch.float32 else ('fma',)):
+            kw = {'max_norm': 1.0001} if scan == 'tf32' else {}
+            for _ in range(2): out = nv.topk_ip(queries, corpus, k, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5): nv.topk_ip(queries, corpus, k, **kw)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            passes = (q + 15) // 16
+            gbs = passes * N * H * corpus.element_size() / ms / 1e6
+            rec = {'N': N, 'H': H, 'corpus': str(dtype).split('.')[-1], 'scan': scan, 'queries': q, 'k': k,
+                   'ms': round(ms, 3), 'queries_per_s': round(q / ms * 1e3, 1), 'corpus_GBps': round(gbs, 1),
+                   'frac_of_hbm': round(gbs / hbm, 3)}
+            if scan == 'fma':
+                ref = out
+            else:
+                rec['fell_back'] = nv.topk_tc_fell_back()
+                rec['same_indices_as_fma'] = round((out[1] == ref[1]).float().mean().item(), 5)
+                rec['max_score_diff'] = float((out[0] - ref[0]).abs().max())
+            print(json.dumps(rec), flush=True)
     del corpus
