@@ -444,6 +444,37 @@ def extra_esm2(device, peaks: dict, reduce_max) -> dict:
                          'flops_per_sequence': flops_per_chunk(ESM2_650M, s)}}
 
 
+def extra_retrieval(device, peaks: dict) -> dict:
+    """SURVEY 8(f) rank 2, the consumer of the gathered matrix: exact inner-product search of 16 queries, k = 100,
+    over a device-resident 1 M x 768 float32 matrix (3.1 GB: far beyond L2) -- CUDA-core scan vs the tensor-core
+    scan with exact fp32 decision; both must name the same rows."""
+    from distllm_b200 import _native as nv
+
+    n, h, q, k = 1_000_000, 768, 16, 100
+    g = torch.Generator(device=device).manual_seed(3)
+    corpus = torch.randn(n, h, device=device, generator=g)
+    corpus = (corpus / corpus.norm(dim=1, keepdim=True)).contiguous()
+    queries = torch.randn(q, h, device=device, generator=g)
+    queries = queries / queries.norm(dim=1, keepdim=True)
+    max_norm = nv.max_row_norm(corpus) * 1.0001
+    out = {'workload': f'{q} queries, k={k}, corpus {n} x {h} float32 L2-normalised rows on the device',
+           'algorithmic_bytes': n * h * 4, 'hbm_peak_gbs': peaks['hbm_gbs']}
+    ref = None
+    for name, kw in (('cuda_core_scan', {}), ('tensor_core_scan', {'max_norm': max_norm})):
+        res = nv.topk_ip(queries, corpus, k, **kw)
+        ms = timed_steps(lambda: nv.topk_ip(queries, corpus, k, **kw), 5, 2, device)
+        gbs = n * h * 4 / ms / 1e6
+        out[name] = {'ms': ms, 'queries_per_s': q / ms * 1e3, 'gb_per_s': gbs, 'frac_of_hbm': gbs / peaks['hbm_gbs']}
+        if ref is None:
+            ref = res
+        else:
+            out[name]['same_rows_as_cuda_core_scan'] = bool(torch.equal(res[1], ref[1]))
+            out[name]['fell_back_to_exact_scan'] = nv.topk_tc_fell_back()
+    del corpus
+    torch.cuda.empty_cache()
+    return out
+
+
 def extra_mistral(device, peaks: dict, reduce_max) -> dict:
     """BASELINE C3: SFR-Embedding-Mistral shape (Mistral-7B), last_token pooler, batch 16, S=4096."""
     from transformers import MistralConfig
@@ -713,6 +744,8 @@ def run_native(args) -> None:
         extra['c3_mistral7b'] = extra_mistral(device, peaks, reduce_max)
         extra['c3_mistral7b']['value'] = world * extra['c3_mistral7b']['value_per_gpu']
         extra.update(extra_worker(device, rank, world, reduce_max, do_c1=(world == 1)))
+        if rank == 0:
+            extra['retrieval'] = extra_retrieval(device, peaks)
 
     if rank == 0:
         fpc = flops_per_chunk(BERT_BASE, SEQ)

@@ -17,6 +17,7 @@
 
 #include "attention3.cuh"
 #include "attention4.cuh"
+#include "attention5.cuh"
 #include "binsearch.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -397,6 +398,16 @@ template <int V>
 int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnScratch& sc,
                        const CUtensorMap& tctx, void* ctx, const SeqLayout& lay, int B, int S, int heads,
                        int grid, float scale_log2e, cudaStream_t st, int window = 0) {
+  if constexpr ((V & 64) != 0) {   // four softmax warpgroups, chunks split by key columns (attention5.cuh)
+    auto kern5 = attention5_d64_kernel<(V & ~64)>;
+    const int arc5 = ensure_smem_attr(kern5, AT3_SMEM_BYTES);
+    if (arc5) return arc5;
+    kern5<<<grid, AT5_THREADS, AT3_SMEM_BYTES, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
+                                                     attn_s_pad(S), heads, scale_log2e, window, lay.cu, lay.len,
+                                                     static_cast<h16*>(ctx));
+    CUDA_TRY(cudaGetLastError());
+    return B2E_OK;
+  }
   auto kern = attention3_d64_kernel<V>;
   const int arc = ensure_smem_attr(kern, AT3_SMEM_BYTES);
   if (arc) return arc;
@@ -419,8 +430,11 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   CUtensorMap tctx;  // [B*S, H]: full 128-row tiles leave through TMA, a sequence's partial last tile row by row
   int rc;
   if ((rc = make_tmap_h16(&tctx, ctx, (uint64_t)B * S, (uint64_t)heads * AT3_D, 128))) return rc;
-  if (window > 0)
+  if (window > 0) {
+    if (att3_variant() & 64)
+      return launch_attention_v<64 + 17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
     return launch_attention_v<17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
+  }
   switch (att3_variant()) {
     case 0: return launch_attention_v<0>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 1: return launch_attention_v<1>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
@@ -433,8 +447,12 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
     case 37: return launch_attention_v<37>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 41: return launch_attention_v<41>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 45: return launch_attention_v<45>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 64: return launch_attention_v<64>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 65: return launch_attention_v<65>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 69: return launch_attention_v<69>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 73: return launch_attention_v<73>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
   }
-  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45)",
+  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45,64,65,69,73)",
               att3_variant());
 }
 

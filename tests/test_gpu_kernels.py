@@ -65,6 +65,20 @@ def test_gemm_rejects_bad_shapes(dev, h16):
                      torch.zeros(100, 64, device=dev, dtype=h16), torch.zeros(100, device=dev))
 
 
+@pytest.fixture(params=[None, 69, 64], ids=['shipping', 'split4-poly', 'split4'])
+def att_variant(request, h16):
+    """Which head_dim-64 attention kernel the calls of a test reach: the library's default, or the
+    four-warpgroup kernel of attention5.cuh (variant bit 6) with / without the polynomial exponentials."""
+    import ctypes
+
+    lib = nv.load(nv.storage_of(h16))
+    lib.b2e_debug_set_att3_variant.argtypes = [ctypes.c_int]
+    if request.param is not None:
+        assert lib.b2e_debug_set_att3_variant(request.param) == 0
+    yield request.param
+    lib.b2e_debug_set_att3_variant(-1)   # back to B2E_ATT3 / the built-in default
+
+
 def ref_attention(qkv, mask, b, s, heads):
     q, k, v = qkv.float().view(b, s, 3, heads, 64).unbind(2)
     q, k, v = (t.permute(0, 2, 1, 3) for t in (q, k, v))
@@ -79,7 +93,7 @@ def ref_attention(qkv, mask, b, s, heads):
                                               (2, 512, 12, True), (4, 37, 4, True), (5, 1, 4, False),
                                               (2, 129, 4, True), (1, 384, 12, True), (2, 640, 2, False),
                                               (1, 1026, 4, True), (3, 257, 2, True)])
-def test_attention_matches_reference(dev, b, s, heads, ragged, h16):
+def test_attention_matches_reference(dev, b, s, heads, ragged, h16, att_variant):
     g = torch.Generator(device=dev).manual_seed(b * 1000 + s)
     qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(h16)
     mask = torch.ones(b, s, dtype=torch.int64, device=dev)
@@ -90,7 +104,7 @@ def test_attention_matches_reference(dev, b, s, heads, ragged, h16):
     close(ctx.float(), ref_attention(qkv, mask, b, s, heads), h16, 2.0)
 
 
-def test_attention_mask_with_holes_and_fully_masked_row(dev, h16):
+def test_attention_mask_with_holes_and_fully_masked_row(dev, h16, att_variant):
     """Arbitrary 0/1 masks (left padding, holes); an all-zero mask degenerates to a uniform
     distribution over the S keys exactly like HF's additive most-negative-finite mask."""
     b, s, heads = 3, 96, 4
@@ -106,7 +120,7 @@ def test_attention_mask_with_holes_and_fully_masked_row(dev, h16):
     close(ctx.float(), ref, h16, 2.0)
 
 
-def test_attention_many_items_per_cta(dev, h16):
+def test_attention_many_items_per_cta(dev, h16, att_variant):
     """More work items than SMs: the persistent CTAs recycle Q buffers, ring stages and TMEM slots."""
     b, s, heads = 40, 300, 12
     g = torch.Generator(device=dev).manual_seed(77)
@@ -120,7 +134,7 @@ def test_attention_many_items_per_cta(dev, h16):
     assert torch.isfinite(ctx.float()).all()
 
 
-def test_attention_large_scores_trigger_rescale(dev, h16):
+def test_attention_large_scores_trigger_rescale(dev, h16, att_variant):
     """Scores that grow along the key axis force the lazy online-softmax rescale path."""
     b, s, heads = 2, 512, 2
     g = torch.Generator(device=dev).manual_seed(78)
@@ -499,7 +513,7 @@ def test_gemm_geglu_epilogue(dev, m, i, k, h16):
 
 @pytest.mark.parametrize('b,s,heads,window', [(2, 512, 4, 64), (3, 333, 2, 64), (1, 1500, 2, 64), (2, 200, 4, 16),
                                               (2, 700, 2, 300)])
-def test_attention_d64_sliding_window(dev, b, s, heads, window, h16):
+def test_attention_d64_sliding_window(dev, b, s, heads, window, h16, att_variant):
     """Bidirectional sliding window |i - j| <= window (ModernBERT's local layers) on ragged batches; rows of
     padding tiles must stay finite."""
     g = torch.Generator(device=dev).manual_seed(b * 100 + s + window)

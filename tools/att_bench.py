@@ -2,7 +2,7 @@
 attention3_d64_kernel<V> (b2e_debug_set_att3_variant), each checked against an fp32 torch reference on a
 small problem and against variant 0 on the timed one.
 
-usage: att_bench.py [variants, comma separated; default 0,1,5,33,37,41,45]
+usage: att_bench.py [variants, comma separated; default 0,5,64,65,69,73]
 """
 import ctypes
 import sys
@@ -16,7 +16,7 @@ from distllm_b200 import _native as nv  # noqa: E402
 dev = torch.device('cuda:0')
 lib = nv.load()
 lib.b2e_debug_set_att3_variant.argtypes = [ctypes.c_int]
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '0,1,5,33,37,41,45').split(',')]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '0,5,64,65,69,73').split(',')]
 # optional second argument: scheduling flags (b2e_debug_set_att3_flags) to run every variant with, e.g. "2,6"
 flag_sets = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [None]
 lib.b2e_debug_set_att3_flags.argtypes = [ctypes.c_int]
