@@ -12,7 +12,7 @@
 // sum, own accumulator O_h = sum_j P_j[:, half h] V_j[half h, :]); the two partial results of a row are merged
 // once per tile, in the epilogue, exactly like split-K flash decoding:
 //     M = max(m_0, m_1),  O = (O_0 2^(m_0 - M) + O_1 2^(m_1 - M)) / (l_0 2^(m_0 - M) + l_1 2^(m_1 - M)).
-// No per-chunk communication between the halves; a thread keeps 32 scores instead of 64 (104 registers).
+// No per-chunk communication between the halves; a thread keeps 32 scores instead of 64 (96 registers).
 //
 //   warps 0-3 / 4-7     softmax of query tile A (slot 0), keys [0,32) / [32,64) of every chunk
 //   warps 8-11 / 12-15  softmax of query tile B (slot 1), keys [0,32) / [32,64)
@@ -64,9 +64,8 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
   const uint32_t o_ready = pv_done + 64;               // [2 slot]
   const uint32_t o_empty = o_ready + 16;               // [2 slot]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + AT3_SMEM_BAR + 384);
-  // (m, l) of every row and half, exchanged once per tile: [2 slot][2 half][128] float2 = 4 KiB, kept in the first
-  // rows of the bias ring's LAST stage?  No: the ring is live.  The exchange lives in the output staging tile of the
-  // slot (16 KiB, written only after the exchange has been read).
+  // (m, l) of every row and half are exchanged once per tile through the slot's output staging tile (2 KiB of its
+  // 16 KiB; the staging rows are written only after every thread has read the exchange).
   if (warp == 16) {
     if (elect_one()) {
       tma_prefetch_desc(&tm_q);
@@ -109,8 +108,10 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     }                                                                  \
   } while (0)
 
+  // No setmaxnreg here: the whole kernel compiles to the 96 registers that 608 threads leave per thread, so there
+  // is nothing to hand from the single-thread roles to the softmax warps (and a setmaxnreg.inc that the register
+  // file cannot satisfy never returns).
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 17) {
       if (elect_one()) {
         // ------------------------------------------------------------ loader (as attention3)
@@ -240,7 +241,6 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     }
   } else {
     // -------------------------------------------------------------- softmax warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int slot = warp >> 3;
     const int half = (warp >> 2) & 1;
     const int r = threadIdx.x & 127;
