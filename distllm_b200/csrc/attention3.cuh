@@ -233,16 +233,44 @@ struct At3Raw {
   int n, np, row0, len;   // loaded: key chunks, plain chunks, first row, rows
   int ok;                 // item < n_items
 };
-__device__ __forceinline__ At3Raw at3_fetch(int item, int npairs, int heads, const int* __restrict__ kv_chunks,
+// Position of a CTA's current work item, advanced by gridDim.x per step WITHOUT divisions: three integer divisions
+// by run-time values are ~450 clk of dependent instructions for a single thread, and every role paid them between
+// two items (the ~700-800 clk gap between an item's last event and the next item's first in
+// profiles/r02_att3_timeline_*.log).
+struct At3Walk {
+  int item, pr, h, b;   // item = (b * heads + h) * npairs + pr
+  int G, gr, gh, gb;    // the stride gridDim.x in the same mixed radix
+  __device__ __forceinline__ void init(int first, int stride, int npairs, int heads) {
+    item = first;
+    pr = first % npairs;
+    const int bh = first / npairs;
+    h = bh % heads;
+    b = bh / heads;
+    G = stride;
+    gr = stride % npairs;
+    const int gq = stride / npairs;
+    gh = gq % heads;
+    gb = gq / heads;
+  }
+  __device__ __forceinline__ void step(int npairs, int heads) {
+    item += G;
+    pr += gr;
+    int c = pr >= npairs ? 1 : 0;
+    pr -= c ? npairs : 0;
+    h += gh + c;
+    c = h >= heads ? 1 : 0;
+    h -= c ? heads : 0;
+    b += gb + c;
+  }
+};
+__device__ __forceinline__ At3Raw at3_fetch(const At3Walk& w, const int* __restrict__ kv_chunks,
                                             const int* __restrict__ plain_chunks, int n_items, int S,
                                             const int* __restrict__ seq_cu, const int* __restrict__ seq_len) {
   At3Raw r;
-  r.ok = item < n_items;
-  const int it = r.ok ? item : 0;   // always a valid index: the loads need no branch
-  r.pr = it % npairs;
-  const int bh = it / npairs;
-  r.h = bh % heads;
-  r.b = bh / heads;
+  r.ok = w.item < n_items;
+  r.pr = r.ok ? w.pr : 0;
+  r.h = r.ok ? w.h : 0;
+  r.b = r.ok ? w.b : 0;   // always a valid index: the loads need no branch
   r.n = __ldg(kv_chunks + r.b);
   r.np = plain_chunks != nullptr ? __ldg(plain_chunks + r.b) : 0;
   // token layout (pack.cuh): rows [row0, row0 + len) hold the sequence; padded layout when seq_cu is null
@@ -383,9 +411,12 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t q_par = 0, q_any = 0;   // per (buf,slot) bit: (#loads so far) & 1 / #loads > 0
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+        At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+          wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = cur.row0;
           const int buf = it & 1;
@@ -436,9 +467,12 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+        At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+          wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int n = cur.n;
           const int buf = it & 1;
           const bool active = 2 * cur.pr + slot < cur.nq;
@@ -521,7 +555,9 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     // Item parameters are decoded one item AHEAD (two integer divisions and a dependent global load
     // cost ~2000 clk when they sit between two items; here they overlap the current item's work).
     int item = blockIdx.x;
-    At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+    At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
     // strict alternation A, B, A, B ...: both slots see the same number of chunks in every item
     // bit 0: strict ping-pong on every chunk (measured 3 % slower); bit 1: only the FIRST chunk of an item
     // is ordered (A before B), which merely de-phases the two warpgroups
@@ -531,7 +567,8 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     for (; item < n_items; item += gridDim.x) {
-      const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+      wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
       const int pr = cur.pr, h = cur.h, n = cur.n;
       const int t = 2 * pr + slot;
       if (t >= cur.nq && pingpong) {

@@ -119,9 +119,12 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t q_par = 0, q_any = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+        At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+          wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int pr = cur.pr, h = cur.h, b = cur.b;
           const int row_base = cur.row0;
           const int buf = it & 1;
@@ -167,9 +170,12 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
         uint32_t tile_cnt = 0;
         int it = 0;
         int item = blockIdx.x;
-        At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+        At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x, ++it) {
-          const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+          wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
           const int n = cur.n;
           const int buf = it & 1;
           const bool active = 2 * cur.pr + slot < cur.nq;
@@ -251,14 +257,17 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
     uint32_t s_par = 0;   // bit sbuf: parity of the s_ready[slot][sbuf] phase to wait for
     uint32_t o_cnt = 0;
     int item = blockIdx.x;
-    At3Item cur = at3_finish(at3_fetch(item, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
+    At3Walk wk;
+        wk.init(item, gridDim.x, npairs, heads);
+        At3Item cur = at3_finish(at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len), window);
     uint8_t* ostage = smem + AT3_SMEM_OST + slot * AT3_QTILE;
     const uint32_t ostage_addr = sb + AT3_SMEM_OST + slot * AT3_QTILE;
     // the (m, l) exchange of the slot: two float2 per row in the slot's staging tile (free until the merge)
     float2* xchg = reinterpret_cast<float2*>(ostage);
     const int stamp_role = slot;   // half 0 of each slot records the timeline
     for (; item < n_items; item += gridDim.x) {
-      const At3Raw nxt = at3_fetch(item + gridDim.x, npairs, heads, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
+      wk.step(npairs, heads);
+          const At3Raw nxt = at3_fetch(wk, kv_chunks, plain_chunks, n_items, S, seq_cu, seq_len);
       const int pr = cur.pr, h = cur.h, n = cur.n;
       const int t = 2 * pr + slot;
       if (t < cur.nq) {

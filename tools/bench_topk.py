@@ -43,3 +43,22 @@ for dtype in (torch.float32, torch.bfloat16):
                 rec['max_score_diff'] = float((out[0] - ref[0]).abs().max())
             print(json.dumps(rec), flush=True)
     del corpus
+
+# ---- the reference's binary branch (search.py:34-56, :202-336): packed sign bits, Hamming top-(k * multiplier), rescoring
+corpus = torch.randn(N, H, device=dev, generator=g)
+bits = nv.pack_ubinary(corpus.contiguous())
+del corpus
+for q, k, mult in [(1, 10, 2), (16, 10, 2), (16, 100, 2), (64, 10, 4)]:
+    queries = torch.randn(q, H, device=dev, generator=g)
+    for _ in range(2): nv.search_ubinary(queries, bits, k, mult)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): nv.search_ubinary(queries, bits, k, mult)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    passes = (q + 7) // 8
+    gbs = 2 * passes * N * (H // 8) / ms / 1e6     # histogram pass + select pass per tile of 8 queries
+    print(json.dumps({'N': N, 'H': H, 'corpus': 'ubinary', 'queries': q, 'k': k, 'rescore_multiplier': mult,
+                      'ms': round(ms, 3), 'queries_per_s': round(q / ms * 1e3, 1), 'packed_GBps': round(gbs, 1),
+                      'frac_of_hbm': round(gbs / hbm, 3)}), flush=True)
