@@ -93,14 +93,16 @@ __device__ __forceinline__ float at4_exp_pack(const uint32_t (&s)[32], const flo
 struct At4Item {
   int b, h, pr, lo[2], hi[2], hi_u;
   int np;   // leading key chunks of the sequence whose 64 keys are all attended
+  int row0, len;   // token layout (pack.cuh): rows [row0, row0 + len) hold the sequence; b * S and S when padded
 };
 // Two steps, like attention3.cuh's at3_fetch / at3_finish: the next item's per-sequence numbers are loaded at
 // the top of the current item and first touched at its end (warps issue in order).
 struct At4Raw {
-  int b, h, pr, kvc, np, ok;
+  int b, h, pr, kvc, np, ok, row0, len;
 };
 __device__ __forceinline__ At4Raw at4_fetch(int item, int npairs, int heads, const int* __restrict__ kv_chunks,
-                                            int n_items, int bh_total,
+                                            int n_items, int bh_total, int S, const int* __restrict__ seq_cu,
+                                            const int* __restrict__ seq_len,
                                             const int* __restrict__ plain_chunks = nullptr) {
   At4Raw r;
   r.ok = item < n_items;
@@ -111,16 +113,21 @@ __device__ __forceinline__ At4Raw at4_fetch(int item, int npairs, int heads, con
   r.b = bh / heads;
   r.kvc = __ldg(kv_chunks + r.b);
   r.np = plain_chunks != nullptr ? __ldg(plain_chunks + r.b) : 0;
+  r.row0 = seq_cu != nullptr ? __ldg(seq_cu + r.b) : r.b * S;
+  r.len = seq_len != nullptr ? __ldg(seq_len + r.b) : S;
   return r;
 }
-__device__ __forceinline__ At4Item at4_finish(At4Raw r, int nq, int window) {
-  asm volatile("" : "+r"(r.kvc), "+r"(r.np));
-  At4Item it{0, 0, 0, {0, 0}, {0, 0}, 0, 0};
+__device__ __forceinline__ At4Item at4_finish(At4Raw r, int window) {
+  asm volatile("" : "+r"(r.kvc), "+r"(r.np), "+r"(r.row0), "+r"(r.len));
+  At4Item it{0, 0, 0, {0, 0}, {0, 0}, 0, 0, 0, 0};
   if (r.ok) {
     it.pr = r.pr;
     it.h = r.h;
     it.b = r.b;
     it.np = r.np;
+    it.row0 = r.row0;
+    it.len = r.len;
+    const int nq = (r.len + 127) / 128;   // query tiles of THIS sequence (tiles behind it belong to the next one)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int t = 2 * it.pr + s;
@@ -142,9 +149,12 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
                               const float* __restrict__ bias,             // [B, S_pad]
                               const int* __restrict__ kv_chunks,          // [B]
                               const int* __restrict__ plain_chunks,       // [B] or nullptr
-                              const __grid_constant__ CUtensorMap tm_ctx, // [B, S, heads*128], box 64 x 128 x 1
+                              const __grid_constant__ CUtensorMap tm_ctx, // [T, heads*128], box 64 x 128 (full tiles)
                               int B, int S, int S_pad, int heads, int kv_heads, int window,
-                              float scale_log2e) {
+                              float scale_log2e,
+                              const int* __restrict__ seq_cu,    // [B] first row of each sequence, or nullptr (= b*S)
+                              const int* __restrict__ seq_len,   // [B] rows of each sequence, or nullptr (= S)
+                              h16* __restrict__ ctx_out) {       // [T, heads*128]: partial last tiles, row by row
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if ((sb & 1023u) != 0) __trap();
@@ -207,12 +217,12 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         uint32_t chunk_ctr = 0;       // ring position, runs across items
         uint32_t q_loads[2] = {0, 0}; // Q tiles loaded so far per slot
         int item = blockIdx.x;
-        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total), nq, window);
+        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x) {
-          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total);
-          const int row_base = cur.b * S;
+          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len);
+          const int row_base = cur.row0;
           const int hk = cur.h / group;
-          const int n_active = (cur.hi[1] > 0) ? 2 : 1;
+          const int n_active = (cur.hi[0] > 0 ? 1 : 0) + (cur.hi[1] > 0 ? 1 : 0);   // slot 1 implies slot 0
           int q_pending = n_active;   // slots [n_active - q_pending, n_active) still need their Q tile
           // Q tile of a slot: its buffer is free once the last Q K^T of the previous tile completed.
           auto try_q = [&](bool block) {
@@ -254,7 +264,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
                          bias + static_cast<size_t>(cur.b) * S_pad + j * AT4_KC, AT4_KC * 4, fb);
           }
           try_q(true);
-          cur = at4_finish(nxt, nq, window);
+          cur = at4_finish(nxt, window);
         }
       }
     } else if (warp == 8 || warp == 10) {
@@ -274,9 +284,9 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
         uint32_t p_par = 0;        // bit sbuf: parity of the p_ready phase to wait for
         uint32_t tile_cnt = 0;
         int item = blockIdx.x;
-        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total), nq, window);
+        At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len), window);
         for (; item < n_items; item += gridDim.x) {
-          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total);
+          const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len);
           const int n_u = cur.hi_u - cur.lo[0];
           const int my_lo = slot ? cur.lo[1] : cur.lo[0];
           const int my_hi = slot ? cur.hi[1] : cur.hi[0];
@@ -345,7 +355,7 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
           }
           for (int c = c_hi; c < n_u; ++c) pass_on(c);
           chunk_base += static_cast<uint32_t>(n_u);
-          cur = at4_finish(nxt, nq, window);
+          cur = at4_finish(nxt, window);
         }
       }
     }
@@ -361,11 +371,11 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
     uint32_t s_par = 0;   // bit sbuf: parity of the s_ready[slot][sbuf] phase to wait for
     uint32_t o_cnt = 0;
     int item = blockIdx.x;
-    At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total, plain_chunks), nq, window);
+    At4Item cur = at4_finish(at4_fetch(item, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len, plain_chunks), window);
     uint8_t* ostage = smem + AT4_SMEM_OST + slot * AT4_QSLAB;
     const uint32_t ostage_addr = sb + AT4_SMEM_OST + slot * AT4_QSLAB;
     for (; item < n_items; item += gridDim.x) {
-      const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total, plain_chunks);
+      const At4Raw nxt = at4_fetch(item + gridDim.x, npairs, heads, kv_chunks, n_items, bh_total, S, seq_cu, seq_len, plain_chunks);
       const int t = 2 * cur.pr + slot;
       const int lo = slot ? cur.lo[1] : cur.lo[0];
       const int hi = slot ? cur.hi[1] : cur.hi[0];
@@ -506,15 +516,26 @@ attention4_d128_causal_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T,
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
-          if (r == 0) {
-            // rows >= S of the last tile are clipped by the 3-D [B,S,H] tensor map
-            tma_store_3d(&tm_ctx, ostage_addr, cur.h * AT4_D + half * 64, t * 128, cur.b);
-            tma_store_commit();
+          const int valid = cur.len - t * 128;   // rows of this tile that belong to the sequence
+          if (valid >= 128) {
+            if (r == 0) {
+              tma_store_2d(&tm_ctx, ostage_addr, cur.h * AT4_D + half * 64, cur.row0 + t * 128);
+              tma_store_commit();
+            }
+          } else if (r < valid) {
+            // last, partial tile of the sequence: the rows behind it belong to the NEXT sequence or do not exist;
+            // every thread stores the row it staged itself
+            h16* dst = ctx_out + static_cast<size_t>(cur.row0 + t * 128 + r) * (heads * AT4_D) + cur.h * AT4_D +
+                       half * 64;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<uint4*>(dst + u * 8) =
+                  *reinterpret_cast<const uint4*>(ostage + r * 128 + ((u ^ (r & 7)) << 4));
           }
         }
       }
       chunk_base += static_cast<uint32_t>(cur.hi_u - cur.lo[0]);
-      cur = at4_finish(nxt, nq, window);
+      cur = at4_finish(nxt, window);
     }
     if (r == 0) tma_store_wait_all();
   }

@@ -115,25 +115,6 @@ int make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
   return B2E_OK;
 }
 
-// 3-D half [batch, rows, cols] tensor (contiguous), box = 64 columns x box_rows x 1: used for
-// per-sequence TMA stores that must clip at the end of EACH sequence, not only at the tensor end.
-int make_tmap_h16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows,
-                      uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[3] = {cols, rows, batch};
-  cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, B2E_TMAP_DTYPE, 3, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(B2E_ERR_CUDA, "cuTensorMapEncodeTiled 3d(batch=%llu, rows=%llu, cols=%llu) -> %d",
-                (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols, (int)r);
-  return B2E_OK;
-}
-
 struct DeviceInfo {
   int sms = 0;
   int cc_major = 0;
@@ -376,7 +357,10 @@ int attention_prepare(AttnScratch& sc, const int64_t* mask, int B, int S, cudaSt
 
 // Softmax variant of the head_dim-64 attention kernel (template parameter V of attention3_d64_kernel);
 // B2E_ATT3=<n> or b2e_debug_set_att3_variant picks one of the instantiated ones for A/B measurements.
-constexpr int AT3_DEFAULT_VARIANT = 5;   // plain-chunk count + one exponential in four on the FMA pipe (profiles/r02_att_bench_variants_v1.log)
+// 65 = four softmax warpgroups (attention5.cuh), fully attended chunks known from attn_prep: same-box A/B of the whole
+// step against 5 (two warpgroups + one exponential in four on the FMA pipe): C2 49.58 vs 49.81 ms, C5 100.6 vs 102.5 ms
+// (profiles/r02_step_ab_att5.log); both kernels pass the same tests.
+constexpr int AT3_DEFAULT_VARIANT = 65;
 int g_att3_variant = -1;
 inline int att3_variant() {
   if (g_att3_variant < 0) {
@@ -459,7 +443,8 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
 // Causal grouped-query attention, head_dim 128 (attention4.cuh).  qkv is [B*S, (heads + 2 kv_heads)*128]
 // with columns  q heads | k heads | v heads;  sc must have been prepared for (mask, B, S).
 int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, int B, int S, int heads,
-                                 int kv_heads, int window, int sms, cudaStream_t st) {
+                                 int kv_heads, int window, int sms, cudaStream_t st,
+                                 const SeqLayout& lay = SeqLayout()) {
   {
     const int arc = ensure_smem_attr(attention4_d128_causal_kernel, AT4_SMEM_BYTES);
     if (arc) return arc;
@@ -469,13 +454,15 @@ int launch_attention_causal_d128(const void* qkv, AttnScratch& sc, void* ctx, in
   int rc;
   if ((rc = make_tmap_h16(&tq, qkv, (uint64_t)B * S, ld, 128))) return rc;
   if ((rc = make_tmap_h16(&tkv, qkv, (uint64_t)B * S, ld, AT4_KC))) return rc;
-  if ((rc = make_tmap_h16_3d(&tctx, ctx, B, S, (uint64_t)heads * AT4_D, 128))) return rc;
+  // [B*S, heads*128]: full 128-row tiles leave through TMA, a sequence's partial last tile row by row
+  if ((rc = make_tmap_h16(&tctx, ctx, (uint64_t)B * S, (uint64_t)heads * AT4_D, 128))) return rc;
   const int nq = (S + 127) / 128;
   const long long items = (long long)B * heads * ((nq + 1) / 2);
   const int grid = items < sms ? (int)items : sms;
   const float scale_log2e = 0.08838834764831845f * 1.4426950408889634f;  // 128^-0.5 * log2(e)
   attention4_d128_causal_kernel<<<grid, AT4_THREADS, AT4_SMEM_BYTES, st>>>(
-      tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S, attn_s_pad(S), heads, kv_heads, window, scale_log2e);
+      tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S, attn_s_pad(S), heads, kv_heads, window,
+      scale_log2e, lay.cu, lay.len, static_cast<h16*>(ctx));
   CUDA_TRY(cudaGetLastError());
   return B2E_OK;
 }
@@ -907,13 +894,13 @@ int run_esm_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B,
 // (attention), :35-48 (MLP).  Like the ESM-2 trunk it leaves xres (before the last MLP output is
 // added) and e->tmp (that down_proj output); the caller applies the final norm to xres + tmp.
 int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, int B, int S,
-                      cudaStream_t st) {
+                      cudaStream_t st, const SeqLayout& lay = SeqLayout()) {
   const B2EModelDesc& d = e->desc;
   const int M = B * S, H = d.hidden, I = d.intermediate, L = d.num_layers;
   const int QC = e->qkv_cols(), CC = e->ctx_cols();
   int rc;
   DISPATCH_NV(H, (mistral_embed_kernel<NV><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                     ids, (const float*)e->w[0], e->xres, M)));
+                     ids, (const float*)e->w[0], e->xres, M, lay.t_real, lay.tok_src)));
   CUDA_TRY(cudaGetLastError());
   if ((rc = attention_prepare(e->attn, mask, B, S, st))) return rc;
   CUtensorMap tm_hidden, tm_ctx, tm_ffn;
@@ -922,33 +909,33 @@ int run_mistral_trunk(B2EEncoder* e, const int64_t* ids, const int64_t* mask, in
   if ((rc = make_tmap_h16(&tm_ffn, e->ffn, M, I, 128))) return rc;
 
   DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                     e->xres, nullptr, (const float*)e->Mi(0, 0), e->hidden, M, d.eps)));
+                     e->xres, nullptr, (const float*)e->Mi(0, 0), e->hidden, M, d.eps, lay.t_real)));
   const int n_rot = d.heads + d.kv_heads;   // q heads and k heads are adjacent columns of qkv
   const long long rope_work = (long long)M * n_rot;
   for (int l = 0; l < L; ++l) {
     if ((rc = launch_gemm(tm_hidden, e->tm_wqkv[l], e->qkv, nullptr, nullptr, M, QC, H, B2E_EPI_BIAS,
-                          e->sms, st)))
+                          e->sms, st, lay.t_real)))
       return rc;
     rope_halves_kernel<64><<<(unsigned)((rope_work * 8 + 255) / 256), 256, 0, st>>>(
-        e->qkv, e->rope_cos, e->rope_sin, M, S, n_rot, QC);
+        e->qkv, e->rope_cos, e->rope_sin, M, S, n_rot, QC, lay.t_real, lay.tok_src);
     if ((rc = launch_attention_causal_d128(e->qkv, e->attn, e->ctx, B, S, d.heads, d.kv_heads,
-                                           d.sliding_window, e->sms, st)))
+                                           d.sliding_window, e->sms, st, lay)))
       return rc;
     if ((rc = launch_gemm(tm_ctx, e->tm_wo[l], e->tmp, nullptr, nullptr, M, H, CC, B2E_EPI_BIAS,
-                          e->sms, st)))
+                          e->sms, st, lay.t_real)))
       return rc;
     DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, (const float*)e->Mi(l, 3), e->hidden, M, d.eps)));
+                       e->xres, e->tmp, (const float*)e->Mi(l, 3), e->hidden, M, d.eps, lay.t_real)));
     // gate and up in one GEMM (interleaved rows), silu(gate) * up in its epilogue: [M, I]
     if ((rc = launch_gemm(tm_hidden, e->tm_w1[l], e->ffn, nullptr, nullptr, M, 2 * I, H,
-                          B2E_EPI_SWIGLU, e->sms, st)))
+                          B2E_EPI_SWIGLU, e->sms, st, lay.t_real)))
       return rc;
     if ((rc = launch_gemm(tm_ffn, e->tm_w2[l], e->tmp, nullptr, nullptr, M, H, I, B2E_EPI_BIAS,
-                          e->sms, st)))
+                          e->sms, st, lay.t_real)))
       return rc;
     if (l + 1 < L) {
       DISPATCH_NV(H, (add_rmsnorm_kernel<NV, h16><<<row_blocks(M), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->Mi(l + 1, 0), e->hidden, M, d.eps)));
+                         e->xres, e->tmp, (const float*)e->Mi(l + 1, 0), e->hidden, M, d.eps, lay.t_real)));
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -1337,14 +1324,18 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
   const B2EModelDesc& d = e->desc;
   const int H = d.hidden, l = d.num_layers - 1;
   PoolScratch& ps = e->pool;
+  // Pooled paths run on the padding-free token layout (pack.cuh): only attended tokens go through the GEMMs, norms
+  // and attention query tiles; nothing here can observe a padded position.
+  SeqLayout lay;
+  if ((rc = pack_prepare(e, mask, B, S, packing_enabled(), st, &lay))) return rc;
   if (d.arch == B2E_ARCH_MISTRAL) {
-    if ((rc = run_mistral_trunk(e, ids, mask, B, S, st))) return rc;
+    if ((rc = run_mistral_trunk(e, ids, mask, B, S, st, lay))) return rc;
     if (pool_kind == B2E_POOL_LAST_TOKEN) {
       // only the B selected rows go through the final norm (fp32 end to end)
       seq_len_kernel<<<(B + 7) / 8, 256, 0, st>>>(mask, ps.seq_len, B, S);
       last_token_index_kernel<<<1, 256, 0, st>>>(mask, ps.seq_len, ps.idx, B, S);
       DISPATCH_NV(H, (rmsnorm_gather_kernel<NV><<<row_blocks(B), ROW_THREADS, 0, st>>>(
-                         e->xres, e->tmp, (const float*)e->w[1], ps.idx, out, B, S, d.eps)));
+                         e->xres, e->tmp, (const float*)e->w[1], ps.idx, out, B, S, d.eps, lay.cu)));
       if (l2) l2_normalize_kernel<<<(B + 7) / 8, 256, 0, st>>>(out, B, H);
       CUDA_TRY(cudaGetLastError());
       return B2E_OK;
@@ -1355,14 +1346,10 @@ int b2e_encode_pooled(B2EEncoder* e, const int64_t* ids, const int64_t* mask, co
     const int rows_per = (S + nsplit - 1) / nsplit;
     dim3 grid(B, nsplit);
     DISPATCH_NV(H, (addnorm_pool_kernel<NV, true><<<grid, ROW_THREADS, 0, st>>>(
-                       e->xres, e->tmp, (const float*)e->w[1], nullptr, ps.w, ps.part, S, rows_per, d.eps)));
+                       e->xres, e->tmp, (const float*)e->w[1], nullptr, ps.w, ps.part, S, rows_per, d.eps, lay.cu)));
     CUDA_TRY(cudaGetLastError());
     return launch_finalize(ps, out, B, H, nsplit, l2, /*round_mode=*/0, st);
   }
-  // Pooled paths of the head_dim-64 families run on the padding-free token layout (pack.cuh): only attended
-  // tokens go through the GEMMs, norms and attention query tiles; nothing here can observe a padded position.
-  SeqLayout lay;
-  if ((rc = pack_prepare(e, mask, B, S, packing_enabled(), st, &lay))) return rc;
   if (d.arch == B2E_ARCH_ESM2 || d.arch == B2E_ARCH_MODERNBERT) {
     const bool mb = d.arch == B2E_ARCH_MODERNBERT;
     if ((rc = mb ? run_modernbert_trunk(e, ids, mask, B, S, st, lay) : run_esm_trunk(e, ids, mask, B, S, st, lay)))
@@ -1839,7 +1826,7 @@ int b2e_max_row_norm(const float* x, int64_t N, int H, float* out_host, void* st
 int b2e_topk_ip_tc(const float* queries, int Q, const float* corpus, int64_t N, int H, int k,
                    float corpus_max_norm, float* out_scores, int64_t* out_indices, void* stream) {
   if (!queries || !corpus || !out_scores || !out_indices) return fail(B2E_ERR_INVALID, "null tensor pointer");
-  const bool fast = N >= 32768 && N < (int64_t)4000000000ll && H % 128 == 0 && H <= 8192 && k > 0 && k <= TOPK_MAX_K &&
+  const bool fast = N >= 32768 && N < ((int64_t)1 << 31) - TC_ROWS && H % 128 == 0 && H <= 8192 && k > 0 && k <= TOPK_MAX_K &&
                     corpus_max_norm > 0.0f && corpus_max_norm < 1e30f && Q > 0;
   if (!fast) return b2e_topk_ip(queries, Q, corpus, B2E_DTYPE_F32, N, H, k, out_scores, out_indices, stream);
   int rc;

@@ -14,12 +14,14 @@ namespace b2e {
 template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 mistral_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
-                     float* __restrict__ xres, int rows) {
+                     float* __restrict__ xres, int rows, const int* __restrict__ n_dev = nullptr,
+                     const int* __restrict__ tok_src = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
-  const int64_t id = ids[row];
+  const int64_t id = ids[tok_src != nullptr ? __ldg(tok_src + row) : row];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = v * 256 + lane * 8;
@@ -54,10 +56,12 @@ __device__ __forceinline__ void warp_rmsnorm(float (&x)[NV][8], const float* __r
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(ROW_THREADS)
 add_rmsnorm_kernel(float* __restrict__ xres, const h16* __restrict__ add,
-                   const float* __restrict__ gamma, OutT* __restrict__ out, int rows, float eps) {
+                   const float* __restrict__ gamma, OutT* __restrict__ out, int rows, float eps,
+                   const int* __restrict__ n_dev = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (n_dev != nullptr) rows = __ldg(n_dev);
   if (row >= rows) return;
   float x[NV][8];
 #pragma unroll
@@ -83,12 +87,12 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_THREADS)
 rmsnorm_gather_kernel(const float* __restrict__ xres, const h16* __restrict__ add,
                       const float* __restrict__ gamma, const int* __restrict__ idx,
-                      float* __restrict__ out, int B, int S, float eps) {
+                      float* __restrict__ out, int B, int S, float eps, const int* __restrict__ cu = nullptr) {
   constexpr int H = NV * 256;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (b >= B) return;
-  const size_t row = static_cast<size_t>(b) * S + idx[b];
+  const size_t row = (cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * S) + idx[b];
   float x[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {

@@ -175,7 +175,7 @@ int b2e_topk_ip(const float* queries, int Q, const void* corpus, int corpus_dtyp
  * candidates do not fit the 4096-row buffer makes the call fall back to b2e_topk_ip's scan on the device).
  * corpus_max_norm >= the Euclidean norm of every corpus row (1 for L2-normalised embeddings; b2e_max_row_norm
  * computes it once when the index is built): it sizes the error margin.  Problems below 32 768 rows go straight
- * to b2e_topk_ip.  N < 4e9. */
+ * to b2e_topk_ip, and so do corpora of 2^31 rows or more. */
 int b2e_topk_ip_tc(const float* queries, int Q, const float* corpus, int64_t N, int H, int k,
                    float corpus_max_norm, float* out_scores, int64_t* out_indices, void* stream);
 /* Largest Euclidean row norm of a device-resident float32 [N,H] matrix -> *out_host (synchronises `stream`:

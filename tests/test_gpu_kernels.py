@@ -65,10 +65,11 @@ def test_gemm_rejects_bad_shapes(dev, h16):
                      torch.zeros(100, 64, device=dev, dtype=h16), torch.zeros(100, device=dev))
 
 
-@pytest.fixture(params=[None, 69, 64], ids=['shipping', 'split4-poly', 'split4'])
+@pytest.fixture(params=[None, 5, 0, 69, 64], ids=['shipping', 'two-wg-poly', 'two-wg', 'four-wg-poly', 'four-wg-vote'])
 def att_variant(request, h16):
-    """Which head_dim-64 attention kernel the calls of a test reach: the library's default, or the
-    four-warpgroup kernel of attention5.cuh (variant bit 6) with / without the polynomial exponentials."""
+    """Which head_dim-64 attention kernel the calls of a test reach: the library's default (variant 65: four
+    softmax warpgroups, attention5.cuh), the two-warpgroup kernel of attention3.cuh (5, 0), or the other
+    four-warpgroup flavours (69: polynomial exponentials, 64: vote over the bias row)."""
     import ctypes
 
     lib = nv.load(nv.storage_of(h16))

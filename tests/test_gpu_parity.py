@@ -578,7 +578,7 @@ def test_modernbert_matches_reference_vectors(tiny_modernbert, modernbert_golden
 
 
 # ---------------------------------------------------------------------------------- padding-free layout
-@pytest.mark.parametrize('family', ['bert', 'esm', 'modernbert'])
+@pytest.mark.parametrize('family', ['bert', 'esm', 'modernbert', 'mistral', 'mistral-window'])
 def test_packed_token_layout_equals_padded(family, tiny_bert, tiny_esm, tiny_modernbert):
     """Pooled forward passes run on the attended tokens only (csrc/pack.cuh).  Same batch, packing on vs off
     (b2e_debug_set_packing): right-padded ragged batches must give the same embeddings (padded positions can
@@ -589,8 +589,15 @@ def test_packed_token_layout_equals_padded(family, tiny_bert, tiny_esm, tiny_mod
     from distllm_b200.embed.encoders.native import NativeEsm2Encoder
     from distllm_b200.embed.encoders.native import NativeModernBertEncoder
 
-    cfg, sd = {'bert': tiny_bert, 'esm': tiny_esm, 'modernbert': tiny_modernbert}[family]
-    cls = {'bert': NativeBertEncoder, 'esm': NativeEsm2Encoder, 'modernbert': NativeModernBertEncoder}[family]
+    from distllm_b200.embed.encoders.native import NativeMistralEncoder
+    from conftest import tiny_mistral_variant
+
+    if family.startswith('mistral'):
+        cfg, sd = tiny_mistral_variant('window' if family.endswith('window') else 'full')
+        cls = NativeMistralEncoder
+    else:
+        cfg, sd = {'bert': tiny_bert, 'esm': tiny_esm, 'modernbert': tiny_modernbert}[family]
+        cls = {'bert': NativeBertEncoder, 'esm': NativeEsm2Encoder, 'modernbert': NativeModernBertEncoder}[family]
     enc = cls(cfg, sd)
     lib = enc._lib
     lib.b2e_debug_set_packing.argtypes = [ctypes.c_int]

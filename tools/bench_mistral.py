@@ -2,7 +2,7 @@
 H=4096, 32 query / 8 kv heads x 128, I=14336, last_token pooler, B=16, S=4096).
 Synthetic ids, seeded random bf16 weights.  Prints sequences/s, the fraction of the bf16 roofline
 (causal-skipped FLOPs) and a per-kernel breakdown of one layer timed with CUDA events.
-usage: bench_mistral.py [B] [S] [layers]"""
+usage: bench_mistral.py [B] [S] [layers] [ragged]   (ragged: right-padded lengths ~ U{S/8..S}, first row full)"""
 import json, sys
 from pathlib import Path
 import torch
@@ -27,6 +27,11 @@ torch.cuda.empty_cache()
 g = torch.Generator().manual_seed(0)
 ids = torch.randint(3, 32000, (B, S), generator=g).to(dev)
 mask = torch.ones(B, S, dtype=torch.int64, device=dev)
+RAGGED = len(sys.argv) > 4 and sys.argv[4] == 'ragged'
+if RAGGED:
+    lens = torch.randint(S // 8, S + 1, (B,), generator=g)
+    lens[0] = S
+    mask = (torch.arange(S)[None] < lens[:, None]).long().to(dev)
 out = torch.empty(B, H, device=dev)
 for _ in range(2):
     enc.encode_pooled(ids, mask, None, nv.POOL_LAST_TOKEN, True, out=out)
@@ -45,7 +50,8 @@ seqs = B / (ms * 1e-3)
 pk = Path(__file__).resolve().parents[1] / 'MEASURED_PEAKS.json'
 peaks = json.loads(pk.read_text()) if pk.exists() else {}
 sus = peaks.get('bf16_tflops_sustained', 1415.2)
-res = {'workload': f'C3: Mistral-7B shape (L={L}), S={S}, last_token pooler', 'batch': B, 'ms_per_step': ms,
+res = {'workload': f'C3: Mistral-7B shape (L={L}), S={S}, last_token pooler' + (' RAGGED' if RAGGED else ''), 'batch': B,
+       'attended_tokens': int(mask.sum().item()), 'padded_tokens': B * S, 'ms_per_step': ms,
        'sequences_per_s': seqs, 'tflops_causal_skipped': seqs * flops_causal / 1e12,
        'frac_of_sustained_bf16': seqs * flops_causal / 1e12 / sus,
        'tflops_dense_counted': seqs * flops_dense / 1e12,
