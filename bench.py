@@ -495,12 +495,23 @@ def extra_mistral(device, peaks: dict, reduce_max) -> dict:
     out = torch.empty(b, cfg.hidden_size, device=device)
     ms = reduce_max(timed_steps(lambda: enc.encode_pooled(ids, mask, None, nv.POOL_LAST_TOKEN, True, out=out),
                                 3, 2, device))
+    # the same batch shape with right-padded lengths ~ U{512..4096} (first row full): the padding-free layout makes
+    # the step cost what its attended tokens cost
+    lens = torch.randint(s // 8, s + 1, (b,), generator=g)
+    lens[0] = s
+    r_mask = (torch.arange(s)[None] < lens[:, None]).long().to(device)
+    r_ms = reduce_max(timed_steps(lambda: enc.encode_pooled(ids, r_mask, None, nv.POOL_LAST_TOKEN, True, out=out),
+                                  2, 1, device))
+    ragged = {'workload': 'same model and batch shape, lengths ~ U{512..4096} right-padded', 'ms_per_step': r_ms,
+              'sequences_per_s_per_gpu': b / (r_ms * 1e-3), 'attended_tokens': int(r_mask.sum().item()),
+              'padded_tokens': b * s}
     enc.close()
     del enc
     torch.cuda.empty_cache()
     seqs = b / (ms * 1e-3)
     tf = seqs * mistral_flops_per_seq(MISTRAL_7B, s) / 1e12
-    return {'workload': 'C3: SFR-Embedding-Mistral shape (Mistral-7B: L32 H4096 32q/8kv x128 I14336), '
+    return {'ragged': ragged,
+            'workload': 'C3: SFR-Embedding-Mistral shape (Mistral-7B: L32 H4096 32q/8kv x128 I14336), '
                         'last_token pooler, batch_size=16, S=4096, synthetic ids, random-init weights; half-storage build (f16)',
             'value_per_gpu': seqs, 'unit': 'sequences/s', 'ms_per_step': ms, 'steps': 3,
             'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
