@@ -92,10 +92,11 @@ def mistral_flops_per_seq(cfg: dict, s: int, causal_skipped: bool = True) -> flo
 
 
 def launches_per_step(cfg: dict) -> int:
-    """Kernels of ours per step: embed+LN, attention mask prep, per layer 4 GEMMs + attention +
-    2 LayerNorms (the last LayerNorm is the fused LN+pool), 3 pool-weight kernels, pool finalize,
-    adjacent-cosine (matches the ncu launch list in profiles/)."""
-    return 1 + 1 + cfg['num_hidden_layers'] * 7 + 3 + 1 + 1
+    """Kernels of ours per step: the 3 kernels of the padding-free layout (lengths, scan, row map), embed+LN,
+    attention mask prep, per layer 4 GEMMs + attention + 2 LayerNorms (the last LayerNorm is the fused LN+pool),
+    3 pool-weight kernels, pool finalize, adjacent-cosine (matches profiles/r02_ncu_launches_final.md: 1413
+    launches in 15 passes)."""
+    return 3 + 1 + 1 + cfg['num_hidden_layers'] * 7 + 3 + 1 + 1
 
 
 def load_peaks() -> tuple[dict, str]:
@@ -761,7 +762,7 @@ def run_native(args) -> None:
     if rank == 0:
         fpc = flops_per_chunk(BERT_BASE, SEQ)
         step_tf = (value / world) * fpc / 1e12
-        # top level: the dominant kernel against the burst peak (timed alone); whole_step: all 91
+        # top level: the dominant kernel against the burst peak (timed alone); whole_step: all 94
         # launches of one step against the sustained peak
         roof = {'bound': 'tensor', 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s',
                 'frac': dom['frac'], 'traffic': ncu_traffic_bytes(), 'kernel': dom['name'],
