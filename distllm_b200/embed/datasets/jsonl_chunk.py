@@ -9,6 +9,7 @@ every row, and drop buffers of ``min_buffer_length`` characters or fewer.
 from __future__ import annotations
 
 import re
+import warnings
 from pathlib import Path
 from typing import Any
 from typing import Callable
@@ -19,6 +20,7 @@ from torch.utils.data import DataLoader
 
 from distllm_b200.embed.datasets.jsonl import read_jsonl
 from distllm_b200.embed.datasets.utils import InMemoryDataset
+from distllm_b200.embed.datasets.utils import SentenceTokenCache
 from distllm_b200.embed.datasets.utils import LoaderConfig
 from distllm_b200.embed.datasets.utils import make_dataloader
 from distllm_b200.embed.encoders.base import Encoder
@@ -98,6 +100,9 @@ def sentences_to_buffers(split: list[str], buffer_size: int) -> list[str]:
 class JsonlChunkDatasetConfig(LoaderConfig):
     name: Literal['jsonl_chunk'] = 'jsonl_chunk'  # type: ignore[assignment]
     text_field: str = 'text'   # which key of each json row holds the text
+    # tokenise every sentence once and assemble buffer / chunk ids from the cached pieces (BERT-style tokenizers
+    # only, identical ids; False = tokenise every buffer and chunk text like the reference)
+    sentence_token_cache: bool = True
     min_buffer_length: int = Field(
         default=750,
         description='Buffers with this many characters or fewer are filtered out '
@@ -127,11 +132,26 @@ class JsonlChunkDataset:
 
         buffers: list[str] = []
         metadatas: list[dict[str, Any]] = []
+        all_sentences: list[str] = []          # every sentence of the file, in order
+        parts: list[tuple[int, ...]] = []      # buffer -> the sentences it is joined from
+        n_buf = self.config.buffer_size
         for doc_meta, text in zip(rows, texts):
             sentences = self.splitter(text)
-            buffers.extend(sentences_to_buffers(sentences, self.config.buffer_size))
+            base, n = len(all_sentences), len(sentences)
+            all_sentences.extend(sentences)
+            buffers.extend(sentences_to_buffers(sentences, n_buf))
+            parts.extend(tuple(range(base + max(0, i - n_buf), base + min(n, i + n_buf + 1))) for i in range(n))
             metadatas.extend({**doc_meta, 'sentence': sentence} for sentence in sentences)
 
         keep = [i for i, buf in enumerate(buffers) if len(buf) > self.config.min_buffer_length]
-        dataset = InMemoryDataset([buffers[i] for i in keep], [metadatas[i] for i in keep])
+        # every sentence is tokenised once instead of once per buffer that contains it (2 * buffer_size + 1 times)
+        cache = SentenceTokenCache.build(encoder.tokenizer, all_sentences) if self.config.sentence_token_cache else None
+        dataset = InMemoryDataset([buffers[i] for i in keep], [metadatas[i] for i in keep],
+                                  parts=[parts[i] for i in keep], token_cache=cache, sentence_index=keep)
+        if cache is not None and len(dataset):
+            sample = sorted({0, len(dataset) // 3, (2 * len(dataset)) // 3, len(dataset) - 1})
+            if not cache.agrees_with(encoder.tokenizer, [dataset[i] for i in sample]):
+                warnings.warn('sentence token cache disagrees with the tokenizer on this file: tokenising every '
+                              'buffer directly', RuntimeWarning, stacklevel=2)
+                dataset.parts = dataset.token_cache = None
         return make_dataloader(self.config, dataset, encoder.tokenizer)

@@ -26,19 +26,146 @@ class LoaderConfig(BaseConfig):
     pin_memory: bool = True     # page-locked batches for the H2D copy
 
 
-class InMemoryDataset(Dataset):
-    """List of texts with optional per-row metadata."""
+class PieceText(str):
+    """A text that is the concatenation of sentences ``parts`` (indices into a SentenceTokenCache)."""
 
-    def __init__(self, data: list[str], metadata: list[dict[str, Any]] | None = None) -> None:
+    parts: tuple[int, ...] = ()
+
+    def __new__(cls, text: str, parts: tuple[int, ...] = ()) -> 'PieceText':
+        obj = super().__new__(cls, text)
+        obj.parts = parts
+        return obj
+
+    def __reduce__(self):   # DataLoader worker processes pickle the items
+        return (PieceText, (str(self), self.parts))
+
+
+class SentenceTokenCache:
+    """Token ids of every sentence of a file, tokenised ONCE.
+
+    ``jsonl_chunk`` feeds the encoder one buffer per sentence -- sentences ``[i - b, i + b]`` joined -- so with
+    the default ``buffer_size`` of 4 every sentence is tokenised nine times in pass 1 of the semantic-chunk
+    pipeline, and once more inside its final chunk in pass 2 ("~9x token redundancy").  For
+    BERT-style tokenizers (BertNormalizer + BertPreTokenizer + WordPiece: every step works on single characters or
+    on whitespace / punctuation delimited words) the ids of a concatenation are the concatenation of the ids,
+    provided every joint falls on whitespace; then ``[CLS] + ids[:max_length - 2] + [SEP]`` is, id for id, what
+    ``tokenizer(text, truncation=True)`` returns.  Joints that do not fall on whitespace make ``row_ids`` return
+    None (the caller tokenises that text directly), other tokenizer families make ``build`` return None, and a
+    sample of rows is checked against the tokenizer itself when the cache is built.
+    """
+
+    def __init__(self, sentence_ids: list[np.ndarray], ends_ws: np.ndarray, starts_ws: np.ndarray,
+                 prefix: list[int], suffix: list[int]) -> None:
+        self.sentence_ids = sentence_ids
+        self.ends_ws = ends_ws
+        self.starts_ws = starts_ws
+        self.prefix = np.asarray(prefix, dtype=np.int64)
+        self.suffix = np.asarray(suffix, dtype=np.int64)
+
+    @staticmethod
+    def supported(tokenizer: PreTrainedTokenizer) -> bool:
+        import json
+
+        backend = getattr(tokenizer, '_tokenizer', None)
+        if not getattr(tokenizer, 'is_fast', False) or backend is None:
+            return False
+        if getattr(tokenizer, 'truncation_side', 'right') != 'right':
+            return False
+        try:
+            spec = json.loads(backend.to_str())
+        except Exception:  # noqa: BLE001
+            return False
+        kinds = tuple((spec.get(k) or {}).get('type') for k in ('normalizer', 'pre_tokenizer', 'model'))
+        return kinds == ('BertNormalizer', 'BertPreTokenizer', 'WordPiece')
+
+    @classmethod
+    def build(cls, tokenizer: PreTrainedTokenizer, sentences: list[str]) -> 'SentenceTokenCache | None':
+        if not sentences or not cls.supported(tokenizer):
+            return None
+        backend = tokenizer._tokenizer
+        # the single-sequence template: ids around a probe word
+        with_special = backend.encode('a', add_special_tokens=True)
+        bare = backend.encode('a', add_special_tokens=False).ids
+        ids = with_special.ids
+        if len(bare) != 1 or ids.count(bare[0]) != 1 or any(t != 0 for t in with_special.type_ids):
+            return None
+        at = ids.index(bare[0])
+        prefix, suffix = ids[:at], ids[at + 1:]
+        saved = (backend.truncation, backend.padding)
+        backend.no_truncation()
+        backend.no_padding()
+        try:
+            encode = getattr(backend, 'encode_batch_fast', backend.encode_batch)
+            encodings = encode(list(sentences), add_special_tokens=False)
+        finally:
+            if saved[0] is not None:
+                backend.enable_truncation(**saved[0])
+            if saved[1] is not None:
+                backend.enable_padding(**saved[1])
+        limit = max(int(min(tokenizer.model_max_length, 1 << 20)) - len(prefix) - len(suffix), 0)
+        sentence_ids = [np.asarray(e.ids[:limit], dtype=np.int64) for e in encodings]
+        ends_ws = np.fromiter((s[-1:].isspace() for s in sentences), dtype=bool, count=len(sentences))
+        starts_ws = np.fromiter((s[:1].isspace() for s in sentences), dtype=bool, count=len(sentences))
+        return cls(sentence_ids, ends_ws, starts_ws, prefix, suffix)
+
+    def row_ids(self, parts: tuple[int, ...], max_length: int) -> np.ndarray | None:
+        """``[prefix] + concatenated sentence ids[:max_length - specials] + [suffix]``; None when a joint between
+        two of the sentences does not fall on whitespace (or there is nothing to join)."""
+        if not parts:
+            return None
+        for a, b in zip(parts, parts[1:]):
+            if not (self.ends_ws[a] or self.starts_ws[b]):
+                return None
+        room = max_length - len(self.prefix) - len(self.suffix)
+        out, used = [self.prefix], 0
+        for i in parts:
+            if used >= room:
+                break
+            piece = self.sentence_ids[i][: room - used]
+            out.append(piece)
+            used += len(piece)
+        out.append(self.suffix)
+        return np.concatenate(out)
+
+    def agrees_with(self, tokenizer: PreTrainedTokenizer, texts: list[PieceText]) -> bool:
+        """The cache reproduces ``tokenizer(text, truncation=True)`` on these rows (checked when it is attached)."""
+        max_length = int(min(tokenizer.model_max_length, 1 << 20))
+        for text in texts:
+            mine = self.row_ids(text.parts, max_length)
+            if mine is None:
+                continue
+            theirs = tokenizer(str(text), truncation=True, max_length=max_length)['input_ids']
+            if len(theirs) != len(mine) or (np.asarray(theirs, dtype=np.int64) != mine).any():
+                return False
+        return True
+
+
+class InMemoryDataset(Dataset):
+    """List of texts with optional per-row metadata.
+
+    ``parts`` / ``token_cache`` (optional): row ``i`` is the concatenation of the sentences ``parts[i]`` of the
+    cache, which lets the collator assemble its ids instead of tokenising the text again; ``sentence_index[i]``
+    names the sentence a ``jsonl_chunk`` buffer is centred on (what semantic chunks are later joined from)."""
+
+    def __init__(self, data: list[str], metadata: list[dict[str, Any]] | None = None,
+                 parts: list[tuple[int, ...]] | None = None, token_cache: SentenceTokenCache | None = None,
+                 sentence_index: list[int] | None = None) -> None:
         if metadata is not None and len(metadata) != len(data):
             raise AssertionError('metadata and data must have the same length')
+        if parts is not None and len(parts) != len(data):
+            raise AssertionError('parts and data must have the same length')
         self.data = data
         self.metadata = metadata
+        self.parts = parts if token_cache is not None else None
+        self.token_cache = token_cache if parts is not None else None
+        self.sentence_index = sentence_index
 
     def __len__(self) -> int:
         return len(self.data)
 
     def __getitem__(self, idx: int) -> str:
+        if self.parts is not None:
+            return PieceText(self.data[idx], self.parts[idx])
         return self.data[idx]
 
 
@@ -54,8 +181,10 @@ class DataCollator:
     (SURVEY 8(f) rank 1).  Slow tokenizers (e.g. ``EsmTokenizer``) take the reference call unchanged.
     """
 
-    def __init__(self, tokenizer: PreTrainedTokenizer, fast: bool = True) -> None:
+    def __init__(self, tokenizer: PreTrainedTokenizer, fast: bool = True,
+                 cache: SentenceTokenCache | None = None) -> None:
         self.tokenizer = tokenizer
+        self.cache = cache
         self._fast = bool(
             fast
             and getattr(tokenizer, 'is_fast', False)
@@ -77,8 +206,20 @@ class DataCollator:
             max_length=max_length, stride=0, pad_to_multiple_of=None, padding_side=None)
         backend = tok._tokenizer
         encode = getattr(backend, 'encode_batch_fast', backend.encode_batch)  # no offset tracking
-        encodings = encode(list(batch), add_special_tokens=True)
-        rows = [e.ids for e in encodings]
+        rows: list[Any] = [None] * len(batch)
+        type_rows: dict[int, list[int]] = {}
+        if self.cache is not None and max_length is not None:
+            # rows that are concatenations of cached sentences: assemble the ids (type ids are all 0: checked at build)
+            for i, text in enumerate(batch):
+                parts = getattr(text, 'parts', None)
+                if parts:
+                    rows[i] = self.cache.row_ids(parts, int(max_length))
+        todo = [i for i, r in enumerate(rows) if r is None]
+        if todo:
+            encodings = encode([str(batch[i]) for i in todo], add_special_tokens=True)
+            for i, e in zip(todo, encodings):
+                rows[i] = e.ids
+                type_rows[i] = e.type_ids
         lengths = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
         width = int(lengths.max())
         left = tok.padding_side == 'left'
@@ -91,7 +232,7 @@ class DataCollator:
             span = slice(width - n, width) if left else slice(0, n)
             ids[i, span] = row
             if want_types:
-                types[i, span] = encodings[i].type_ids
+                types[i, span] = type_rows.get(i, 0)
         cols = np.arange(width)[None, :]
         mask = (cols >= (width - lengths)[:, None]) if left else (cols < lengths[:, None])
 
@@ -115,5 +256,5 @@ def make_dataloader(config: Any, dataset: InMemoryDataset, tokenizer: PreTrained
         batch_size=config.batch_size,
         num_workers=config.num_data_workers,
         pin_memory=config.pin_memory,
-        collate_fn=DataCollator(tokenizer),
+        collate_fn=DataCollator(tokenizer, cache=getattr(dataset, 'token_cache', None)),
     )

@@ -125,6 +125,13 @@ def compute_semantic_chunks(
     metas = [metas[i] for i in keep]
     for meta in metas:
         meta.pop('sentence')
+    # a chunk is the concatenation of the sentences its rows are centred on: with a sentence token cache on the
+    # pass-1 dataset (jsonl_chunk) pass 2 assembles its ids from the same cached pieces
+    cache = getattr(dataset, 'token_cache', None)
+    index = getattr(dataset, 'sentence_index', None)
+    if cache is not None and index is not None:
+        parts = [tuple(index[r] for r in range(*row_groups[i])) for i in keep]
+        return InMemoryDataset(texts, metas, parts=parts, token_cache=cache)
     return InMemoryDataset(texts, metas)
 
 
@@ -170,7 +177,7 @@ class SemanticChunkEmbedder:
             batch_size=cfg.chunk_batch_size,
             num_workers=dataloader.num_workers,
             dataset=chunks,
-            collate_fn=DataCollator(encoder.tokenizer),
+            collate_fn=DataCollator(encoder.tokenizer, cache=getattr(chunks, 'token_cache', None)),
         )
         device_rows, chunk_embeds = compute_embeddings_pair(
             dataloader=chunk_loader,

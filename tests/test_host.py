@@ -706,3 +706,112 @@ def test_weight_lists_follow_the_abi_order_on_cpu(dtype):
     tensors = mb[3](mb[1](mb[0], seed=0, device='cpu'), 4, torch.device('cpu'), dt)
     assert tensors[5 + 6].shape == (512, 256) and tensors[5 + 7].shape == (256, 256)
     assert not tensors[5 + 7][:, 200:].any()
+
+
+# ------------------------------------------------------------------- host feed (sentence token cache)
+def _wordpiece_tokenizer(tmp_path, max_len=48):
+    from transformers import BertTokenizerFast
+
+    words = [f'w{i:03d}' for i in range(200)] + ['play', '##ing', '##ed', 'un', '##believ', '##able', 'the', 'a',
+                                                 'cell', '##s', 'protein', '.', ',', '!', '?', '(', ')', '-', ';',
+                                                 'é', 'e', '中', '文', 'x', '##x']
+    (tmp_path / 'vocab.txt').write_text('\n'.join(['[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]', *words]) + '\n')
+    tok = BertTokenizerFast(vocab=str(tmp_path / 'vocab.txt'), do_lower_case=True)
+    tok.model_max_length = max_len
+    assert tok.convert_tokens_to_ids('playing') == tok.unk_token_id and len(tok('playing')['input_ids']) == 4
+    return tok
+
+
+def _documents(n_docs=5, seed=3):
+    import random
+
+    rng = random.Random(seed)
+    words = [f'w{i:03d}' for i in range(200)] + ['playing', 'played', 'unbelievable', 'The', 'cells', 'protein',
+                                                 'Élan', '中文', 'xxxx', 'w001-w002', '(w003)', 'ét']
+    seps = [' ', '  ', '\n', '\t', ' \n ', ' ']
+    docs = []
+    for d in range(n_docs):
+        sentences = []
+        for s in range(rng.randint(6, 30)):
+            n = rng.choice([2, 5, 9, 14, 60]) if s % 7 else 80      # some sentences exceed max_length alone
+            sentences.append('The ' + ' '.join(rng.choice(words) for _ in range(n)) + rng.choice(['.', '!', '?', '...']))
+        text = ''
+        for s in sentences:
+            text += s + rng.choice(seps)
+        docs.append(text)
+    return docs
+
+
+def test_sentence_token_cache_gives_the_tokenizers_own_ids(tmp_path):
+    """jsonl_chunk buffers and semantic chunks assembled from once-tokenised sentences == tokenizer(text), id for
+    id (padding, truncation, special tokens, type ids, attention mask), through the real dataset and collator."""
+    import json
+    from types import SimpleNamespace
+
+    import torch
+
+    from distllm_b200.embed.datasets.jsonl_chunk import JsonlChunkDataset
+    from distllm_b200.embed.datasets.jsonl_chunk import JsonlChunkDatasetConfig
+    from distllm_b200.embed.datasets.utils import DataCollator
+    from distllm_b200.embed.datasets.utils import InMemoryDataset
+    from distllm_b200.embed.datasets.utils import SentenceTokenCache
+
+    tok = _wordpiece_tokenizer(tmp_path)
+    assert SentenceTokenCache.supported(tok)
+    path = tmp_path / 'docs.jsonl'
+    with path.open('w') as f:
+        for i, text in enumerate(_documents()):
+            f.write(json.dumps({'text': text, 'path': f'doc{i}'}) + '\n')
+    enc = SimpleNamespace(tokenizer=tok)
+    loaders = {}
+    for on in (True, False):
+        cfg = JsonlChunkDatasetConfig(buffer_size=2, batch_size=7, num_data_workers=0, pin_memory=False,
+                                      sentence_splitter='regex', sentence_token_cache=on, min_buffer_length=20)
+        loaders[on] = JsonlChunkDataset(cfg).get_dataloader(path, enc)
+    fast, plain = loaders[True], loaders[False]
+    assert fast.dataset.token_cache is not None and plain.dataset.token_cache is None
+    assert fast.dataset.data == plain.dataset.data and len(fast.dataset) > 40
+    n_rows = 0
+    for a, b in zip(fast, plain):
+        assert set(a.keys()) == set(b.keys()) == {'input_ids', 'token_type_ids', 'attention_mask'}
+        for key in a.keys():
+            assert torch.equal(a[key], b[key]), key
+        n_rows += a['input_ids'].shape[0]
+        assert a['input_ids'].shape[1] <= tok.model_max_length
+    assert n_rows == len(fast.dataset)
+    # pass 2: chunks = runs of consecutive rows, joined from the sentences those rows are centred on
+    ds = fast.dataset
+    groups = [(0, 3), (3, 4), (4, 11), (11, len(ds))]
+    texts = [''.join(m['sentence'] for m in ds.metadata[s:e]) for s, e in groups]
+    parts = [tuple(ds.sentence_index[r] for r in range(s, e)) for s, e in groups]
+    chunks = InMemoryDataset(texts, None, parts=parts, token_cache=ds.token_cache)
+    got = DataCollator(tok, cache=chunks.token_cache)([chunks[i] for i in range(len(chunks))])
+    want = DataCollator(tok)(texts)
+    for key in want.keys():
+        assert torch.equal(got[key], want[key]), key
+
+
+def test_sentence_token_cache_refuses_what_it_cannot_prove(tmp_path):
+    import torch
+
+    from distllm_b200.embed.datasets.utils import DataCollator
+    from distllm_b200.embed.datasets.utils import PieceText
+    from distllm_b200.embed.datasets.utils import SentenceTokenCache
+
+    tok = _wordpiece_tokenizer(tmp_path)
+    # a joint inside a word: "un" + "believable" must NOT be assembled from two pieces
+    sentences = ['w001 un', 'believable w002. ', 'w003 w004.']
+    cache = SentenceTokenCache.build(tok, sentences)
+    assert cache.row_ids((0, 1), 48) is None and cache.row_ids((1, 2), 48) is not None
+    text = PieceText(''.join(sentences), (0, 1, 2))
+    got = DataCollator(tok, cache=cache)([text])
+    want = DataCollator(tok)([str(text)])
+    assert torch.equal(got['input_ids'], want['input_ids'])     # fell back to tokenising the text
+    # other tokenizer families are left alone
+    llama, _ = _llama_like_tokenizer()
+    assert not SentenceTokenCache.supported(llama) and SentenceTokenCache.build(llama, sentences) is None
+    # DataLoader worker processes pickle the items
+    import pickle
+
+    back = pickle.loads(pickle.dumps(text))
+    assert back == text and back.parts == (0, 1, 2)
