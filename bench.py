@@ -618,10 +618,12 @@ def run_native(args) -> None:
     from distllm_b200.embed.encoders.native import NativeBertEncoder
     from distllm_b200.embed.encoders.weights import random_bert_state_dict
     from distllm_b200.sharding import all_gather_rows
+    from distllm_b200.sharding import partition_host_threads
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    partition_host_threads()   # each rank its share of the host cores (the product's torchrun driver does the same)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl native needs a B200; there is no CPU fallback')
     build_native()

@@ -137,6 +137,7 @@ def main(argv: list[str] | None = None) -> None:
     from distllm_b200.sharding import all_ranks_ok
     from distllm_b200.sharding import count_documents
     from distllm_b200.sharding import materialize_piece
+    from distllm_b200.sharding import partition_host_threads
     from distllm_b200.sharding import plan_document_shards
     from distllm_b200.sharding import world_info
 
@@ -150,6 +151,7 @@ def main(argv: list[str] | None = None) -> None:
 
     config = Config.from_yaml(args.config)
     rank, world, local_rank = world_info()
+    partition_host_threads()   # before any tokenizer starts its thread pool
     use_cuda = torch.cuda.is_available()
     if use_cuda:
         # one GPU per rank; ranks wrap around only when there are fewer GPUs than ranks (the 2-rank test

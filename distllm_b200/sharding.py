@@ -25,6 +25,25 @@ def world_info() -> tuple[int, int, int]:
     )
 
 
+def partition_host_threads() -> int | None:
+    """Give this rank its share of the host's cores: ``RAYON_NUM_THREADS`` (the Rust tokenizers' pool) and
+    torch's intra-op threads become ``cores // LOCAL_WORLD_SIZE`` unless the user set them.  Eight ranks each
+    starting a pool as wide as the whole host oversubscribe it eightfold exactly where the pipeline is
+    host-bound (tokenisation).  Call before the first tokenizer use; returns the thread count or None (single rank)."""
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
+    if local_world <= 1:
+        return None
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:   # not Linux
+        cores = os.cpu_count() or 1
+    share = max(1, cores // local_world)
+    os.environ.setdefault('RAYON_NUM_THREADS', str(share))
+    if 'OMP_NUM_THREADS' not in os.environ:
+        torch.set_num_threads(share)
+    return share
+
+
 def shard_range(n_units: int, world_size: int, rank: int) -> tuple[int, int]:
     """Contiguous, balanced ``[lo, hi)`` slice of ``n_units`` for ``rank`` (sizes differ by <= 1)."""
     if not 0 <= rank < world_size:

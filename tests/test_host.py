@@ -815,3 +815,30 @@ def test_sentence_token_cache_refuses_what_it_cannot_prove(tmp_path):
 
     back = pickle.loads(pickle.dumps(text))
     assert back == text and back.parts == (0, 1, 2)
+
+
+def test_partition_host_threads_gives_each_local_rank_its_share(monkeypatch):
+    import os
+
+    import torch
+
+    from distllm_b200.sharding import partition_host_threads
+
+    before = torch.get_num_threads()
+    try:
+        monkeypatch.delenv('LOCAL_WORLD_SIZE', raising=False)
+        monkeypatch.delenv('WORLD_SIZE', raising=False)
+        monkeypatch.delenv('RAYON_NUM_THREADS', raising=False)
+        monkeypatch.delenv('OMP_NUM_THREADS', raising=False)
+        assert partition_host_threads() is None and 'RAYON_NUM_THREADS' not in os.environ
+        monkeypatch.setenv('LOCAL_WORLD_SIZE', '4')
+        cores = len(os.sched_getaffinity(0))
+        share = partition_host_threads()
+        assert share == max(1, cores // 4) and os.environ['RAYON_NUM_THREADS'] == str(share)
+        assert torch.get_num_threads() == share
+        # an explicit user setting wins
+        monkeypatch.setenv('RAYON_NUM_THREADS', '3')
+        partition_host_threads()
+        assert os.environ['RAYON_NUM_THREADS'] == '3'
+    finally:
+        torch.set_num_threads(before)
