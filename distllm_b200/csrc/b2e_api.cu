@@ -384,9 +384,11 @@ int launch_attention_v(const CUtensorMap& tq, const CUtensorMap& tkv, const Attn
                        int grid, float scale_log2e, cudaStream_t st, int window = 0) {
   if constexpr ((V & 64) != 0) {   // four softmax warpgroups, chunks split by key columns (attention5.cuh)
     auto kern5 = attention5_d64_kernel<(V & ~64)>;
-    const int arc5 = ensure_smem_attr(kern5, AT3_SMEM_BYTES);
+    constexpr bool epi = (V & 128) != 0;   // + the epilogue warpgroup
+    constexpr int smem5 = At5Smem<epi>::BYTES;
+    const int arc5 = ensure_smem_attr(kern5, smem5);
     if (arc5) return arc5;
-    kern5<<<grid, AT5_THREADS, AT3_SMEM_BYTES, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
+    kern5<<<grid, epi ? AT5_THREADS_EPI : AT5_THREADS, smem5, st>>>(tq, tkv, sc.bias, sc.kv_chunks, sc.plain_chunks, tctx, B, S,
                                                      attn_s_pad(S), heads, scale_log2e, window, lay.cu, lay.len,
                                                      static_cast<h16*>(ctx));
     CUDA_TRY(cudaGetLastError());
@@ -415,6 +417,8 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
   int rc;
   if ((rc = make_tmap_h16(&tctx, ctx, (uint64_t)B * S, (uint64_t)heads * AT3_D, 128))) return rc;
   if (window > 0) {
+    if ((att3_variant() & 192) == 192)
+      return launch_attention_v<192 + 17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
     if (att3_variant() & 64)
       return launch_attention_v<64 + 17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
     return launch_attention_v<17>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st, window);
@@ -435,8 +439,10 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
     case 65: return launch_attention_v<65>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 69: return launch_attention_v<69>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 73: return launch_attention_v<73>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 193: return launch_attention_v<193>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 197: return launch_attention_v<197>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
   }
-  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45,64,65,69,73)",
+  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45,64,65,69,73,193,197)",
               att3_variant());
 }
 

@@ -65,11 +65,12 @@ def test_gemm_rejects_bad_shapes(dev, h16):
                      torch.zeros(100, 64, device=dev, dtype=h16), torch.zeros(100, device=dev))
 
 
-@pytest.fixture(params=[None, 5, 0, 69, 64], ids=['shipping', 'two-wg-poly', 'two-wg', 'four-wg-poly', 'four-wg-vote'])
+@pytest.fixture(params=[None, 5, 0, 69, 64, 193], ids=['shipping', 'two-wg-poly', 'two-wg', 'four-wg-poly', 'four-wg-vote', 'four-wg-epilogue-role'])
 def att_variant(request, h16):
     """Which head_dim-64 attention kernel the calls of a test reach: the library's default (variant 65: four
     softmax warpgroups, attention5.cuh), the two-warpgroup kernel of attention3.cuh (5, 0), or the other
-    four-warpgroup flavours (69: polynomial exponentials, 64: vote over the bias row)."""
+    four-warpgroup flavours (69: polynomial exponentials, 64: vote over the bias row, 193: a fifth warpgroup takes
+    the per-tile epilogue)."""
     import ctypes
 
     lib = nv.load(nv.storage_of(h16))
