@@ -318,6 +318,7 @@ __device__ int g_att3_flags = 2;   // 0 free-running, 1 strict ping-pong of the 
 //   bits 2-3  exponentials per four that run on the FMA pipe (plain chunks only): 0, 1 or 2
 //   bit 5  packed fp32x2 arithmetic on plain chunks; bits 2-3 then mean 0, 4, 6 or 8 exponentials per 16 on
 //          the FMA pipe
+//   bit 8  timeline stamps compiled in (profiling instantiation, tools/att3_timeline.py)
 //   bit 4  bidirectional sliding window (`window` > 0: ModernBERT's local layers): chunk range per item narrowed
 //          to the band, scores outside |q - k| <= window masked per element
 template <int V>
@@ -385,13 +386,18 @@ attention3_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
   const uint32_t tmem_base = *tmem_slot;
   long long* const clk = (blockIdx.x == 0) ? g_att3_clock : nullptr;
   int clk_n = 0;
-  // role 0/1: softmax slot A/B (thread 0 of the warpgroup), role 2: MMA issuer; 2 x 256 int64 each
+  // role 0/1: softmax slot A/B (thread 0 of the warpgroup), role 2: MMA issuer; 2 x 256 int64 each.  Compiled in
+  // only with V bit 8: the volatile clock reads pin the instruction schedule around them and cost the
+  // four-warpgroup kernel 8 % when they were unconditional (profiles/r02_notes.md section 6c).
+  constexpr bool kStamp = (V & 256) != 0;
 #define AT3_STAMP(role, code)                                          \
   do {                                                                 \
-    if (clk != nullptr && clk_n < 256) {                               \
-      clk[(role) * 512 + clk_n] = clock64();                           \
-      clk[(role) * 512 + 256 + clk_n] = (code);                        \
-      ++clk_n;                                                         \
+    if constexpr (kStamp) {                                            \
+      if (clk != nullptr && clk_n < 256) {                             \
+        clk[(role) * 512 + clk_n] = clock64();                         \
+        clk[(role) * 512 + 256 + clk_n] = (code);                      \
+        ++clk_n;                                                       \
+      }                                                                \
     }                                                                  \
   } while (0)
 

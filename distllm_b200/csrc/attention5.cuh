@@ -49,6 +49,7 @@ static_assert(At5Smem<false>::BAR == AT3_SMEM_BAR && At5Smem<false>::BYTES == AT
 //    bit 4 bidirectional sliding window.  (Same meaning as attention3_d64_kernel's.)
 //    bit 7 a fifth warpgroup (warps 19-22) takes the per-tile epilogue -- merge of the halves, normalisation,
 //    staging, store -- off the softmax warpgroups, which hand it (m, l) through shared memory and move on.
+//    bit 8 timeline stamps compiled in (profiling builds only).
 template <int V>
 __global__ void __launch_bounds__((V & 128) ? AT5_THREADS_EPI : AT5_THREADS, 1)
 attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16, box 64 x 128
@@ -123,12 +124,17 @@ attention5_d64_kernel(const __grid_constant__ CUtensorMap tm_q,   // [T, 3H] h16
   const uint32_t tmem_base = *tmem_slot;
   long long* const clk = (blockIdx.x == 0) ? g_att3_clock : nullptr;
   int clk_n = 0;
+  // timeline stamps exist only in the instantiations with V bit 8 (tools/att3_timeline.py): four predicated stamp
+  // sites per chunk were 2-3 % of the softmax warps' issue slots (ISETP / CS2R samples in r02_ncu_att5_source.md)
+  constexpr bool kStamp = (V & 256) != 0;
 #define AT5_STAMP(role, code)                                          \
   do {                                                                 \
-    if (clk != nullptr && clk_n < 256) {                               \
-      clk[(role) * 512 + clk_n] = clock64();                           \
-      clk[(role) * 512 + 256 + clk_n] = (code);                        \
-      ++clk_n;                                                         \
+    if constexpr (kStamp) {                                            \
+      if (clk != nullptr && clk_n < 256) {                             \
+        clk[(role) * 512 + clk_n] = clock64();                         \
+        clk[(role) * 512 + 256 + clk_n] = (code);                      \
+        ++clk_n;                                                       \
+      }                                                                \
     }                                                                  \
   } while (0)
 

@@ -440,9 +440,11 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnSc
     case 69: return launch_attention_v<69>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 73: return launch_attention_v<73>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
     case 193: return launch_attention_v<193>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
+    case 261: return launch_attention_v<261>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);   // 5 + timeline stamps
+    case 321: return launch_attention_v<321>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);   // 65 + timeline stamps
     case 197: return launch_attention_v<197>(tq, tkv, sc, tctx, ctx, lay, B, S, heads, grid, scale_log2e, st);
   }
-  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45,64,65,69,73,193,197)",
+  return fail(B2E_ERR_INVALID, "attention variant %d is not instantiated (0,1,2,3,5,7,11,33,37,41,45,64,65,69,73,193,197,261,321)",
               att3_variant());
 }
 

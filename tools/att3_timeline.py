@@ -1,4 +1,6 @@
-"""clock64 timeline of CTA 0 of the streaming attention kernel (b2e_debug_set_att3_clock)."""
+"""clock64 timeline of CTA 0 of the streaming attention kernel (b2e_debug_set_att3_clock).
+The four-warpgroup kernel carries its stamps only in the profiling instantiation: B2E_ATT3=321 (= 65 + bit 8);
+the two-warpgroup kernel (B2E_ATT3=5) always has them."""
 import ctypes, sys
 from pathlib import Path
 import torch
