@@ -45,7 +45,9 @@ struct Gemm2Cfg {
 __device__ long long* g_gemm2_clock = nullptr;   // CTAs 0/1: clock64() timelines, [cta*2 + role][256]
 __device__ int g_gemm2_flags = 0;                // 1 skip epilogue math+stores, 2 no MMAs, 4 no TMA loads
 
-template <int STAGES, int EPI>
+// TL: the profiling instantiation (clock64 timelines, experiment knobs); production kernels carry neither the
+// volatile clock reads nor the flag tests.
+template <int STAGES, int EPI, bool TL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box 64 x 128
                        const __grid_constant__ CUtensorMap tm_b,    // [N,K], box 64 x 128
@@ -69,7 +71,7 @@ gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int flags = g_gemm2_flags;   // experiment knobs, read once (0 in production)
+  const int flags = TL ? g_gemm2_flags : 0;   // experiment knobs, read once (compiled out of production kernels)
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
@@ -102,11 +104,13 @@ gemm2_h16_pair_kernel(const __grid_constant__ CUtensorMap tm_a,    // [M,K], box
   const int kblocks = K / GEMM_BK;
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
-  long long* const clk = (blockIdx.x < 2) ? g_gemm2_clock : nullptr;
+  long long* const clk = (TL && blockIdx.x < 2) ? g_gemm2_clock : nullptr;
   int clk_n = 0;
 #define G2_STAMP(role)                                                                       \
   do {                                                                                       \
-    if (clk != nullptr && clk_n < 256) clk[(blockIdx.x * 2 + (role)) * 256 + clk_n++] = clock64(); \
+    if constexpr (TL) {                                                                      \
+      if (clk != nullptr && clk_n < 256) clk[(blockIdx.x * 2 + (role)) * 256 + clk_n++] = clock64(); \
+    }                                                                                        \
   } while (0)
 
   if (warp == 0) {
