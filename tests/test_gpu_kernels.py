@@ -533,3 +533,54 @@ def test_attention_d64_sliding_window(dev, b, s, heads, window, h16, att_variant
     valid = mask.bool().view(-1)
     assert torch.isfinite(ctx.float()).all()
     close(ctx.float()[valid], ref[valid], h16, 2.0)
+
+
+# ------------------------------------------------------------------------- profiling instantiations
+def test_profiling_instantiations_write_timelines_and_change_no_result(dev):
+    """The clock64 timelines live in separate instantiations (attention: variant bit 8; pair GEMM: selected while a
+    clock buffer is set): they must fill their buffers and give the production kernels' results bit for bit."""
+    import ctypes
+
+    lib = nv.load('bf16')
+    lib.b2e_debug_set_att3_variant.argtypes = [ctypes.c_int]
+    lib.b2e_debug_set_att3_clock.argtypes = [ctypes.c_void_p]
+    lib.b2e_debug_set_clock_buffer.argtypes = [ctypes.c_void_p]
+    g = torch.Generator(device=dev).manual_seed(11)
+    b, s, heads = 6, 512, 4
+    qkv = torch.randn(b * s, 3 * heads * 64, device=dev, generator=g).to(torch.bfloat16)
+    mask = torch.ones(b, s, dtype=torch.int64, device=dev)
+    try:
+        for plain, timed in ((65, 321), (5, 261)):
+            lib.b2e_debug_set_att3_variant(plain)
+            want = nv.attention_d64(qkv, mask, b, s, heads).clone()
+            buf = torch.zeros(4 * 512, dtype=torch.int64, device=dev)
+            assert lib.b2e_debug_set_att3_clock(buf.data_ptr()) == 0
+            nv.attention_d64(qkv, mask, b, s, heads)          # production kernel: no stamps even with a buffer set
+            torch.cuda.synchronize()
+            assert int((buf != 0).sum()) == 0
+            lib.b2e_debug_set_att3_variant(timed)
+            got = nv.attention_d64(qkv, mask, b, s, heads).clone()
+            torch.cuda.synchronize()
+            assert lib.b2e_debug_set_att3_clock(None) == 0
+            assert torch.equal(got, want)
+            assert int((buf.view(4, 2, 256)[0, 0] != 0).sum()) > 8   # the first softmax role recorded its chunks
+    finally:
+        lib.b2e_debug_set_att3_clock(None)
+        lib.b2e_debug_set_att3_variant(-1)
+    # pair GEMM
+    a = (torch.randn(4096, 768, device=dev, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(768, 768, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(768, device=dev, generator=g)
+    want = nv.gemm_h16(a, w, bias).clone()
+    buf = torch.zeros(4 * 256, dtype=torch.int64, device=dev)
+    try:
+        assert lib.b2e_debug_set_clock_buffer(buf.data_ptr()) == 0
+        got = nv.gemm_h16(a, w, bias).clone()
+        torch.cuda.synchronize()
+    finally:
+        assert lib.b2e_debug_set_clock_buffer(None) == 0
+    assert torch.equal(got, want) and int((buf != 0).sum()) > 8
+    buf.zero_()
+    nv.gemm_h16(a, w, bias)
+    torch.cuda.synchronize()
+    assert int((buf != 0).sum()) == 0
