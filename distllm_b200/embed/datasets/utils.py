@@ -54,13 +54,20 @@ class SentenceTokenCache:
     sample of rows is checked against the tokenizer itself when the cache is built.
     """
 
-    def __init__(self, sentence_ids: list[np.ndarray], ends_ws: np.ndarray, starts_ws: np.ndarray,
-                 prefix: list[int], suffix: list[int]) -> None:
-        self.sentence_ids = sentence_ids
-        self.ends_ws = ends_ws
-        self.starts_ws = starts_ws
+    LOOKAHEAD = 2048   # sentences tokenised per call once one of them is needed
+
+    def __init__(self, tokenizer: PreTrainedTokenizer, sentences: list[str], prefix: list[int], suffix: list[int],
+                 limit: int) -> None:
+        self.tokenizer = tokenizer
+        self.sentences = sentences
+        # filled on demand, LOOKAHEAD sentences at a time, by whichever thread / worker process collates: batches
+        # walk a file front to back, so tokenisation runs under the encoder instead of in front of the first batch
+        self.sentence_ids: list[np.ndarray | None] = [None] * len(sentences)
+        self.ends_ws = np.fromiter((s[-1:].isspace() for s in sentences), dtype=bool, count=len(sentences))
+        self.starts_ws = np.fromiter((s[:1].isspace() for s in sentences), dtype=bool, count=len(sentences))
         self.prefix = np.asarray(prefix, dtype=np.int64)
         self.suffix = np.asarray(suffix, dtype=np.int64)
+        self.limit = limit
 
     @staticmethod
     def supported(tokenizer: PreTrainedTokenizer) -> bool:
@@ -91,24 +98,38 @@ class SentenceTokenCache:
             return None
         at = ids.index(bare[0])
         prefix, suffix = ids[:at], ids[at + 1:]
+        limit = max(int(min(tokenizer.model_max_length, 1 << 20)) - len(prefix) - len(suffix), 0)
+        return cls(tokenizer, sentences, prefix, suffix, limit)
+
+    def _tokenise(self, lo: int, hi: int) -> None:
+        """Fill sentence_ids[lo:hi] (those still missing) with one backend call, truncation and padding off."""
+        todo = [i for i in range(lo, hi) if self.sentence_ids[i] is None]
+        if not todo:
+            return
+        backend = self.tokenizer._tokenizer
         saved = (backend.truncation, backend.padding)
         backend.no_truncation()
         backend.no_padding()
         try:
             encode = getattr(backend, 'encode_batch_fast', backend.encode_batch)
-            encodings = encode(list(sentences), add_special_tokens=False)
+            encodings = encode([self.sentences[i] for i in todo], add_special_tokens=False)
         finally:
             if saved[0] is not None:
                 backend.enable_truncation(**saved[0])
             if saved[1] is not None:
                 backend.enable_padding(**saved[1])
-        limit = max(int(min(tokenizer.model_max_length, 1 << 20)) - len(prefix) - len(suffix), 0)
-        sentence_ids = [np.asarray(e.ids[:limit], dtype=np.int64) for e in encodings]
-        ends_ws = np.fromiter((s[-1:].isspace() for s in sentences), dtype=bool, count=len(sentences))
-        starts_ws = np.fromiter((s[:1].isspace() for s in sentences), dtype=bool, count=len(sentences))
-        return cls(sentence_ids, ends_ws, starts_ws, prefix, suffix)
+        for i, e in zip(todo, encodings):
+            # a sentence alone can fill a row: ids beyond the row limit are never used
+            self.sentence_ids[i] = np.asarray(e.ids[: self.limit], dtype=np.int64)
 
-    def row_ids(self, parts: tuple[int, ...], max_length: int) -> np.ndarray | None:
+    def ensure(self, parts: tuple[int, ...], lookahead: bool = True) -> None:
+        if any(self.sentence_ids[i] is None for i in parts):
+            lo, hi = min(parts), max(parts) + 1
+            if lookahead:
+                hi = min(len(self.sentences), max(hi, lo + self.LOOKAHEAD))
+            self._tokenise(lo, hi)
+
+    def row_ids(self, parts: tuple[int, ...], max_length: int, lookahead: bool = True) -> np.ndarray | None:
         """``[prefix] + concatenated sentence ids[:max_length - specials] + [suffix]``; None when a joint between
         two of the sentences does not fall on whitespace (or there is nothing to join)."""
         if not parts:
@@ -116,6 +137,7 @@ class SentenceTokenCache:
         for a, b in zip(parts, parts[1:]):
             if not (self.ends_ws[a] or self.starts_ws[b]):
                 return None
+        self.ensure(parts, lookahead)
         room = max_length - len(self.prefix) - len(self.suffix)
         out, used = [self.prefix], 0
         for i in parts:
@@ -131,7 +153,7 @@ class SentenceTokenCache:
         """The cache reproduces ``tokenizer(text, truncation=True)`` on these rows (checked when it is attached)."""
         max_length = int(min(tokenizer.model_max_length, 1 << 20))
         for text in texts:
-            mine = self.row_ids(text.parts, max_length)
+            mine = self.row_ids(text.parts, max_length, lookahead=False)
             if mine is None:
                 continue
             theirs = tokenizer(str(text), truncation=True, max_length=max_length)['input_ids']
